@@ -1,0 +1,150 @@
+/* ultra_rspmm.h - C ABI of the B200-native relational SpMM ("rspmm") hot path.
+ *
+ * This is the drop-in boundary underneath
+ *     torchdrug.layers.functional.generalized_rspmm(sparse, relation, input, sum=, mul=)
+ * as called by the reference at ultra/layer.py:134-167 (GeneralizedRelationalConvNBF) and
+ * ultra/layer.py:336-369 (GeneralizedRelationalConvNBFMod).  In the reference that Python entry
+ * dispatches to torchdrug's pybind functions rspmm_{add,min,max}_{mul,add}_{forward,backward}_{cpu,cuda}
+ * (torchdrug/layers/functional/extension/rspmm.{h,cpp,cu}; un-vendored).
+ * The entry points below are what a binding for this path binds instead: plain pointers and sizes,
+ * no torch types, one CUDA stream argument, integer status codes.
+ *
+ * Conventions
+ *   - all `dev_*` / device pointers are CUDA device memory on the current device; nothing here
+ *     allocates or frees device memory except the ultra_rspmm_ctx_* convenience layer (host-buffer API);
+ *   - kernels are enqueued on `stream` and return without synchronising, except where stated;
+ *   - dense operands are row-major, contiguous: relation (n_rel, dim), input (n_in, dim),
+ *     output / grad_output (n_out, dim); feature index = batch * d + channel (reference layer.py:118,306);
+ *   - the sparse operand is COO (n_out, n_in, n_rel): row = node_out (destination), col = node_in (source),
+ *     layer = relation (reference layer.py:127,328 `graph.adjacency.transpose(0, 1)`); it need not be
+ *     coalesced - ultra_rspmm_index_build sorts by (row, col, layer) and merges duplicates by summing
+ *     their values, exactly what `sparse.coalesce()` does before torchdrug's coo2csr3d;
+ *   - empty rows produce the reduction identity: 0 (add), -FLT_MAX / -DBL_MAX (max), +FLT_MAX / +DBL_MAX (min);
+ *   - arg-index = position (in coalesced order) of the first edge attaining the extremum, -1 for empty rows;
+ *   - max/min backward follows the reference's all-ties rule (gate `output == message`).
+ */
+#ifndef ULTRA_RSPMM_H_
+#define ULTRA_RSPMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ULTRA_RSPMM_ABI_VERSION 1
+
+/* status codes (0 = ok).  For ULTRA_RSPMM_ERR_CUDA the cudaError_t is kept per thread, see
+ * ultra_rspmm_last_cuda_error(). */
+enum {
+    ULTRA_RSPMM_OK = 0,
+    ULTRA_RSPMM_ERR_ARG = 1,        /* null pointer, negative size, unknown op / dtype code            */
+    ULTRA_RSPMM_ERR_WORKSPACE = 2,  /* caller-provided buffer smaller than the *_bytes query answered   */
+    ULTRA_RSPMM_ERR_CUDA = 3,       /* a CUDA runtime call failed                                       */
+    ULTRA_RSPMM_ERR_INDEX = 4,      /* a COO index is outside (n_out, n_in, n_rel)                      */
+    ULTRA_RSPMM_ERR_DTYPE = 5       /* operand dtype does not match the dtype the index was built for   */
+};
+
+/* op codes: torchdrug's NaryOp {add,min,max} x BinaryOp {mul,add} (reference layer.py:18-21 message2mul) */
+enum { ULTRA_RSPMM_SUM_ADD = 0, ULTRA_RSPMM_SUM_MIN = 1, ULTRA_RSPMM_SUM_MAX = 2 };
+enum { ULTRA_RSPMM_MUL_MUL = 0, ULTRA_RSPMM_MUL_ADD = 1 };
+enum { ULTRA_RSPMM_F32 = 0, ULTRA_RSPMM_F64 = 1 };
+
+/* Graph index: int32 device arrays describing the coalesced operand in the three edge orders the
+ * kernels walk.  A POD the caller keeps on the host; every pointer points into the caller's
+ * `index_buffer` (see ultra_rspmm_index_build).  Replaces coo2csr3d + the per-call
+ * `sparse.transpose(0,1).coalesce()` of the reference. */
+typedef struct ultra_rspmm_index {
+    int64_t nnz;          /* coalesced edge count M                                                     */
+    int64_t nnz_raw;      /* edge count before merging duplicates                                       */
+    int32_t n_out, n_in, n_rel;
+    int32_t dtype;        /* ULTRA_RSPMM_F32 / F64: element type of the three *_w arrays                 */
+    int32_t unit_weight;  /* 1 if every merged value == 1 (the multiply and the w stream are skipped)   */
+    int32_t max_row_nnz, max_col_nnz, max_rel_nnz;
+    /* destination-sorted CSR (forward): edges of row i are [csr_ptr[i], csr_ptr[i+1])                    */
+    const int32_t *csr_ptr;   /* n_out + 1                                                              */
+    const int32_t *csr_edge;  /* M x {src, rel} (int2)                                                  */
+    const void *csr_w;        /* M                                                                      */
+    /* source-sorted CSC (backward w.r.t. input): edges leaving node j, sorted by (src, dst, rel)        */
+    const int32_t *csc_ptr;   /* n_in + 1                                                               */
+    const int32_t *csc_edge;  /* M x {dst, rel}                                                         */
+    const void *csc_w;
+    const int32_t *csc_eid;   /* M: position of the edge in CSR (coalesced) order                        */
+    /* relation-sorted (backward w.r.t. relation): stable by coalesced position inside a relation        */
+    const int32_t *rel_ptr;   /* n_rel + 1                                                              */
+    const int32_t *rel_edge;  /* M x {dst, src}                                                         */
+    const void *rel_w;
+    const int32_t *rel_eid;   /* M                                                                      */
+    /* rows / sources ordered by descending edge count (longest-first scheduling of the row passes)      */
+    const int32_t *row_order; /* n_out                                                                  */
+    const int32_t *col_order; /* n_in                                                                   */
+} ultra_rspmm_index_t;
+
+/* ---- version / diagnostics ------------------------------------------------------------------- */
+int ultra_rspmm_abi_version(void);
+int ultra_rspmm_last_cuda_error(void);          /* cudaError_t of the last failure on this thread */
+const char *ultra_rspmm_status_string(int status);
+/* number of kernels this library has enqueued since load / last reset (process-wide counter) */
+int64_t ultra_rspmm_launch_count(void);
+void ultra_rspmm_launch_count_reset(void);
+
+/* ---- index build (replaces sparse.coalesce() + coo2csr3d) ---------- */
+/* Bytes needed for the index arrays (upper bound, from the raw edge count) and for scratch. */
+int ultra_rspmm_index_bytes(int64_t nnz_raw, int32_t n_out, int32_t n_in, int32_t n_rel, int32_t dtype,
+                            size_t *index_bytes, size_t *scratch_bytes);
+/* dev_indices: int64 (3, nnz_raw) row-major = rows [node_out; node_in; relation] with row stride
+ * `index_stride` elements (torch `sparse._indices()` of the transposed adjacency; stride = nnz_raw when
+ * contiguous).  dev_values: nnz_raw values of `dtype`.  Fills *index (host POD).  Synchronises `stream`
+ * once (the merged edge count must reach the host). */
+int ultra_rspmm_index_build(const int64_t *dev_indices, int64_t index_stride, const void *dev_values,
+                            int64_t nnz_raw, int32_t n_out, int32_t n_in, int32_t n_rel, int32_t dtype,
+                            void *index_buffer, size_t index_bytes, void *scratch, size_t scratch_bytes,
+                            ultra_rspmm_index_t *index, void *stream);
+/* 128-bit content fingerprint of (indices, values) written to dev_out[2] (uint64); lets a caller
+ * recognise an edge set it already indexed without a sort.  Asynchronous. */
+int ultra_rspmm_fingerprint(const int64_t *dev_indices, int64_t index_stride, const void *dev_values,
+                            int64_t nnz_raw, int32_t dtype, uint64_t *dev_out, void *stream);
+
+/* ---- forward: rspmm_{sum}_{mul}_forward_cuda -------------------------------------------------- */
+/* workspace bytes for forward / backward at feature width `dim` (may be 0) */
+int ultra_rspmm_workspace_bytes(const ultra_rspmm_index_t *index, int64_t dim, int32_t dtype,
+                                size_t *forward_bytes, size_t *backward_bytes);
+/* output[i,:] = (sum)_{(i,j,k)} w * (relation[k,:] (mul) input[j,:]);  dev_argidx (n_out, dim) int32 may be
+ * NULL (only meaningful for min/max). */
+int ultra_rspmm_forward(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
+                        void *dev_output, int32_t *dev_argidx, int64_t dim, int32_t dtype, int32_t sum_op,
+                        int32_t mul_op, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- backward: rspmm_{sum}_{mul}_backward_cuda (overload without value_grad) ------------------- */
+/* dev_output is read only for min/max (may be NULL for add).  Either gradient pointer may be NULL to
+ * skip that pass.  Results are written (not accumulated). */
+int ultra_rspmm_backward(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
+                         const void *dev_output, const void *dev_grad_output, void *dev_grad_relation,
+                         void *dev_grad_input, int64_t dim, int32_t dtype, int32_t sum_op, int32_t mul_op,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- host-buffer convenience layer (what a non-torch host binds; used for end-to-end timing) --- */
+/* Owns device copies of one graph's index and of the dense operands; every call below takes HOST
+ * pointers, copies host->device, runs the kernels and copies the results back, synchronising before
+ * it returns.  Pinned host memory makes the copies asynchronous DMA; pageable memory also works. */
+typedef struct ultra_rspmm_ctx ultra_rspmm_ctx_t;
+int ultra_rspmm_ctx_create(ultra_rspmm_ctx_t **ctx, int32_t device);
+int ultra_rspmm_ctx_destroy(ultra_rspmm_ctx_t *ctx);
+/* host_indices: int64 (3, nnz_raw) contiguous; host_values: nnz_raw of dtype */
+int ultra_rspmm_ctx_set_graph(ultra_rspmm_ctx_t *ctx, const int64_t *host_indices, const void *host_values,
+                              int64_t nnz_raw, int32_t n_out, int32_t n_in, int32_t n_rel, int32_t dtype);
+int ultra_rspmm_ctx_forward(ultra_rspmm_ctx_t *ctx, const void *host_relation, const void *host_input,
+                            void *host_output, int64_t dim, int32_t sum_op, int32_t mul_op);
+/* forward + backward in one call: uploads relation, input, grad_output; downloads output,
+ * grad_relation, grad_input */
+int ultra_rspmm_ctx_forward_backward(ultra_rspmm_ctx_t *ctx, const void *host_relation, const void *host_input,
+                                     const void *host_grad_output, void *host_output, void *host_grad_relation,
+                                     void *host_grad_input, int64_t dim, int32_t sum_op, int32_t mul_op);
+/* device time (ms, CUDA events on the context's stream) of the kernels of the last ctx_* call */
+float ultra_rspmm_ctx_last_kernel_ms(const ultra_rspmm_ctx_t *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ULTRA_RSPMM_H_ */

@@ -1,0 +1,112 @@
+// Shared device helpers for the rspmm kernels (sm_100a).
+//
+// Data layout in HBM (DESIGN.md "Data layout"): dense operands are row-major (rows, dim) with the
+// query batch folded into the feature axis (feature = batch * 64 + channel, reference layer.py:118,306);
+// a "slab" is a contiguous run of SLAB = LPE * VEC features of every row.  Kernels walk slabs in
+// slab-major block order so that the co-resident CTAs share one N x SLAB column block of the gathered
+// operand (L2-resident) and one R' x SLAB column block of the relation table (L1/L2-resident).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "ultra_rspmm.h"
+
+namespace ultra {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreadsPerBlock = kWarpsPerBlock * 32;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+enum MsgKind { MSG_MUL = 0, MSG_ADD = 1, MSG_COPY = 2 };  // rel*x, rel+x, x (relation not read)
+
+template <typename T> struct Limits;
+template <> struct Limits<float> {
+    static __host__ __device__ constexpr float lowest() { return -FLT_MAX; }
+    static __host__ __device__ constexpr float highest() { return FLT_MAX; }
+};
+template <> struct Limits<double> {
+    static __host__ __device__ constexpr double lowest() { return -DBL_MAX; }
+    static __host__ __device__ constexpr double highest() { return DBL_MAX; }
+};
+
+template <typename T, int SUM> __device__ __forceinline__ T reduce_identity() {
+    return SUM == ULTRA_RSPMM_SUM_ADD ? T(0)
+                                      : (SUM == ULTRA_RSPMM_SUM_MAX ? Limits<T>::lowest() : Limits<T>::highest());
+}
+
+// ---------------------------------------------------------------------------------------------
+// 128-bit (or scalar) global loads with explicit cache policy.
+//   gather_*: rows of the big gathered operand (input / grad_output / output): read-only path,
+//             no L1 allocation - they are reused through L2 (slab-major order), not through L1;
+//   table_* : rows of the small relation table: read-only path WITH L1 allocation, so the
+//             R' x SLAB block that the CTAs of one SM share stays on chip.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VEC> struct Vec { T v[VEC]; };
+
+__device__ __forceinline__ void gather_load(const float *p, Vec<float, 4> &out) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(out.v[0]), "=f"(out.v[1]), "=f"(out.v[2]), "=f"(out.v[3]) : "l"(p));
+}
+__device__ __forceinline__ void gather_load(const float *p, Vec<float, 1> &out) {
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(out.v[0]) : "l"(p));
+}
+__device__ __forceinline__ void gather_load(const double *p, Vec<double, 2> &out) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(out.v[0]), "=d"(out.v[1]) : "l"(p));
+}
+__device__ __forceinline__ void gather_load(const double *p, Vec<double, 1> &out) {
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(out.v[0]) : "l"(p));
+}
+
+__device__ __forceinline__ void table_load(const float *p, Vec<float, 4> &out) {
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    out.v[0] = t.x; out.v[1] = t.y; out.v[2] = t.z; out.v[3] = t.w;
+}
+__device__ __forceinline__ void table_load(const float *p, Vec<float, 1> &out) { out.v[0] = __ldg(p); }
+__device__ __forceinline__ void table_load(const double *p, Vec<double, 2> &out) {
+    const double2 t = __ldg(reinterpret_cast<const double2 *>(p));
+    out.v[0] = t.x; out.v[1] = t.y;
+}
+__device__ __forceinline__ void table_load(const double *p, Vec<double, 1> &out) { out.v[0] = __ldg(p); }
+
+// streaming (evict-first) stores for results that are written once and not re-read by this kernel
+__device__ __forceinline__ void stream_store(float *p, const Vec<float, 4> &v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.v[0]), "f"(v.v[1]), "f"(v.v[2]), "f"(v.v[3]) : "memory");
+}
+__device__ __forceinline__ void stream_store(float *p, const Vec<float, 1> &v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v.v[0]) : "memory");
+}
+__device__ __forceinline__ void stream_store(double *p, const Vec<double, 2> &v) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.v[0]), "d"(v.v[1]) : "memory");
+}
+__device__ __forceinline__ void stream_store(double *p, const Vec<double, 1> &v) {
+    asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v.v[0]) : "memory");
+}
+__device__ __forceinline__ void stream_store(int32_t *p, const Vec<int32_t, 4> &v) {
+    asm volatile("st.global.cs.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.v[0]), "r"(v.v[1]), "r"(v.v[2]), "r"(v.v[3]) : "memory");
+}
+__device__ __forceinline__ void stream_store(int32_t *p, const Vec<int32_t, 2> &v) {
+    asm volatile("st.global.cs.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(v.v[0]), "r"(v.v[1]) : "memory");
+}
+__device__ __forceinline__ void stream_store(int32_t *p, const Vec<int32_t, 1> &v) {
+    asm volatile("st.global.cs.s32 [%0], %1;" ::"l"(p), "r"(v.v[0]) : "memory");
+}
+
+__device__ __forceinline__ double shfl_value(double v, int src) { return __shfl_sync(kFullMask, v, src); }
+__device__ __forceinline__ float shfl_value(float v, int src) { return __shfl_sync(kFullMask, v, src); }
+__device__ __forceinline__ double shfl_xor_value(double v, int m) { return __shfl_xor_sync(kFullMask, v, m); }
+__device__ __forceinline__ float shfl_xor_value(float v, int m) { return __shfl_xor_sync(kFullMask, v, m); }
+
+// message = w * (rel (x) x) with the rounding sequence of the reference (two roundings, no contraction
+// into the following add for min/max, where the value itself is the result).
+template <typename T, int MSG> __device__ __forceinline__ T message(T w, T r, T x) {
+    if (MSG == MSG_MUL) return w * (r * x);
+    if (MSG == MSG_ADD) return w * (r + x);
+    return w * x;
+}
+
+// launch bookkeeping (claimed in bench.py as `gpu_launches`)
+void note_launch();
+
+}  // namespace ultra
