@@ -10,9 +10,10 @@
  * no torch types, one CUDA stream argument, integer status codes.
  *
  * Conventions
- *   - all `dev_*` / device pointers are CUDA device memory on the current device; nothing here
- *     allocates or frees device memory except the ultra_rspmm_ctx_* convenience layer (host-buffer API);
- *   - kernels are enqueued on `stream` and return without synchronising, except where stated;
+ *   - all `dev_*` pointers are CUDA device memory on the current device; nothing here allocates or
+ *     frees device memory except the ultra_rspmm_ctx_* convenience layer (host-buffer API);
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*) and return without
+ *     synchronising, except where stated;
  *   - dense operands are row-major, contiguous: relation (n_rel, dim), input (n_in, dim),
  *     output / grad_output (n_out, dim); feature index = batch * d + channel (reference layer.py:118,306);
  *   - the sparse operand is COO (n_out, n_in, n_rel): row = node_out (destination), col = node_in (source),
@@ -33,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ULTRA_RSPMM_ABI_VERSION 1
+#define ULTRA_RSPMM_ABI_VERSION 2
 
 /* status codes (0 = ok).  For ULTRA_RSPMM_ERR_CUDA the cudaError_t is kept per thread, see
  * ultra_rspmm_last_cuda_error(). */
@@ -43,13 +44,34 @@ enum {
     ULTRA_RSPMM_ERR_WORKSPACE = 2,  /* caller-provided buffer smaller than the *_bytes query answered   */
     ULTRA_RSPMM_ERR_CUDA = 3,       /* a CUDA runtime call failed                                       */
     ULTRA_RSPMM_ERR_INDEX = 4,      /* a COO index is outside (n_out, n_in, n_rel)                      */
-    ULTRA_RSPMM_ERR_DTYPE = 5       /* operand dtype does not match the dtype the index was built for   */
+    ULTRA_RSPMM_ERR_DTYPE = 5,      /* operand dtype does not match the dtype the index was built for   */
+    ULTRA_RSPMM_ERR_RANGE = 6       /* n_out * n_in * n_rel does not fit the 63-bit sort key / int32 ids */
 };
 
 /* op codes: torchdrug's NaryOp {add,min,max} x BinaryOp {mul,add} (reference layer.py:18-21 message2mul) */
 enum { ULTRA_RSPMM_SUM_ADD = 0, ULTRA_RSPMM_SUM_MIN = 1, ULTRA_RSPMM_SUM_MAX = 2 };
 enum { ULTRA_RSPMM_MUL_MUL = 0, ULTRA_RSPMM_MUL_ADD = 1 };
 enum { ULTRA_RSPMM_F32 = 0, ULTRA_RSPMM_F64 = 1 };
+
+/* One ordering of the coalesced edges, cut into segments (the rows a pass reduces into) and into
+ * tasks (at most `chunk` consecutive edges of one segment; one warp per task and feature slab).
+ * A segment with more than one task is "split": its tasks write partial rows (slots) that a
+ * fixed-order combine pass folds into the result row, so results do not depend on scheduling. */
+typedef struct ultra_rspmm_order {
+    int32_t n_seg;        /* rows of the result this order reduces into                                 */
+    int32_t n_task;       /* >= n_seg (an empty segment still has one task: it writes the identity)     */
+    int32_t n_slot;       /* partial rows needed by the split segments                                  */
+    int32_t n_split;      /* number of split segments                                                   */
+    int32_t max_seg_nnz;  /* longest segment                                                            */
+    int32_t reserved;
+    const int32_t *ptr;   /* n_seg + 1: edges of segment s are [ptr[s], ptr[s+1])                        */
+    const int32_t *edge;  /* M x int2: the two row ids each edge gathers from (see ultra_rspmm_index_t)  */
+    const void *w;        /* M merged values, element type = index dtype                                */
+    const int32_t *eid;   /* M: position of the edge in coalesced (CSR) order; NULL for the CSR itself   */
+    const int32_t *task;  /* n_task x int4 {seg, begin, end, slot}; slot = -1: writes the result row.
+                             Sorted by descending edge count (longest first).                           */
+    const int32_t *split; /* n_split x int4 {seg, first_slot, n_slots, 0}                                */
+} ultra_rspmm_order_t;
 
 /* Graph index: int32 device arrays describing the coalesced operand in the three edge orders the
  * kernels walk.  A POD the caller keeps on the host; every pointer points into the caller's
@@ -59,26 +81,12 @@ typedef struct ultra_rspmm_index {
     int64_t nnz;          /* coalesced edge count M                                                     */
     int64_t nnz_raw;      /* edge count before merging duplicates                                       */
     int32_t n_out, n_in, n_rel;
-    int32_t dtype;        /* ULTRA_RSPMM_F32 / F64: element type of the three *_w arrays                 */
-    int32_t unit_weight;  /* 1 if every merged value == 1 (the multiply and the w stream are skipped)   */
-    int32_t max_row_nnz, max_col_nnz, max_rel_nnz;
-    /* destination-sorted CSR (forward): edges of row i are [csr_ptr[i], csr_ptr[i+1])                    */
-    const int32_t *csr_ptr;   /* n_out + 1                                                              */
-    const int32_t *csr_edge;  /* M x {src, rel} (int2)                                                  */
-    const void *csr_w;        /* M                                                                      */
-    /* source-sorted CSC (backward w.r.t. input): edges leaving node j, sorted by (src, dst, rel)        */
-    const int32_t *csc_ptr;   /* n_in + 1                                                               */
-    const int32_t *csc_edge;  /* M x {dst, rel}                                                         */
-    const void *csc_w;
-    const int32_t *csc_eid;   /* M: position of the edge in CSR (coalesced) order                        */
-    /* relation-sorted (backward w.r.t. relation): stable by coalesced position inside a relation        */
-    const int32_t *rel_ptr;   /* n_rel + 1                                                              */
-    const int32_t *rel_edge;  /* M x {dst, src}                                                         */
-    const void *rel_w;
-    const int32_t *rel_eid;   /* M                                                                      */
-    /* rows / sources ordered by descending edge count (longest-first scheduling of the row passes)      */
-    const int32_t *row_order; /* n_out                                                                  */
-    const int32_t *col_order; /* n_in                                                                   */
+    int32_t dtype;        /* ULTRA_RSPMM_F32 / F64: element type of the w arrays                          */
+    int32_t unit_weight;  /* 1 if every merged value == 1 (the w stream is not read)                    */
+    int32_t chunk;        /* maximum edges per task                                                     */
+    ultra_rspmm_order_t csr;  /* forward: segments = destination rows, sorted (dst, src, rel); edge = {src, rel} */
+    ultra_rspmm_order_t csc;  /* backward w.r.t. input: segments = source rows, sorted (src, dst, rel); edge = {dst, rel} */
+    ultra_rspmm_order_t rel;  /* backward w.r.t. relation: segments = relations, stable by coalesced position; edge = {dst, src} */
 } ultra_rspmm_index_t;
 
 /* ---- version / diagnostics ------------------------------------------------------------------- */
@@ -88,21 +96,27 @@ const char *ultra_rspmm_status_string(int status);
 /* number of kernels this library has enqueued since load / last reset (process-wide counter) */
 int64_t ultra_rspmm_launch_count(void);
 void ultra_rspmm_launch_count_reset(void);
+/* tuning knobs (process-wide; 0 keeps the current value).  chunk: edges per task for indexes built
+ * afterwards (default 256).  variant: 0 = automatic kernel choice, 1 = force the generic L2-gather
+ * kernel, 2 = force the shared-memory-staged relation-table kernel where it is legal. */
+int ultra_rspmm_set_tuning(int32_t chunk, int32_t variant);
 
 /* ---- index build (replaces sparse.coalesce() + coo2csr3d) ---------- */
 /* Bytes needed for the index arrays (upper bound, from the raw edge count) and for scratch. */
 int ultra_rspmm_index_bytes(int64_t nnz_raw, int32_t n_out, int32_t n_in, int32_t n_rel, int32_t dtype,
                             size_t *index_bytes, size_t *scratch_bytes);
-/* dev_indices: int64 (3, nnz_raw) row-major = rows [node_out; node_in; relation] with row stride
- * `index_stride` elements (torch `sparse._indices()` of the transposed adjacency; stride = nnz_raw when
- * contiguous).  dev_values: nnz_raw values of `dtype`.  Fills *index (host POD).  Synchronises `stream`
- * once (the merged edge count must reach the host). */
+/* dev_indices: int64 (3, nnz_raw) = rows [node_out; node_in; relation], row r starting at
+ * dev_indices + r * index_stride (torch `sparse._indices()` of the transposed adjacency; stride =
+ * nnz_raw when contiguous).  dev_values: nnz_raw values of `dtype`.  Both buffers must be 256-byte
+ * aligned (cudaMalloc / torch allocations are).  Fills *index (host POD).  Synchronises `stream`
+ * (the merged edge and task counts must reach the host). */
 int ultra_rspmm_index_build(const int64_t *dev_indices, int64_t index_stride, const void *dev_values,
                             int64_t nnz_raw, int32_t n_out, int32_t n_in, int32_t n_rel, int32_t dtype,
                             void *index_buffer, size_t index_bytes, void *scratch, size_t scratch_bytes,
                             ultra_rspmm_index_t *index, void *stream);
 /* 128-bit content fingerprint of (indices, values) written to dev_out[2] (uint64); lets a caller
- * recognise an edge set it already indexed without a sort.  Asynchronous. */
+ * recognise an edge set it already indexed without a sort.  dev_out must be zero on entry is NOT
+ * required (the call clears it).  Asynchronous. */
 int ultra_rspmm_fingerprint(const int64_t *dev_indices, int64_t index_stride, const void *dev_values,
                             int64_t nnz_raw, int32_t dtype, uint64_t *dev_out, void *stream);
 
@@ -143,6 +157,11 @@ int ultra_rspmm_ctx_forward_backward(ultra_rspmm_ctx_t *ctx, const void *host_re
                                      void *host_grad_input, int64_t dim, int32_t sum_op, int32_t mul_op);
 /* device time (ms, CUDA events on the context's stream) of the kernels of the last ctx_* call */
 float ultra_rspmm_ctx_last_kernel_ms(const ultra_rspmm_ctx_t *ctx);
+/* coalesced edge count of the context's graph (-1 before set_graph) */
+int64_t ultra_rspmm_ctx_nnz(const ultra_rspmm_ctx_t *ctx);
+/* pinned host memory helpers for callers without a CUDA runtime binding of their own */
+int ultra_rspmm_host_alloc(void **ptr, size_t bytes);
+int ultra_rspmm_host_free(void *ptr);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,278 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Needs a B200: `-m gpu`.
+
+Bar (BASELINE.json north_star): min/max values and arg-indices bit-exact; fp32 sums and gradients within
+rtol 1e-5 / atol 1e-6 of the oracle.  Sums are compared against the oracle evaluated in float64 (the
+"true" value) because the kernel's summation order legitimately differs from any sequential order; the
+absolute tolerance is scaled by the row's sum of |terms| as usual for floating-point sums.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _assert_sum_close(actual, expected64, scale64, what):
+    """|actual - expected| <= atol + rtol * sum_of_abs_terms  (per element)."""
+    err = np.abs(actual.astype(np.float64) - expected64)
+    bound = ATOL + RTOL * scale64
+    worst = np.unravel_index(np.argmax(err - bound), err.shape) if err.size else None
+    assert (err <= bound).all(), "%s: error %g > bound %g at %s" % (what, err[worst], bound[worst], worst)
+
+
+def _run_case(cuda, n_out, n_in, n_rel, nnz, dim, sum, mul, seed=0, duplicates=0, weights="unit", skew=False,
+              ties=False, dtype=np.float32, check_backward=True):
+    from ultra_torchdrug_b200 import functional as F
+    indices, values = util.random_coo(n_out, n_in, n_rel, nnz, seed, duplicates, weights, skew, dtype)
+    shape = (n_out, n_in, n_rel)
+    relation = util.random_dense(n_rel, dim, seed + 1, dtype, ties)
+    input = util.random_dense(n_in, dim, seed + 2, dtype, ties)
+    grad_output = util.random_dense(n_out, dim, seed + 3, dtype)
+
+    index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), shape)
+    d_rel, d_in = torch.from_numpy(relation).to(cuda), torch.from_numpy(input).to(cuda)
+    out, arg = index.forward(d_rel, d_in, sum, mul, return_argidx=True)
+    out_np = out.cpu().numpy()
+
+    exp, exp_arg = util.oracle_forward(indices, values, shape, relation, input, sum, mul)
+    if sum == "add":
+        exp64, _ = util.oracle_forward(indices, values, shape, relation, input, sum, mul, dtype=np.float64)
+        scale, _ = util.oracle_forward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), sum, mul,
+                                       dtype=np.float64)
+        _assert_sum_close(out_np, exp64, scale, "forward %s/%s" % (sum, mul))
+    else:
+        assert np.array_equal(out_np, exp), "forward %s/%s values not bit-exact" % (sum, mul)
+        assert np.array_equal(arg.cpu().numpy().astype(np.int64), exp_arg), "arg-index mismatch"
+    if not check_backward:
+        return
+    g_rel, g_in = index.backward(d_rel, d_in, out, torch.from_numpy(grad_output).to(cuda), sum, mul)
+    e_rel, e_in = util.oracle_backward(indices, values, shape, relation, input, out_np, grad_output, sum, mul,
+                                       dtype=np.float64)
+    s_rel, s_in = util.oracle_backward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), out_np,
+                                       np.abs(grad_output), "add", mul, dtype=np.float64)
+    _assert_sum_close(g_rel.cpu().numpy(), e_rel, s_rel, "grad_relation %s/%s" % (sum, mul))
+    _assert_sum_close(g_in.cpu().numpy(), e_in, s_in, "grad_input %s/%s" % (sum, mul))
+
+
+@pytest.mark.parametrize("sum,mul", util.OPS)
+@pytest.mark.parametrize("dim", [1, 3, 64, 100, 128, 260])
+def test_parity_small(cuda, sum, mul, dim):
+    # 37 destination rows over 23 sources: duplicates, empty rows (n_out > distinct rows), random weights
+    _run_case(cuda, 37, 23, 5, 150, dim, sum, mul, seed=dim, duplicates=20, weights="random")
+
+
+@pytest.mark.parametrize("sum,mul", util.OPS)
+def test_parity_unit_weights_with_ties(cuda, sum, mul):
+    # integer-valued operands: every min/max has many exact ties (all-ties backward rule, lowest arg-index)
+    _run_case(cuda, 64, 64, 7, 900, 192, sum, mul, seed=7, duplicates=0, weights="unit", ties=True)
+
+
+@pytest.mark.parametrize("sum,mul", util.OPS)
+def test_parity_split_rows(cuda, sum, mul):
+    # hub rows: with chunk = 8 most segments are split into partial rows + combine pass
+    from ultra_torchdrug_b200 import _lib
+    lib = _lib.lib()
+    lib.ultra_rspmm_set_tuning(8, 0)
+    try:
+        _run_case(cuda, 50, 40, 3, 2000, 132, sum, mul, seed=11, duplicates=50, weights="random", skew=True, ties=True)
+    finally:
+        lib.ultra_rspmm_set_tuning(256, 0)
+
+
+@pytest.mark.parametrize("sum,mul", [("add", "mul"), ("max", "mul"), ("min", "add")])
+def test_parity_medium_default_chunk(cuda, sum, mul):
+    # Zipf destinations: the hub row has > 256 edges => split under the default chunk
+    _run_case(cuda, 300, 300, 11, 6000, 256, sum, mul, seed=3, duplicates=10, skew=True)
+
+
+@pytest.mark.parametrize("sum,mul", util.OPS)
+def test_parity_float64(cuda, sum, mul):
+    _run_case(cuda, 20, 20, 4, 90, 6, sum, mul, seed=5, duplicates=5, weights="random", dtype=np.float64)
+    _run_case(cuda, 20, 20, 4, 90, 7, sum, mul, seed=6, duplicates=5, weights="random", dtype=np.float64)
+
+
+def test_empty_and_degenerate(cuda):
+    for sum, mul in util.OPS:
+        _run_case(cuda, 5, 4, 3, 0, 8, sum, mul)            # no edges at all: identity rows, zero grads
+        _run_case(cuda, 1, 1, 1, 1, 1, sum, mul)            # single edge, single feature
+    from ultra_torchdrug_b200 import functional as F
+    empty = F.GraphIndex(torch.zeros(3, 0, dtype=torch.long, device=cuda), torch.zeros(0, device=cuda), (0, 3, 2))
+    out = empty.forward(torch.zeros(2, 4, device=cuda), torch.zeros(3, 4, device=cuda))
+    assert out.shape == (0, 4)
+    out = F.GraphIndex(torch.zeros(3, 0, dtype=torch.long, device=cuda), torch.zeros(0, device=cuda),
+                       (3, 3, 2)).forward(torch.zeros(2, 0, device=cuda), torch.zeros(3, 0, device=cuda))
+    assert out.shape == (3, 0)
+
+
+def test_index_matches_coalesce(cuda):
+    """The CSR order is exactly `coalesce()` order: sorted by (row, col, layer), duplicates merged by sum."""
+    from oracle import rspmm_oracle
+    from ultra_torchdrug_b200 import functional as F
+    indices, values = util.random_coo(40, 30, 6, 500, seed=2, duplicates=80, weights="random")
+    shape = (40, 30, 6)
+    index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), shape)
+    exp_index, exp_w, _ = rspmm_oracle.coalesce(indices, values, shape)
+    m = exp_index.shape[1]
+    assert index.nnz == m and index.c.nnz_raw == indices.shape[1] and index.c.unit_weight == 0
+
+    # read the device arrays back through torch views of the index buffer
+    base = index.buffer.data_ptr()
+
+    def view(ptr, count, dtype):
+        offset = ptr - base
+        return index.buffer[offset:offset + count * torch.tensor([], dtype=dtype).element_size()].view(dtype).cpu().numpy()
+
+    ptr = view(index.c.csr.ptr, shape[0] + 1, torch.int32)
+    edge = view(index.c.csr.edge, 2 * m, torch.int32).reshape(m, 2)
+    w = view(index.c.csr.w, m, torch.float32)
+    exp_ptr = np.searchsorted(exp_index[0], np.arange(shape[0] + 1))
+    assert np.array_equal(ptr, exp_ptr)
+    assert np.array_equal(edge[:, 0], exp_index[1]) and np.array_equal(edge[:, 1], exp_index[2])
+    np.testing.assert_allclose(w, exp_w, rtol=1e-6)
+    # CSC: same multiset of edges, sorted by (src, dst, rel); eid maps back to CSR positions
+    csc_edge = view(index.c.csc.edge, 2 * m, torch.int32).reshape(m, 2)
+    csc_eid = view(index.c.csc.eid, m, torch.int32)
+    csc_ptr = view(index.c.csc.ptr, shape[1] + 1, torch.int32)
+    order = np.lexsort((exp_index[2], exp_index[0], exp_index[1]))
+    assert np.array_equal(csc_eid, order)
+    assert np.array_equal(csc_edge[:, 0], exp_index[0][order]) and np.array_equal(csc_edge[:, 1], exp_index[2][order])
+    assert np.array_equal(csc_ptr, np.searchsorted(exp_index[1][order], np.arange(shape[1] + 1)))
+    # relation order: stable by coalesced position
+    rel_eid = view(index.c.rel.eid, m, torch.int32)
+    rel_edge = view(index.c.rel.edge, 2 * m, torch.int32).reshape(m, 2)
+    order = np.argsort(exp_index[2], kind="stable")
+    assert np.array_equal(rel_eid, order)
+    assert np.array_equal(rel_edge[:, 0], exp_index[0][order]) and np.array_equal(rel_edge[:, 1], exp_index[1][order])
+    # tasks cover every segment exactly once, longest first
+    for order_c, n_seg in ((index.c.csr, shape[0]), (index.c.csc, shape[1]), (index.c.rel, shape[2])):
+        task = view(order_c.task, 4 * order_c.n_task, torch.int32).reshape(-1, 4)
+        seg_ptr = view(order_c.ptr, n_seg + 1, torch.int32)
+        length = task[:, 2] - task[:, 1]
+        assert (np.diff(length) <= 0).all()
+        covered = np.zeros(m, dtype=np.int64)
+        for seg, begin, end, slot in task:
+            assert seg_ptr[seg] <= begin <= end <= seg_ptr[seg + 1]
+            covered[begin:end] += 1
+        assert (covered == 1).all() and set(task[:, 0]) == set(range(n_seg))
+
+
+def test_out_of_range_index_raises(cuda):
+    from ultra_torchdrug_b200 import functional as F, _lib
+    indices = torch.tensor([[0, 5], [0, 1], [0, 0]], device=cuda)
+    with pytest.raises(_lib.RspmmError) as info:
+        F.GraphIndex(indices, torch.ones(2, device=cuda), (3, 3, 1))
+    assert info.value.status == _lib.ERR_INDEX
+
+
+def test_deterministic(cuda):
+    from ultra_torchdrug_b200 import functional as F
+    indices, values = util.random_coo(500, 500, 9, 30000, seed=9, skew=True)
+    relation, input = util.random_dense(9, 512, 1), util.random_dense(500, 512, 2)
+    grad = util.random_dense(500, 512, 3)
+    index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), (500, 500, 9))
+    d = [torch.from_numpy(x).to(cuda) for x in (relation, input, grad)]
+    first = None
+    for _ in range(3):
+        out = index.forward(d[0], d[1])
+        g_rel, g_in = index.backward(d[0], d[1], out, d[2])
+        now = [t.clone() for t in (out, g_rel, g_in)]
+        if first is None:
+            first = now
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(first, now)), "results differ between runs"
+
+
+def test_operator_autograd_and_cache(cuda):
+    """The public operator: autograd wiring, index sharing across fresh `transpose` objects, error behaviour."""
+    from ultra_torchdrug_b200 import functional as F
+    indices, values = util.random_coo(60, 60, 6, 700, seed=4, duplicates=30)
+    shape = (60, 60, 6)
+    relation = torch.from_numpy(util.random_dense(6, 128, 1)).to(cuda).requires_grad_()
+    input = torch.from_numpy(util.random_dense(60, 128, 2)).to(cuda).requires_grad_()
+    F.clear_index_cache()
+    before = dict(F.cache_stats)
+    outs = []
+    for _ in range(3):  # a fresh sparse tensor object with equal content per "layer"
+        sparse = util.to_sparse(indices, values, shape, cuda)
+        outs.append(F.generalized_rspmm(sparse, relation, input, sum="add", mul="mul"))
+    assert F.cache_stats["built"] - before["built"] == 1
+    assert F.cache_stats["fingerprint_hit"] - before["fingerprint_hit"] == 2
+    out = F.generalized_rspmm(sparse, relation, input)  # same object again: attached index
+    assert F.cache_stats["attached"] - before["attached"] == 1
+    loss = (out * torch.arange(128, device=cuda)).sum()
+    loss.backward()
+    exp, _ = util.oracle_forward(indices, values, shape, relation.detach().cpu().numpy(), input.detach().cpu().numpy(),
+                                 "add", "mul", dtype=np.float64)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), exp, rtol=1e-4, atol=1e-4)
+    g = np.broadcast_to(np.arange(128, dtype=np.float32), (60, 128))
+    e_rel, e_in = util.oracle_backward(indices, values, shape, relation.detach().cpu().numpy(),
+                                       input.detach().cpu().numpy(), None, g, "add", "mul", dtype=np.float64)
+    np.testing.assert_allclose(relation.grad.cpu().numpy(), e_rel, rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(input.grad.cpu().numpy(), e_in, rtol=1e-4, atol=1e-2)
+    # no_grad: nothing saved
+    with torch.no_grad():
+        assert not F.generalized_rspmm(sparse, relation, input).requires_grad
+    # error behaviour (torchdrug: ValueError for unknown ops, RuntimeError from TORCH_CHECK)
+    with pytest.raises(ValueError):
+        F.generalized_rspmm(sparse, relation, input, sum="mean")
+    with pytest.raises(RuntimeError):
+        F.generalized_rspmm(sparse, relation[:, :64], input)
+    with pytest.raises(RuntimeError):
+        F.generalized_rspmm(sparse, relation.double(), input)
+    with pytest.raises(RuntimeError):
+        F.generalized_rspmm(sparse, relation.cpu(), input.cpu())
+    # non-contiguous operands are accepted (callee makes them contiguous)
+    wide = torch.randn(60, 256, device=cuda)
+    assert torch.equal(F.generalized_rspmm(sparse, relation.detach(), wide[:, ::2]),
+                       F.generalized_rspmm(sparse, relation.detach(), wide[:, ::2].contiguous()))
+
+
+@pytest.mark.parametrize("sum,mul", util.OPS)
+def test_gradcheck_float64(cuda, sum, mul):
+    from ultra_torchdrug_b200 import functional as F
+    indices, values = util.random_coo(7, 6, 3, 25, seed=8, duplicates=3, weights="random", dtype=np.float64)
+    sparse = util.to_sparse(indices, values, (7, 6, 3), cuda)
+    relation = torch.randn(3, 5, dtype=torch.float64, device=cuda, requires_grad=True)
+    input = torch.randn(6, 5, dtype=torch.float64, device=cuda, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda r, x: F.generalized_rspmm(sparse, r, x, sum=sum, mul=mul),
+                                    (relation, input), eps=1e-6, atol=1e-6)
+
+
+def test_host_buffer_ctx(cuda):
+    """The torch-free host-buffer entry points (what a non-Python host binds; bench.py's e2e path)."""
+    from ultra_torchdrug_b200 import _lib
+    lib = _lib.lib()
+    indices, values = util.random_coo(80, 70, 5, 900, seed=12, duplicates=40, weights="random")
+    shape = (80, 70, 5)
+    relation, input, grad = util.random_dense(5, 96, 1), util.random_dense(70, 96, 2), util.random_dense(80, 96, 3)
+    ctx = ctypes.c_void_p()
+    _lib.check(lib.ultra_rspmm_ctx_create(ctypes.byref(ctx), 0), "ctx_create")
+    try:
+        indices = np.ascontiguousarray(indices)
+        _lib.check(lib.ultra_rspmm_ctx_set_graph(ctx, indices.ctypes.data, values.ctypes.data, indices.shape[1],
+                                                 80, 70, 5, _lib.F32), "ctx_set_graph")
+        out = np.empty((80, 96), dtype=np.float32)
+        g_rel, g_in = np.empty_like(relation), np.empty_like(input)
+        _lib.check(lib.ultra_rspmm_ctx_forward_backward(
+            ctx, relation.ctypes.data, input.ctypes.data, grad.ctypes.data, out.ctypes.data, g_rel.ctypes.data,
+            g_in.ctypes.data, 96, 0, 0), "ctx_forward_backward")
+        assert lib.ultra_rspmm_ctx_last_kernel_ms(ctx) > 0
+        exp, _ = util.oracle_forward(indices, values, shape, relation, input, "add", "mul", dtype=np.float64)
+        e_rel, e_in = util.oracle_backward(indices, values, shape, relation, input, None, grad, "add", "mul",
+                                           dtype=np.float64)
+        np.testing.assert_allclose(out, exp, rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(g_rel, e_rel, rtol=1e-4, atol=1e-3)
+        np.testing.assert_allclose(g_in, e_in, rtol=1e-4, atol=1e-3)
+        out2 = np.empty_like(out)
+        _lib.check(lib.ultra_rspmm_ctx_forward(ctx, relation.ctypes.data, input.ctypes.data, out2.ctypes.data, 96, 2, 1),
+                   "ctx_forward")
+        exp2, _ = util.oracle_forward(indices, values, shape, relation, input, "max", "add")
+        assert np.array_equal(out2, exp2)
+    finally:
+        lib.ultra_rspmm_ctx_destroy(ctx)

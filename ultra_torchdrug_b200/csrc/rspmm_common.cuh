@@ -108,5 +108,17 @@ template <typename T, int MSG> __device__ __forceinline__ T message(T w, T r, T 
 
 // launch bookkeeping (claimed in bench.py as `gpu_launches`)
 void note_launch();
+// per-thread status plumbing shared by the translation units
+int fail_cuda(cudaError_t error);
+extern int g_chunk;    // edges per task for new indexes
+extern int g_variant;  // 0 auto, 1 generic, 2 staged
+
+#define ULTRA_CUDA_OK(expr)                                      \
+    do {                                                         \
+        cudaError_t ultra_err_ = (expr);                         \
+        if (ultra_err_ != cudaSuccess) return ::ultra::fail_cuda(ultra_err_); \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 }  // namespace ultra

@@ -1,0 +1,506 @@
+// Graph index build: un-coalesced int64 COO  ->  three int32 edge orders + task lists.
+//
+// Replaces what the reference redoes on every operator call: `graph.adjacency.transpose(0,1)`
+// (reference ultra/layer.py:127,328), `sparse.coalesce()` and torchdrug's `coo2csr3d`
+// (SURVEY.md section 8 row a5).  Done once per distinct edge set and cached by the caller.
+//
+//   1. key = (row * n_in + col) * n_rel + rel  (row = node_out, col = node_in), stable radix sort
+//   2. runs of equal keys are merged, values summed in fp64   ->  coalesced order = CSR order
+//   3. second sort by (col, row, rel)  -> CSC order (backward w.r.t. input)
+//   4. third, stable sort by rel        -> relation order (backward w.r.t. relation)
+//   5. per order: segment pointers by binary search, tasks of <= chunk edges, split-segment slots,
+//      tasks sorted longest first
+// Sorting and scans use CUB (library code, like calling cuBLAS for a plain GEMM); this is not the
+// measured hot path.
+#include <cub/cub.cuh>
+
+#include "rspmm_common.cuh"
+
+namespace ultra {
+
+namespace {
+
+constexpr int kBuildThreads = 256;
+inline int blocks_for(int64_t n) { return (int)((n + kBuildThreads - 1) / kBuildThreads); }
+
+enum Counter {
+    CNT_ERROR = 0,    // an index was out of range
+    CNT_NONUNIT = 1,  // a merged value differs from 1
+    CNT_NNZ = 2,      // merged edge count
+    CNT_MAXSEG = 3,   // +order: longest segment
+    CNT_TOTALS = 8,   // +3*order: n_task, n_slot, n_split
+    CNT_SIZE = 32
+};
+
+__global__ void make_keys_kernel(const int64_t *__restrict__ indices, int64_t stride, int64_t nnz, int64_t n_out,
+                                 int64_t n_in, int64_t n_rel, unsigned long long *__restrict__ keys,
+                                 int32_t *__restrict__ vals, int32_t *__restrict__ counters) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const int64_t r = indices[e], c = indices[stride + e], k = indices[2 * stride + e];
+    if (r < 0 || r >= n_out || c < 0 || c >= n_in || k < 0 || k >= n_rel) {
+        atomicOr(&counters[CNT_ERROR], 1);
+        keys[e] = 0;
+    } else {
+        keys[e] = ((unsigned long long)r * n_in + c) * n_rel + k;
+    }
+    vals[e] = (int32_t)e;
+}
+
+__global__ void head_flags_kernel(const unsigned long long *__restrict__ keys, int64_t nnz, int32_t *__restrict__ head) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > nnz) return;
+    head[e] = (e < nnz && (e == 0 || keys[e] != keys[e - 1])) ? 1 : 0;
+}
+
+// one thread per run head: sums the run's values (fp64 accumulate), decodes the key, emits the CSR edge
+template <typename T>
+__global__ void merge_kernel(const unsigned long long *__restrict__ keys, const int32_t *__restrict__ vals,
+                             const int32_t *__restrict__ pos, const T *__restrict__ values, int64_t nnz,
+                             int64_t n_in, int64_t n_rel, int2 *__restrict__ csr_edge, T *__restrict__ csr_w,
+                             int32_t *__restrict__ row_of, int32_t *__restrict__ counters) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    const unsigned long long key = keys[e];
+    if (e > 0 && keys[e - 1] == key) return;
+    double total = 0.0;
+    for (int64_t q = e; q < nnz && keys[q] == key; ++q) total += (double)values[vals[q]];
+    const T w = (T)total;
+    const int32_t m = pos[e];
+    const unsigned long long rc = key / (unsigned long long)n_rel;
+    csr_edge[m] = make_int2((int32_t)(rc % (unsigned long long)n_in), (int32_t)(key % (unsigned long long)n_rel));
+    csr_w[m] = w;
+    row_of[m] = (int32_t)(rc / (unsigned long long)n_in);
+    if (w != T(1)) atomicOr(&counters[CNT_NONUNIT], 1);
+    if (e == 0) counters[CNT_NNZ] = pos[nnz];
+}
+
+__global__ void csc_keys_kernel(const int2 *__restrict__ csr_edge, const int32_t *__restrict__ row_of, int32_t nnz,
+                                int64_t n_out, int64_t n_rel, unsigned long long *__restrict__ keys,
+                                int32_t *__restrict__ vals) {
+    const int32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nnz) return;
+    const int2 e = csr_edge[m];
+    keys[m] = ((unsigned long long)e.x * n_out + row_of[m]) * n_rel + e.y;
+    vals[m] = m;
+}
+
+__global__ void rel_keys_kernel(const int2 *__restrict__ csr_edge, int32_t nnz, unsigned long long *__restrict__ keys,
+                                int32_t *__restrict__ vals) {
+    const int32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nnz) return;
+    keys[m] = (unsigned long long)csr_edge[m].y;
+    vals[m] = m;
+}
+
+// permute the coalesced edges into another order; MODE 0: CSC {dst, rel} / segment = src,
+// MODE 1: relation order {dst, src} / segment = rel
+template <typename T, int MODE>
+__global__ void permute_kernel(const int32_t *__restrict__ perm, int32_t nnz, const int2 *__restrict__ csr_edge,
+                               const T *__restrict__ csr_w, const int32_t *__restrict__ row_of,
+                               int2 *__restrict__ edge, T *__restrict__ w, int32_t *__restrict__ eid,
+                               int32_t *__restrict__ seg_of) {
+    const int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    const int32_t m = perm[p];
+    const int2 e = csr_edge[m];
+    const int32_t r = row_of[m];
+    edge[p] = MODE == 0 ? make_int2(r, e.y) : make_int2(r, e.x);
+    seg_of[p] = MODE == 0 ? e.x : e.y;
+    w[p] = csr_w[m];
+    eid[p] = m;
+}
+
+// ptr[s] = first position whose segment id is >= s   (s in [0, n_seg])
+__global__ void segment_ptr_kernel(const int32_t *__restrict__ seg_of, int32_t nnz, int32_t n_seg,
+                                   int32_t *__restrict__ ptr) {
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_seg) return;
+    int32_t lo = 0, hi = nnz;
+    while (lo < hi) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (seg_of[mid] < s) lo = mid + 1; else hi = mid;
+    }
+    ptr[s] = lo;
+}
+
+__global__ void task_count_kernel(const int32_t *__restrict__ ptr, int32_t n_seg, int32_t chunk,
+                                  int32_t *__restrict__ cnt_task, int32_t *__restrict__ cnt_slot,
+                                  int32_t *__restrict__ cnt_split, int32_t *__restrict__ max_seg) {
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_seg) return;
+    if (s == n_seg) {
+        cnt_task[s] = cnt_slot[s] = cnt_split[s] = 0;
+        return;
+    }
+    const int32_t deg = ptr[s + 1] - ptr[s];
+    const int32_t c = deg <= chunk ? 1 : (deg + chunk - 1) / chunk;
+    cnt_task[s] = c;
+    cnt_slot[s] = c > 1 ? c : 0;
+    cnt_split[s] = c > 1 ? 1 : 0;
+    atomicMax(max_seg, deg);
+}
+
+__global__ void gather_totals_kernel(const int32_t *__restrict__ off_task, const int32_t *__restrict__ off_slot,
+                                     const int32_t *__restrict__ off_split, int32_t n_seg,
+                                     int32_t *__restrict__ totals) {
+    totals[0] = off_task[n_seg];
+    totals[1] = off_slot[n_seg];
+    totals[2] = off_split[n_seg];
+}
+
+__global__ void task_emit_kernel(const int32_t *__restrict__ ptr, int32_t n_seg, int32_t chunk,
+                                 const int32_t *__restrict__ off_task, const int32_t *__restrict__ off_slot,
+                                 const int32_t *__restrict__ off_split, int4 *__restrict__ task,
+                                 uint32_t *__restrict__ task_key, int32_t *__restrict__ task_val,
+                                 int4 *__restrict__ split) {
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const int32_t begin = ptr[s], end = ptr[s + 1];
+    const int32_t deg = end - begin;
+    const int32_t t0 = off_task[s];
+    if (deg <= chunk) {
+        task[t0] = make_int4(s, begin, end, -1);
+        task_key[t0] = (uint32_t)(chunk - deg);
+        task_val[t0] = t0;
+        return;
+    }
+    const int32_t c = (deg + chunk - 1) / chunk;
+    const int32_t slot0 = off_slot[s];
+    // equal-sized chunks (sizes differ by at most one) so that no task of a split row is tiny
+    const int32_t base = deg / c, extra = deg % c;
+    int32_t at = begin;
+    for (int32_t q = 0; q < c; ++q) {
+        const int32_t len = base + (q < extra ? 1 : 0);
+        task[t0 + q] = make_int4(s, at, at + len, slot0 + q);
+        task_key[t0 + q] = (uint32_t)(chunk - len);
+        task_val[t0 + q] = t0 + q;
+        at += len;
+    }
+    split[off_split[s]] = make_int4(s, slot0, c, 0);
+}
+
+__global__ void task_gather_kernel(const int4 *__restrict__ task_in, const int32_t *__restrict__ order, int32_t n_task,
+                                   int4 *__restrict__ task_out) {
+    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_task) task_out[t] = task_in[order[t]];
+}
+
+// FNV-style 2 x 64-bit fingerprint; order-sensitive (position mixed into each term), combined with
+// integer atomics so that the result does not depend on scheduling.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+template <typename T>
+__global__ void fingerprint_kernel(const int64_t *__restrict__ indices, int64_t stride, const T *__restrict__ values,
+                                   int64_t nnz, unsigned long long *__restrict__ out) {
+    unsigned long long a = 0, b = 0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long h = mix64((unsigned long long)e + 0x9e3779b97f4a7c15ULL);
+        h = mix64(h ^ (unsigned long long)indices[e]);
+        h = mix64(h ^ ((unsigned long long)indices[stride + e] << 1));
+        h = mix64(h ^ ((unsigned long long)indices[2 * stride + e] << 2));
+        unsigned long long bits = 0;
+        const T v = values[e];
+        memcpy(&bits, &v, sizeof(T));
+        h = mix64(h ^ bits);
+        a += h;
+        b ^= mix64(h + 0x632be59bd9b4e019ULL);
+    }
+    for (int off = 16; off; off >>= 1) {
+        a += __shfl_xor_sync(kFullMask, a, off);
+        b ^= __shfl_xor_sync(kFullMask, b, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], a);
+        atomicXor(&out[1], b);
+    }
+}
+
+int bit_length(unsigned long long v) {
+    int bits = 0;
+    while (v) { ++bits; v >>= 1; }
+    return bits;
+}
+
+struct OrderLayout {
+    size_t ptr, edge, w, eid, task, split;
+};
+
+struct IndexLayout {
+    OrderLayout order[3];
+    size_t total;
+};
+
+struct ScratchLayout {
+    size_t keys_a, keys_b, vals_a, vals_b, pos, row_of, seg_of, cnt, off, task_tmp, tkey_a, tkey_b, tval_a, tval_b,
+        counters, cub, cub_bytes, total;
+};
+
+int64_t task_upper(int64_t nnz_raw, int64_t n_seg, int chunk) { return n_seg + nnz_raw / chunk + 2; }
+int64_t split_upper(int64_t nnz_raw, int chunk) { return nnz_raw / chunk + 2; }
+
+IndexLayout index_layout(int64_t nnz_raw, const int32_t n_seg[3], size_t elem, int chunk) {
+    IndexLayout L;
+    size_t at = 0;
+    const int64_t e = nnz_raw > 0 ? nnz_raw : 1;
+    for (int o = 0; o < 3; ++o) {
+        OrderLayout &q = L.order[o];
+        q.ptr = at; at = align_up(at + sizeof(int32_t) * ((size_t)n_seg[o] + 1));
+        q.edge = at; at = align_up(at + sizeof(int2) * e);
+        q.w = at; at = align_up(at + elem * e);
+        q.eid = at; at = align_up(at + (o == 0 ? 0 : sizeof(int32_t) * e));
+        q.task = at; at = align_up(at + sizeof(int4) * task_upper(nnz_raw, n_seg[o], chunk));
+        q.split = at; at = align_up(at + sizeof(int4) * split_upper(nnz_raw, chunk));
+    }
+    L.total = at;
+    return L;
+}
+
+ScratchLayout scratch_layout(int64_t nnz_raw, int32_t n_seg_max, int chunk) {
+    ScratchLayout S;
+    size_t at = 0;
+    const size_t e = nnz_raw > 0 ? nnz_raw : 1;
+    const size_t nt = task_upper(nnz_raw, n_seg_max, chunk);
+    S.keys_a = at; at = align_up(at + 8 * e);
+    S.keys_b = at; at = align_up(at + 8 * e);
+    S.vals_a = at; at = align_up(at + 4 * (e + 1));  // doubles as the head-flag array (nnz + 1)
+    S.vals_b = at; at = align_up(at + 4 * e);
+    S.pos = at; at = align_up(at + 4 * (e + 1));
+    S.row_of = at; at = align_up(at + 4 * e);
+    S.seg_of = at; at = align_up(at + 4 * e);
+    S.cnt = at; at = align_up(at + 3 * 4 * ((size_t)n_seg_max + 1));
+    S.off = at; at = align_up(at + 9 * 4 * ((size_t)n_seg_max + 1));
+    S.task_tmp = at; at = align_up(at + 16 * nt);
+    S.tkey_a = at; at = align_up(at + 4 * nt);
+    S.tkey_b = at; at = align_up(at + 4 * nt);
+    S.tval_a = at; at = align_up(at + 4 * nt);
+    S.tval_b = at; at = align_up(at + 4 * nt);
+    S.counters = at; at = align_up(at + 4 * CNT_SIZE);
+    S.cub = at;
+    // CUB temporary storage: radix sort / scan need O(tiles) words; provision generously and verify at build time
+    S.cub_bytes = align_up((size_t)(16u << 20) + 8 * e + 8 * nt);
+    at += S.cub_bytes;
+    S.total = at;
+    return S;
+}
+
+template <typename T>
+int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values, int64_t nnz_raw, int32_t n_out,
+                int32_t n_in, int32_t n_rel, char *ibuf, char *sbuf, ultra_rspmm_index_t *index, cudaStream_t stream) {
+    const int chunk = g_chunk;
+    const int32_t n_seg[3] = {n_out, n_in, n_rel};
+    const int32_t n_seg_max = n_out > n_in ? (n_out > n_rel ? n_out : n_rel) : (n_in > n_rel ? n_in : n_rel);
+    const IndexLayout L = index_layout(nnz_raw, n_seg, sizeof(T), chunk);
+    const ScratchLayout S = scratch_layout(nnz_raw, n_seg_max, chunk);
+
+    unsigned long long *keys_a = (unsigned long long *)(sbuf + S.keys_a), *keys_b = (unsigned long long *)(sbuf + S.keys_b);
+    int32_t *vals_a = (int32_t *)(sbuf + S.vals_a), *vals_b = (int32_t *)(sbuf + S.vals_b);
+    int32_t *pos = (int32_t *)(sbuf + S.pos), *row_of = (int32_t *)(sbuf + S.row_of), *seg_of = (int32_t *)(sbuf + S.seg_of);
+    int32_t *counters = (int32_t *)(sbuf + S.counters);
+    void *cub_tmp = sbuf + S.cub;
+    size_t need = 0;
+
+    int2 *csr_edge = (int2 *)(ibuf + L.order[0].edge);
+    T *csr_w = (T *)(ibuf + L.order[0].w);
+
+    ULTRA_CUDA_OK(cudaMemsetAsync(counters, 0, 4 * CNT_SIZE, stream));
+    int32_t host_counters[CNT_SIZE] = {0};
+    int32_t nnz = 0;
+
+    if (nnz_raw > 0) {
+        make_keys_kernel<<<blocks_for(nnz_raw), kBuildThreads, 0, stream>>>(dev_indices, stride, nnz_raw, n_out, n_in,
+                                                                           n_rel, keys_a, vals_a, counters);
+        note_launch();
+        const unsigned long long span = (unsigned long long)n_out * (unsigned long long)n_in * (unsigned long long)n_rel;
+        const int bits = bit_length(span > 0 ? span - 1 : 0);
+        need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, keys_a, keys_b, vals_a, vals_b, (int)nnz_raw, 0, bits > 0 ? bits : 1, stream);
+        if (need > S.cub_bytes) return ULTRA_RSPMM_ERR_WORKSPACE;
+        need = S.cub_bytes;
+        ULTRA_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, need, keys_a, keys_b, vals_a, vals_b, (int)nnz_raw, 0,
+                                                      bits > 0 ? bits : 1, stream));
+        note_launch();
+        head_flags_kernel<<<blocks_for(nnz_raw + 1), kBuildThreads, 0, stream>>>(keys_b, nnz_raw, vals_a);
+        note_launch();
+        need = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, need, vals_a, pos, (int)nnz_raw + 1, stream);
+        if (need > S.cub_bytes) return ULTRA_RSPMM_ERR_WORKSPACE;
+        need = S.cub_bytes;
+        ULTRA_CUDA_OK(cub::DeviceScan::ExclusiveSum(cub_tmp, need, vals_a, pos, (int)nnz_raw + 1, stream));
+        note_launch();
+        merge_kernel<T><<<blocks_for(nnz_raw), kBuildThreads, 0, stream>>>(keys_b, vals_b, pos, dev_values, nnz_raw, n_in,
+                                                                          n_rel, csr_edge, csr_w, row_of, counters);
+        note_launch();
+        ULTRA_CUDA_OK(cudaMemcpyAsync(host_counters, counters, 4 * CNT_SIZE, cudaMemcpyDeviceToHost, stream));
+        ULTRA_CUDA_OK(cudaStreamSynchronize(stream));
+        if (host_counters[CNT_ERROR]) return ULTRA_RSPMM_ERR_INDEX;
+        nnz = host_counters[CNT_NNZ];
+    }
+
+    // ---- the two other orders -------------------------------------------------------------------
+    for (int o = 0; o < 3; ++o) {
+        int32_t *ptr = (int32_t *)(ibuf + L.order[o].ptr);
+        const int32_t *segments = row_of;
+        if (o > 0 && nnz > 0) {
+            int2 *edge = (int2 *)(ibuf + L.order[o].edge);
+            T *w = (T *)(ibuf + L.order[o].w);
+            int32_t *eid = (int32_t *)(ibuf + L.order[o].eid);
+            int bits;
+            if (o == 1) {
+                csc_keys_kernel<<<blocks_for(nnz), kBuildThreads, 0, stream>>>(csr_edge, row_of, nnz, n_out, n_rel, keys_a, vals_a);
+                const unsigned long long span = (unsigned long long)n_out * (unsigned long long)n_in * (unsigned long long)n_rel;
+                bits = bit_length(span > 0 ? span - 1 : 0);
+            } else {
+                rel_keys_kernel<<<blocks_for(nnz), kBuildThreads, 0, stream>>>(csr_edge, nnz, keys_a, vals_a);
+                bits = bit_length(n_rel > 0 ? (unsigned long long)n_rel - 1 : 0);
+            }
+            note_launch();
+            need = S.cub_bytes;
+            ULTRA_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, need, keys_a, keys_b, vals_a, vals_b, nnz, 0,
+                                                          bits > 0 ? bits : 1, stream));
+            note_launch();
+            if (o == 1)
+                permute_kernel<T, 0><<<blocks_for(nnz), kBuildThreads, 0, stream>>>(vals_b, nnz, csr_edge, csr_w, row_of, edge, w, eid, seg_of);
+            else
+                permute_kernel<T, 1><<<blocks_for(nnz), kBuildThreads, 0, stream>>>(vals_b, nnz, csr_edge, csr_w, row_of, edge, w, eid, seg_of);
+            note_launch();
+            segments = seg_of;
+        }
+        segment_ptr_kernel<<<blocks_for((int64_t)n_seg[o] + 1), kBuildThreads, 0, stream>>>(segments, nnz, n_seg[o], ptr);
+        note_launch();
+        int32_t *cnt = (int32_t *)(sbuf + S.cnt);
+        int32_t *off = (int32_t *)(sbuf + S.off) + (size_t)o * 3 * ((size_t)n_seg_max + 1);
+        const size_t span = (size_t)n_seg_max + 1;
+        task_count_kernel<<<blocks_for((int64_t)n_seg[o] + 1), kBuildThreads, 0, stream>>>(
+            ptr, n_seg[o], chunk, cnt, cnt + span, cnt + 2 * span, counters + CNT_MAXSEG + o);
+        note_launch();
+        for (int q = 0; q < 3; ++q) {
+            need = S.cub_bytes;
+            ULTRA_CUDA_OK(cub::DeviceScan::ExclusiveSum(cub_tmp, need, cnt + q * span, off + q * span, n_seg[o] + 1, stream));
+            note_launch();
+        }
+        gather_totals_kernel<<<1, 1, 0, stream>>>(off, off + span, off + 2 * span, n_seg[o], counters + CNT_TOTALS + 3 * o);
+        note_launch();
+    }
+    ULTRA_CUDA_OK(cudaMemcpyAsync(host_counters, counters, 4 * CNT_SIZE, cudaMemcpyDeviceToHost, stream));
+    ULTRA_CUDA_OK(cudaStreamSynchronize(stream));
+
+    // ---- tasks ------------------------------------------------------------------------------------
+    ultra_rspmm_order_t *orders[3] = {&index->csr, &index->csc, &index->rel};
+    for (int o = 0; o < 3; ++o) {
+        ultra_rspmm_order_t &out = *orders[o];
+        const size_t span = (size_t)n_seg_max + 1;
+        const int32_t *off = (int32_t *)(sbuf + S.off) + (size_t)o * 3 * span;
+        out.n_seg = n_seg[o];
+        out.n_task = host_counters[CNT_TOTALS + 3 * o];
+        out.n_slot = host_counters[CNT_TOTALS + 3 * o + 1];
+        out.n_split = host_counters[CNT_TOTALS + 3 * o + 2];
+        out.max_seg_nnz = host_counters[CNT_MAXSEG + o];
+        out.reserved = 0;
+        out.ptr = (const int32_t *)(ibuf + L.order[o].ptr);
+        out.edge = (const int32_t *)(ibuf + L.order[o].edge);
+        out.w = ibuf + L.order[o].w;
+        out.eid = o == 0 ? nullptr : (const int32_t *)(ibuf + L.order[o].eid);
+        out.task = (const int32_t *)(ibuf + L.order[o].task);
+        out.split = (const int32_t *)(ibuf + L.order[o].split);
+        if (out.n_task > task_upper(nnz_raw, n_seg[o], chunk) || out.n_split > split_upper(nnz_raw, chunk))
+            return ULTRA_RSPMM_ERR_WORKSPACE;
+        if (out.n_task == 0) continue;
+        int4 *task_tmp = (int4 *)(sbuf + S.task_tmp);
+        uint32_t *tkey_a = (uint32_t *)(sbuf + S.tkey_a), *tkey_b = (uint32_t *)(sbuf + S.tkey_b);
+        int32_t *tval_a = (int32_t *)(sbuf + S.tval_a), *tval_b = (int32_t *)(sbuf + S.tval_b);
+        task_emit_kernel<<<blocks_for(n_seg[o]), kBuildThreads, 0, stream>>>(
+            out.ptr, n_seg[o], chunk, off, off + span, off + 2 * span, task_tmp, tkey_a, tval_a, (int4 *)(ibuf + L.order[o].split));
+        note_launch();
+        need = S.cub_bytes;
+        ULTRA_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, need, tkey_a, tkey_b, tval_a, tval_b, out.n_task, 0,
+                                                      bit_length((unsigned long long)chunk), stream));
+        note_launch();
+        task_gather_kernel<<<blocks_for(out.n_task), kBuildThreads, 0, stream>>>(task_tmp, tval_b, out.n_task,
+                                                                               (int4 *)(ibuf + L.order[o].task));
+        note_launch();
+    }
+    ULTRA_CUDA_OK(cudaGetLastError());
+    ULTRA_CUDA_OK(cudaStreamSynchronize(stream));  // scratch may be released by the caller on return
+
+    index->nnz = nnz;
+    index->nnz_raw = nnz_raw;
+    index->n_out = n_out;
+    index->n_in = n_in;
+    index->n_rel = n_rel;
+    index->dtype = sizeof(T) == 4 ? ULTRA_RSPMM_F32 : ULTRA_RSPMM_F64;
+    index->unit_weight = host_counters[CNT_NONUNIT] ? 0 : 1;
+    index->chunk = chunk;
+    return ULTRA_RSPMM_OK;
+}
+
+int check_shape(int64_t nnz_raw, int32_t n_out, int32_t n_in, int32_t n_rel, int32_t dtype) {
+    if (nnz_raw < 0 || n_out < 0 || n_in < 0 || n_rel < 0) return ULTRA_RSPMM_ERR_ARG;
+    if (dtype != ULTRA_RSPMM_F32 && dtype != ULTRA_RSPMM_F64) return ULTRA_RSPMM_ERR_ARG;
+    if (nnz_raw >= (int64_t)1 << 31) return ULTRA_RSPMM_ERR_RANGE;
+    const unsigned __int128 span = (unsigned __int128)n_out * (unsigned __int128)n_in * (unsigned __int128)n_rel;
+    if (span >> 63) return ULTRA_RSPMM_ERR_RANGE;
+    return ULTRA_RSPMM_OK;
+}
+
+}  // namespace
+
+}  // namespace ultra
+
+using namespace ultra;
+
+extern "C" int ultra_rspmm_index_bytes(int64_t nnz_raw, int32_t n_out, int32_t n_in, int32_t n_rel, int32_t dtype,
+                                       size_t *index_bytes, size_t *scratch_bytes) {
+    const int status = check_shape(nnz_raw, n_out, n_in, n_rel, dtype);
+    if (status) return status;
+    if (!index_bytes || !scratch_bytes) return ULTRA_RSPMM_ERR_ARG;
+    const int32_t n_seg[3] = {n_out, n_in, n_rel};
+    const int32_t n_seg_max = n_out > n_in ? (n_out > n_rel ? n_out : n_rel) : (n_in > n_rel ? n_in : n_rel);
+    *index_bytes = index_layout(nnz_raw, n_seg, dtype == ULTRA_RSPMM_F32 ? 4 : 8, g_chunk).total;
+    *scratch_bytes = scratch_layout(nnz_raw, n_seg_max, g_chunk).total;
+    return ULTRA_RSPMM_OK;
+}
+
+extern "C" int ultra_rspmm_index_build(const int64_t *dev_indices, int64_t index_stride, const void *dev_values,
+                                       int64_t nnz_raw, int32_t n_out, int32_t n_in, int32_t n_rel, int32_t dtype,
+                                       void *index_buffer, size_t index_bytes, void *scratch, size_t scratch_bytes,
+                                       ultra_rspmm_index_t *index, void *stream) {
+    int status = check_shape(nnz_raw, n_out, n_in, n_rel, dtype);
+    if (status) return status;
+    if (!index || !index_buffer || !scratch) return ULTRA_RSPMM_ERR_ARG;
+    if (nnz_raw > 0 && (!dev_indices || !dev_values || index_stride < nnz_raw)) return ULTRA_RSPMM_ERR_ARG;
+    size_t need_index = 0, need_scratch = 0;
+    status = ultra_rspmm_index_bytes(nnz_raw, n_out, n_in, n_rel, dtype, &need_index, &need_scratch);
+    if (status) return status;
+    if (index_bytes < need_index || scratch_bytes < need_scratch) return ULTRA_RSPMM_ERR_WORKSPACE;
+    if (((uintptr_t)index_buffer | (uintptr_t)scratch) & 255) return ULTRA_RSPMM_ERR_ARG;
+    memset(index, 0, sizeof(*index));
+    if (dtype == ULTRA_RSPMM_F32)
+        return build_typed<float>(dev_indices, index_stride, (const float *)dev_values, nnz_raw, n_out, n_in, n_rel,
+                                  (char *)index_buffer, (char *)scratch, index, (cudaStream_t)stream);
+    return build_typed<double>(dev_indices, index_stride, (const double *)dev_values, nnz_raw, n_out, n_in, n_rel,
+                               (char *)index_buffer, (char *)scratch, index, (cudaStream_t)stream);
+}
+
+extern "C" int ultra_rspmm_fingerprint(const int64_t *dev_indices, int64_t index_stride, const void *dev_values,
+                                       int64_t nnz_raw, int32_t dtype, uint64_t *dev_out, void *stream) {
+    if (nnz_raw < 0 || !dev_out || (nnz_raw > 0 && (!dev_indices || !dev_values))) return ULTRA_RSPMM_ERR_ARG;
+    if (dtype != ULTRA_RSPMM_F32 && dtype != ULTRA_RSPMM_F64) return ULTRA_RSPMM_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    ULTRA_CUDA_OK(cudaMemsetAsync(dev_out, 0, 16, s));
+    if (nnz_raw == 0) return ULTRA_RSPMM_OK;
+    int blocks = blocks_for(nnz_raw);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (dtype == ULTRA_RSPMM_F32)
+        fingerprint_kernel<float><<<blocks, kBuildThreads, 0, s>>>(dev_indices, index_stride, (const float *)dev_values,
+                                                                  nnz_raw, (unsigned long long *)dev_out);
+    else
+        fingerprint_kernel<double><<<blocks, kBuildThreads, 0, s>>>(dev_indices, index_stride, (const double *)dev_values,
+                                                                   nnz_raw, (unsigned long long *)dev_out);
+    note_launch();
+    ULTRA_CUDA_OK(cudaGetLastError());
+    return ULTRA_RSPMM_OK;
+}

@@ -1,0 +1,475 @@
+// Gather-combine-reduce kernels of the rspmm hot path (sm_100a) and their C-ABI launchers.
+//
+// One kernel shape serves the forward pass and both atomic-free backward passes
+// (DESIGN.md "Kernels"): a *task* is at most `chunk` consecutive edges of one segment of an edge
+// order; a warp owns (task, feature slab of 32*VEC features) and reduces
+//     acc[:] (+)= w_e * f(A[edge.x, slab], B[edge.y, slab])
+// in registers, then writes the result row (or a partial row for split segments).
+//
+//   pass                      order  segment   A (gathered)     B                     f
+//   forward                   csr    dst i     input[src j]     relation[k] (table)   mul | add
+//   backward wrt input  (add) csc    src j     grad_out[dst i]  relation[k] (table)   mul | copy A
+//   backward wrt relation(add) rel   rel k     grad_out[dst i]  input[src j] (gather) mul | copy A
+//   backward (min/max)        csc / rel: gated variant, see seg_gated_kernel
+//
+// Warps are numbered slab-major (all tasks of slab 0, then slab 1, ...), so the CTAs resident at
+// any moment read one (rows x SLAB) column block of the gathered operand - it stays in the 126 MB
+// L2 - and one (n_rel x SLAB) block of the relation table, which stays in L1.  HBM traffic is then
+// the compulsory bytes; the gathers are L2 hits.  No atomics anywhere: results are bit-reproducible.
+#include "rspmm_common.cuh"
+
+namespace ultra {
+
+namespace {
+
+constexpr int kUnroll = 4;
+
+template <typename T> struct SegArgs {
+    const int4 *task;
+    const int2 *edge;
+    const T *w;        // null when all weights are 1
+    const T *A;
+    const T *B;
+    T *out;
+    T *partial;
+    int32_t *arg_out;       // ARG only
+    int32_t *partial_arg;   // ARG only
+    long long dim;
+    int n_task;
+    int n_slab;
+};
+
+template <typename T, int SUM> __device__ __forceinline__ void reduce_into(T &acc, T m) {
+    if (SUM == ULTRA_RSPMM_SUM_ADD) acc += m;
+    else if (SUM == ULTRA_RSPMM_SUM_MAX) acc = acc > m ? acc : m;   // torchdrug NaryMax::forward
+    else acc = acc < m ? acc : m;                                  // torchdrug NaryMin::forward
+}
+
+template <typename T, int VEC, int SUM, int MSG, bool B_TABLE, bool ARG>
+__global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const SegArgs<T> a) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (gw >= (long long)a.n_task * a.n_slab) return;
+    const int slab = (int)(gw / a.n_task);
+    const int4 task = __ldg(a.task + (gw - (long long)slab * a.n_task));
+    const long long col = (long long)slab * (32 * VEC) + lane * VEC;
+    const bool active = col < a.dim;
+    const T *__restrict__ A = a.A + col;
+    const T *__restrict__ B = a.B + col;
+
+    T acc[VEC];
+    int32_t arg[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        acc[v] = reduce_identity<T, SUM>();
+        arg[v] = -1;
+    }
+
+    for (int base = task.y; base < task.z; base += 32) {
+        const int n = min(32, task.z - base);
+        int2 mine = make_int2(0, 0);
+        T mine_w = T(1);
+        if (lane < n) {
+            mine = __ldg(a.edge + base + lane);
+            if (a.w) mine_w = __ldg(a.w + base + lane);
+        }
+        for (int u = 0; u < n; u += kUnroll) {
+            Vec<T, VEC> va[kUnroll], vb[kUnroll];
+            T w[kUnroll];
+#pragma unroll
+            for (int q = 0; q < kUnroll; ++q) {
+                const int src = (u + q) & 31;
+                const long long ia = __shfl_sync(kFullMask, mine.x, src);
+                const long long ib = __shfl_sync(kFullMask, mine.y, src);
+                w[q] = shfl_value(mine_w, src);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) va[q].v[v] = vb[q].v[v] = T(0);
+                if (u + q < n && active) {
+                    gather_load(A + ia * a.dim, va[q]);
+                    if (MSG != MSG_COPY) {
+                        if (B_TABLE) table_load(B + ib * a.dim, vb[q]);
+                        else gather_load(B + ib * a.dim, vb[q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kUnroll; ++q) {
+                if (u + q < n) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const T m = message<T, MSG>(w[q], vb[q].v[v], va[q].v[v]);
+                        if (ARG) {
+                            if (SUM == ULTRA_RSPMM_SUM_MAX ? (m > acc[v]) : (m < acc[v])) arg[v] = base + u + q;
+                        }
+                        reduce_into<T, SUM>(acc[v], m);
+                    }
+                }
+            }
+        }
+    }
+    if (!active) return;
+    Vec<T, VEC> r;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r.v[v] = acc[v];
+    if (task.w < 0) {
+        stream_store(a.out + (long long)task.x * a.dim + col, r);
+    } else {
+        T *p = a.partial + (long long)task.w * a.dim + col;   // re-read soon by the combine pass: default policy
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) p[v] = r.v[v];
+    }
+    if (ARG) {
+        int32_t *p = task.w < 0 ? a.arg_out + (long long)task.x * a.dim + col
+                                : a.partial_arg + (long long)task.w * a.dim + col;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) p[v] = arg[v];
+    }
+}
+
+// Gated variant for the min/max backward (reference all-ties rule: NaryMin/NaryMax::backward = (out == y)).
+//   csc order: segment = src j, own row S = input[j], P = relation[edge.y] (table)  -> grad_input[j]
+//   rel order: segment = rel k, own row S = relation[k], P = input[edge.y] (gather)  -> grad_relation[k]
+// per edge (dst i = edge.x):  y = w * (P (x) S);  if (output[i] == y)  acc += grad_out[i] * w * (mul ? P : 1)
+template <typename T> struct GatedArgs {
+    const int4 *task;
+    const int2 *edge;
+    const T *w;
+    const T *G;   // grad_output, gathered by edge.x
+    const T *O;   // output, gathered by edge.x
+    const T *P;   // gathered / table by edge.y
+    const T *S;   // own row, by segment
+    T *out;
+    T *partial;
+    long long dim;
+    int n_task;
+    int n_slab;
+};
+
+template <typename T, int VEC, int MSG, bool P_TABLE>
+__global__ void __launch_bounds__(kThreadsPerBlock, 3) seg_gated_kernel(const GatedArgs<T> a) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (gw >= (long long)a.n_task * a.n_slab) return;
+    const int slab = (int)(gw / a.n_task);
+    const int4 task = __ldg(a.task + (gw - (long long)slab * a.n_task));
+    const long long col = (long long)slab * (32 * VEC) + lane * VEC;
+    const bool active = col < a.dim;
+
+    Vec<T, VEC> own;
+    T acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { acc[v] = T(0); own.v[v] = T(0); }
+    if (active && task.z > task.y) gather_load(a.S + (long long)task.x * a.dim + col, own);
+
+    for (int base = task.y; base < task.z; base += 32) {
+        const int n = min(32, task.z - base);
+        int2 mine = make_int2(0, 0);
+        T mine_w = T(1);
+        if (lane < n) {
+            mine = __ldg(a.edge + base + lane);
+            if (a.w) mine_w = __ldg(a.w + base + lane);
+        }
+        for (int u = 0; u < n; u += kUnroll) {
+            Vec<T, VEC> vg[kUnroll], vo[kUnroll], vp[kUnroll];
+            T w[kUnroll];
+#pragma unroll
+            for (int q = 0; q < kUnroll; ++q) {
+                const int src = (u + q) & 31;
+                const long long ia = __shfl_sync(kFullMask, mine.x, src);
+                const long long ib = __shfl_sync(kFullMask, mine.y, src);
+                w[q] = shfl_value(mine_w, src);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) vg[q].v[v] = vo[q].v[v] = vp[q].v[v] = T(0);
+                if (u + q < n && active) {
+                    gather_load(a.G + ia * a.dim + col, vg[q]);
+                    gather_load(a.O + ia * a.dim + col, vo[q]);
+                    if (P_TABLE) table_load(a.P + ib * a.dim + col, vp[q]);
+                    else gather_load(a.P + ib * a.dim + col, vp[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kUnroll; ++q) {
+                if (u + q < n) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const T y = message<T, MSG>(w[q], vp[q].v[v], own.v[v]);
+                        const T up = vg[q].v[v] * w[q];
+                        const T term = MSG == MSG_MUL ? up * vp[q].v[v] : up;
+                        if (vo[q].v[v] == y) acc[v] += term;
+                    }
+                }
+            }
+        }
+    }
+    if (!active) return;
+    T *p = task.w < 0 ? a.out + (long long)task.x * a.dim + col : a.partial + (long long)task.w * a.dim + col;
+    Vec<T, VEC> r;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r.v[v] = acc[v];
+    if (task.w < 0) stream_store(p, r);
+    else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) p[v] = r.v[v];
+    }
+}
+
+// Fixed-order fold of the partial rows of split segments (deterministic second stage).
+template <typename T, int SUM, bool ARG>
+__global__ void combine_kernel(const int4 *__restrict__ split, int n_split, const T *__restrict__ partial,
+                               const int32_t *__restrict__ partial_arg, T *__restrict__ out,
+                               int32_t *__restrict__ arg_out, long long dim) {
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= dim) return;
+    const int4 s = __ldg(split + blockIdx.y);
+    T acc = reduce_identity<T, SUM>();
+    int32_t arg = -1;
+    for (int q = 0; q < s.z; ++q) {
+        const long long at = (long long)(s.y + q) * dim + col;
+        const T m = partial[at];
+        if (ARG) {
+            if (SUM == ULTRA_RSPMM_SUM_MAX ? (m > acc) : (m < acc)) arg = partial_arg[at];
+        }
+        reduce_into<T, SUM>(acc, m);
+    }
+    out[(long long)s.x * dim + col] = acc;
+    if (ARG) arg_out[(long long)s.x * dim + col] = arg;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side dispatch
+// ------------------------------------------------------------------------------------------------
+template <typename T> constexpr int wide_vec() { return 16 / sizeof(T); }
+
+inline bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+template <typename T, int VEC, int SUM, int MSG, bool B_TABLE, bool ARG>
+int launch_seg(const SegArgs<T> &args, cudaStream_t stream) {
+    const long long warps = (long long)args.n_task * args.n_slab;
+    if (warps == 0) return ULTRA_RSPMM_OK;
+    const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks > 0x7fffffffLL) return ULTRA_RSPMM_ERR_RANGE;
+    seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    note_launch();
+    return ULTRA_RSPMM_OK;
+}
+
+template <typename T, int SUM, bool ARG>
+int launch_combine(const ultra_rspmm_order_t &order, const T *partial, const int32_t *partial_arg, T *out,
+                   int32_t *arg_out, long long dim, cudaStream_t stream) {
+    if (order.n_split == 0 || dim == 0) return ULTRA_RSPMM_OK;
+    const dim3 grid((unsigned)((dim + 255) / 256), (unsigned)order.n_split);
+    if (order.n_split > 65535) {
+        // y-dimension limit: fold in slices
+        for (int at = 0; at < order.n_split; at += 65535) {
+            const int n = order.n_split - at < 65535 ? order.n_split - at : 65535;
+            combine_kernel<T, SUM, ARG><<<dim3(grid.x, n), 256, 0, stream>>>((const int4 *)order.split + at, n, partial,
+                                                                              partial_arg, out, arg_out, dim);
+            note_launch();
+        }
+        return ULTRA_RSPMM_OK;
+    }
+    combine_kernel<T, SUM, ARG><<<grid, 256, 0, stream>>>((const int4 *)order.split, order.n_split, partial, partial_arg,
+                                                          out, arg_out, dim);
+    note_launch();
+    return ULTRA_RSPMM_OK;
+}
+
+// one reduction pass + its combine
+template <typename T, int SUM, int MSG, bool B_TABLE, bool ARG>
+int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, const T *B, T *out, int32_t *arg_out,
+             long long dim, void *workspace, cudaStream_t stream) {
+    SegArgs<T> args;
+    args.task = (const int4 *)order.task;
+    args.edge = (const int2 *)order.edge;
+    args.w = unit_weight ? nullptr : (const T *)order.w;
+    args.A = A;
+    args.B = B;
+    args.out = out;
+    args.partial = (T *)workspace;
+    args.arg_out = arg_out;
+    args.partial_arg = ARG ? (int32_t *)((char *)workspace + align_up((size_t)order.n_slot * dim * sizeof(T))) : nullptr;
+    args.dim = dim;
+    args.n_task = order.n_task;
+    constexpr int W = wide_vec<T>();
+    const bool wide = dim % W == 0 && aligned16(A) && aligned16(B) && aligned16(out) && aligned16(workspace);
+    int status;
+    if (wide) {
+        args.n_slab = (int)((dim + 32 * W - 1) / (32 * W));
+        status = launch_seg<T, W, SUM, MSG, B_TABLE, ARG>(args, stream);
+    } else {
+        args.n_slab = (int)((dim + 31) / 32);
+        status = launch_seg<T, 1, SUM, MSG, B_TABLE, ARG>(args, stream);
+    }
+    if (status) return status;
+    return launch_combine<T, SUM, ARG>(order, args.partial, args.partial_arg, out, arg_out, dim, stream);
+}
+
+template <typename T, int MSG, bool P_TABLE>
+int run_gated(const ultra_rspmm_order_t &order, bool unit_weight, const T *G, const T *O, const T *P, const T *S, T *out,
+              long long dim, void *workspace, cudaStream_t stream) {
+    GatedArgs<T> args;
+    args.task = (const int4 *)order.task;
+    args.edge = (const int2 *)order.edge;
+    args.w = unit_weight ? nullptr : (const T *)order.w;
+    args.G = G; args.O = O; args.P = P; args.S = S;
+    args.out = out;
+    args.partial = (T *)workspace;
+    args.dim = dim;
+    args.n_task = order.n_task;
+    constexpr int W = wide_vec<T>();
+    const bool wide = dim % W == 0 && aligned16(G) && aligned16(O) && aligned16(P) && aligned16(S) && aligned16(out) &&
+                      aligned16(workspace);
+    args.n_slab = wide ? (int)((dim + 32 * W - 1) / (32 * W)) : (int)((dim + 31) / 32);
+    const long long warps = (long long)args.n_task * args.n_slab;
+    if (warps > 0) {
+        const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        if (blocks > 0x7fffffffLL) return ULTRA_RSPMM_ERR_RANGE;
+        if (wide) seg_gated_kernel<T, W, MSG, P_TABLE><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        else seg_gated_kernel<T, 1, MSG, P_TABLE><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        note_launch();
+    }
+    return launch_combine<T, ULTRA_RSPMM_SUM_ADD, false>(order, args.partial, nullptr, out, nullptr, dim, stream);
+}
+
+template <typename T, int SUM>
+int forward_sum(const ultra_rspmm_index_t &ix, const T *relation, const T *input, T *output, int32_t *argidx,
+                long long dim, int mul_op, void *ws, cudaStream_t stream) {
+    const bool unit = ix.unit_weight != 0;
+    if (SUM != ULTRA_RSPMM_SUM_ADD && argidx) {
+        if (mul_op == ULTRA_RSPMM_MUL_MUL)
+            return run_pass<T, SUM, MSG_MUL, true, true>(ix.csr, unit, input, relation, output, argidx, dim, ws, stream);
+        return run_pass<T, SUM, MSG_ADD, true, true>(ix.csr, unit, input, relation, output, argidx, dim, ws, stream);
+    }
+    if (mul_op == ULTRA_RSPMM_MUL_MUL)
+        return run_pass<T, SUM, MSG_MUL, true, false>(ix.csr, unit, input, relation, output, nullptr, dim, ws, stream);
+    return run_pass<T, SUM, MSG_ADD, true, false>(ix.csr, unit, input, relation, output, nullptr, dim, ws, stream);
+}
+
+template <typename T>
+int forward_typed(const ultra_rspmm_index_t &ix, const void *relation, const void *input, void *output, int32_t *argidx,
+                  long long dim, int sum_op, int mul_op, void *ws, cudaStream_t stream) {
+    const T *r = (const T *)relation, *x = (const T *)input;
+    T *o = (T *)output;
+    switch (sum_op) {
+        case ULTRA_RSPMM_SUM_ADD: return forward_sum<T, ULTRA_RSPMM_SUM_ADD>(ix, r, x, o, nullptr, dim, mul_op, ws, stream);
+        case ULTRA_RSPMM_SUM_MIN: return forward_sum<T, ULTRA_RSPMM_SUM_MIN>(ix, r, x, o, argidx, dim, mul_op, ws, stream);
+        default: return forward_sum<T, ULTRA_RSPMM_SUM_MAX>(ix, r, x, o, argidx, dim, mul_op, ws, stream);
+    }
+}
+
+template <typename T>
+int backward_typed(const ultra_rspmm_index_t &ix, const void *relation, const void *input, const void *output,
+                   const void *grad_output, void *grad_relation, void *grad_input, long long dim, int sum_op,
+                   int mul_op, void *ws, cudaStream_t stream) {
+    const T *r = (const T *)relation, *x = (const T *)input, *o = (const T *)output, *g = (const T *)grad_output;
+    T *gr = (T *)grad_relation, *gx = (T *)grad_input;
+    const bool unit = ix.unit_weight != 0;
+    constexpr int ADD = ULTRA_RSPMM_SUM_ADD;
+    int status = ULTRA_RSPMM_OK;
+    if (sum_op == ULTRA_RSPMM_SUM_ADD) {
+        if (gx) {
+            status = mul_op == ULTRA_RSPMM_MUL_MUL
+                         ? run_pass<T, ADD, MSG_MUL, true, false>(ix.csc, unit, g, r, gx, nullptr, dim, ws, stream)
+                         : run_pass<T, ADD, MSG_COPY, true, false>(ix.csc, unit, g, r, gx, nullptr, dim, ws, stream);
+            if (status) return status;
+        }
+        if (gr) {
+            status = mul_op == ULTRA_RSPMM_MUL_MUL
+                         ? run_pass<T, ADD, MSG_MUL, false, false>(ix.rel, unit, g, x, gr, nullptr, dim, ws, stream)
+                         : run_pass<T, ADD, MSG_COPY, true, false>(ix.rel, unit, g, x, gr, nullptr, dim, ws, stream);
+        }
+        return status;
+    }
+    if (gx) {
+        status = mul_op == ULTRA_RSPMM_MUL_MUL ? run_gated<T, MSG_MUL, true>(ix.csc, unit, g, o, r, x, gx, dim, ws, stream)
+                                               : run_gated<T, MSG_ADD, true>(ix.csc, unit, g, o, r, x, gx, dim, ws, stream);
+        if (status) return status;
+    }
+    if (gr) {
+        status = mul_op == ULTRA_RSPMM_MUL_MUL ? run_gated<T, MSG_MUL, false>(ix.rel, unit, g, o, x, r, gr, dim, ws, stream)
+                                               : run_gated<T, MSG_ADD, false>(ix.rel, unit, g, o, x, r, gr, dim, ws, stream);
+    }
+    return status;
+}
+
+int check_call(const ultra_rspmm_index_t *index, int64_t dim, int32_t dtype, int32_t sum_op, int32_t mul_op) {
+    if (!index || dim < 0) return ULTRA_RSPMM_ERR_ARG;
+    if (dtype != ULTRA_RSPMM_F32 && dtype != ULTRA_RSPMM_F64) return ULTRA_RSPMM_ERR_ARG;
+    if (dtype != index->dtype) return ULTRA_RSPMM_ERR_DTYPE;
+    if (sum_op < 0 || sum_op > 2 || mul_op < 0 || mul_op > 1) return ULTRA_RSPMM_ERR_ARG;
+    return ULTRA_RSPMM_OK;
+}
+
+size_t pass_bytes(const ultra_rspmm_order_t &order, int64_t dim, size_t elem, bool with_arg) {
+    size_t bytes = align_up((size_t)order.n_slot * dim * elem);
+    if (with_arg) bytes += align_up((size_t)order.n_slot * dim * sizeof(int32_t));
+    return bytes;
+}
+
+}  // namespace
+
+}  // namespace ultra
+
+using namespace ultra;
+
+extern "C" int ultra_rspmm_workspace_bytes(const ultra_rspmm_index_t *index, int64_t dim, int32_t dtype,
+                                           size_t *forward_bytes, size_t *backward_bytes) {
+    if (!index || dim < 0 || (dtype != ULTRA_RSPMM_F32 && dtype != ULTRA_RSPMM_F64)) return ULTRA_RSPMM_ERR_ARG;
+    const size_t elem = dtype == ULTRA_RSPMM_F32 ? 4 : 8;
+    if (forward_bytes) *forward_bytes = pass_bytes(index->csr, dim, elem, true);
+    if (backward_bytes) {
+        const size_t a = pass_bytes(index->csc, dim, elem, false), b = pass_bytes(index->rel, dim, elem, false);
+        *backward_bytes = a > b ? a : b;
+    }
+    return ULTRA_RSPMM_OK;
+}
+
+extern "C" int ultra_rspmm_forward(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
+                                   void *dev_output, int32_t *dev_argidx, int64_t dim, int32_t dtype, int32_t sum_op,
+                                   int32_t mul_op, void *workspace, size_t workspace_bytes, void *stream) {
+    int status = check_call(index, dim, dtype, sum_op, mul_op);
+    if (status) return status;
+    if (index->n_out == 0 || dim == 0) return ULTRA_RSPMM_OK;
+    if (!dev_output || ((index->n_rel > 0 && !dev_relation) || (index->n_in > 0 && !dev_input)))
+        return ULTRA_RSPMM_ERR_ARG;
+    const bool with_arg = dev_argidx && sum_op != ULTRA_RSPMM_SUM_ADD;
+    const size_t need = pass_bytes(index->csr, dim, dtype == ULTRA_RSPMM_F32 ? 4 : 8, with_arg);
+    if (index->csr.n_slot > 0 && (!workspace || workspace_bytes < need)) return ULTRA_RSPMM_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    status = dtype == ULTRA_RSPMM_F32
+                 ? forward_typed<float>(*index, dev_relation, dev_input, dev_output, dev_argidx, dim, sum_op, mul_op, workspace, s)
+                 : forward_typed<double>(*index, dev_relation, dev_input, dev_output, dev_argidx, dim, sum_op, mul_op, workspace, s);
+    if (status) return status;
+    ULTRA_CUDA_OK(cudaGetLastError());
+    return ULTRA_RSPMM_OK;
+}
+
+extern "C" int ultra_rspmm_backward(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
+                                    const void *dev_output, const void *dev_grad_output, void *dev_grad_relation,
+                                    void *dev_grad_input, int64_t dim, int32_t dtype, int32_t sum_op, int32_t mul_op,
+                                    void *workspace, size_t workspace_bytes, void *stream) {
+    int status = check_call(index, dim, dtype, sum_op, mul_op);
+    if (status) return status;
+    if (dim == 0 || (!dev_grad_relation && !dev_grad_input)) return ULTRA_RSPMM_OK;
+    if (index->n_out > 0 && !dev_grad_output) return ULTRA_RSPMM_ERR_ARG;
+    if (sum_op != ULTRA_RSPMM_SUM_ADD && index->n_out > 0 && !dev_output) return ULTRA_RSPMM_ERR_ARG;
+    if ((index->n_rel > 0 && !dev_relation) || (index->n_in > 0 && !dev_input)) return ULTRA_RSPMM_ERR_ARG;
+    const size_t elem = dtype == ULTRA_RSPMM_F32 ? 4 : 8;
+    size_t need = 0;
+    if (dev_grad_input) need = pass_bytes(index->csc, dim, elem, false);
+    if (dev_grad_relation) {
+        const size_t b = pass_bytes(index->rel, dim, elem, false);
+        need = b > need ? b : need;
+    }
+    const bool uses_slots = (dev_grad_input && index->csc.n_slot > 0) || (dev_grad_relation && index->rel.n_slot > 0);
+    if (uses_slots && (!workspace || workspace_bytes < need)) return ULTRA_RSPMM_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    status = dtype == ULTRA_RSPMM_F32
+                 ? backward_typed<float>(*index, dev_relation, dev_input, dev_output, dev_grad_output, dev_grad_relation,
+                                         dev_grad_input, dim, sum_op, mul_op, workspace, s)
+                 : backward_typed<double>(*index, dev_relation, dev_input, dev_output, dev_grad_output, dev_grad_relation,
+                                          dev_grad_input, dim, sum_op, mul_op, workspace, s);
+    if (status) return status;
+    ULTRA_CUDA_OK(cudaGetLastError());
+    return ULTRA_RSPMM_OK;
+}

@@ -1,0 +1,283 @@
+"""`generalized_rspmm` - the drop-in operator behind `torchdrug.layers.functional.generalized_rspmm`.
+
+Reference call sites: ultra/layer.py:134-167 (GeneralizedRelationalConvNBF) and :336-369
+(GeneralizedRelationalConvNBFMod).  Signature, operand layout, error behaviour and autograd
+semantics mirror torchdrug's `layers/functional/spmm.py` (un-vendored):
+
+    generalized_rspmm(sparse, relation, input, sum="add", mul="mul") -> Tensor
+        out[i, :] = (sum)_{(i, j, k) in sparse} w_ijk * (relation[k, :] (mul) input[j, :])
+
+Everything below the Python argument checks runs in `libultra_rspmm.so` (hand-written sm_100a kernels
+behind the C ABI of `include/ultra_rspmm.h`).  There is no CPU path: CPU tensors raise.
+"""
+import collections
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+
+__all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count"]
+
+_SUM_OPS = ("add", "min", "max")
+_MUL_OPS = ("mul", "add")
+_DTYPE_CODE = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+INDEX_CACHE_SIZE = int(os.environ.get("ULTRA_RSPMM_INDEX_CACHE", "8"))
+_index_cache = collections.OrderedDict()
+#: statistics for tests / benchmarks: how the index of each call was obtained
+cache_stats = {"attached": 0, "fingerprint_hit": 0, "built": 0}
+
+
+def _stream_handle():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(tensor):
+    """Raw device address (NULL for None / empty tensors)."""
+    if tensor is None or tensor.numel() == 0:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(tensor.data_ptr())
+
+
+class GraphIndex(object):
+    """Device-resident int32 edge orders (CSR / CSC / by-relation) + task lists of one coalesced operand.
+
+    Replaces the per-call `adjacency.transpose(0, 1)` -> `coalesce()` -> `coo2csr3d` of the reference
+    (SURVEY.md section 8 row a5): built once per distinct edge set, shared by all layers and by backward.
+    """
+
+    def __init__(self, indices, values, shape):
+        if indices.dim() != 2 or indices.shape[0] != 3 or indices.dtype != torch.int64:
+            raise RuntimeError("Expect `sparse` to have 3 sparse dims with int64 indices, got %s %s"
+                               % (tuple(indices.shape), indices.dtype))
+        if values.dtype not in _DTYPE_CODE:
+            raise RuntimeError("generalized_rspmm supports float32 and float64, got %s" % values.dtype)
+        if not indices.is_cuda:
+            raise RuntimeError("generalized_rspmm has no CPU implementation: `sparse` must live on a CUDA device")
+        lib = _lib.lib()
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = values.dtype
+        self.device = indices.device
+        nnz = indices.shape[1]
+        if indices.stride(1) != 1:
+            indices = indices.contiguous()
+        values = values.contiguous()
+        code = _DTYPE_CODE[values.dtype]
+        index_bytes, scratch_bytes = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(lib.ultra_rspmm_index_bytes(nnz, self.shape[0], self.shape[1], self.shape[2], code,
+                                               ctypes.byref(index_bytes), ctypes.byref(scratch_bytes)),
+                   "ultra_rspmm_index_bytes")
+        with torch.cuda.device(self.device):
+            self.buffer = torch.empty(max(index_bytes.value, 256), dtype=torch.uint8, device=self.device)
+            scratch = torch.empty(max(scratch_bytes.value, 256), dtype=torch.uint8, device=self.device)
+            self.c = _lib.Index()
+            _lib.check(lib.ultra_rspmm_index_build(
+                _ptr(indices), indices.stride(0) if nnz else 0, _ptr(values), nnz, self.shape[0], self.shape[1],
+                self.shape[2], code, self.buffer.data_ptr(), self.buffer.numel(), scratch.data_ptr(),
+                scratch.numel(), ctypes.byref(self.c), _stream_handle()), "ultra_rspmm_index_build")
+        del scratch
+        self.nnz = int(self.c.nnz)
+        self._workspace_bytes = {}
+
+    def workspace_bytes(self, dim):
+        if dim not in self._workspace_bytes:
+            forward, backward = ctypes.c_size_t(), ctypes.c_size_t()
+            _lib.check(_lib.lib().ultra_rspmm_workspace_bytes(ctypes.byref(self.c), dim, _DTYPE_CODE[self.dtype],
+                                                              ctypes.byref(forward), ctypes.byref(backward)),
+                       "ultra_rspmm_workspace_bytes")
+            self._workspace_bytes[dim] = (forward.value, backward.value)
+        return self._workspace_bytes[dim]
+
+    # -- raw operator calls (device tensors in, device tensors out) ---------------------------------
+    def forward(self, relation, input, sum="add", mul="mul", return_argidx=False):
+        dim = input.shape[1]
+        output = torch.empty((self.shape[0], dim), dtype=input.dtype, device=input.device)
+        argidx = None
+        if return_argidx and sum != "add":
+            argidx = torch.empty((self.shape[0], dim), dtype=torch.int32, device=input.device)
+        need = self.workspace_bytes(dim)[0]
+        with torch.cuda.device(input.device):
+            workspace = torch.empty(need, dtype=torch.uint8, device=input.device) if need else None
+            _lib.check(_lib.lib().ultra_rspmm_forward(
+                ctypes.byref(self.c), _ptr(relation), _ptr(input), _ptr(output), _ptr(argidx), dim,
+                _DTYPE_CODE[self.dtype], _lib.SUM_CODE[sum], _lib.MUL_CODE[mul], _ptr(workspace), need,
+                _stream_handle()), "ultra_rspmm_forward")
+        return (output, argidx) if return_argidx else output
+
+    def backward(self, relation, input, output, grad_output, sum="add", mul="mul", need_relation=True,
+                 need_input=True):
+        dim = input.shape[1]
+        grad_relation = torch.empty_like(relation) if need_relation else None
+        grad_input = torch.empty_like(input) if need_input else None
+        need = self.workspace_bytes(dim)[1]
+        with torch.cuda.device(input.device):
+            workspace = torch.empty(need, dtype=torch.uint8, device=input.device) if need else None
+            _lib.check(_lib.lib().ultra_rspmm_backward(
+                ctypes.byref(self.c), _ptr(relation), _ptr(input), _ptr(output), _ptr(grad_output),
+                _ptr(grad_relation), _ptr(grad_input), dim, _DTYPE_CODE[self.dtype], _lib.SUM_CODE[sum],
+                _lib.MUL_CODE[mul], _ptr(workspace), need, _stream_handle()), "ultra_rspmm_backward")
+        return grad_relation, grad_input
+
+
+def clear_index_cache():
+    _index_cache.clear()
+
+
+def launch_count(reset=False):
+    """Kernels enqueued by the library so far (`gpu_launches` in bench.py)."""
+    lib = _lib.lib()
+    count = int(lib.ultra_rspmm_launch_count())
+    if reset:
+        lib.ultra_rspmm_launch_count_reset()
+    return count
+
+
+def _fingerprint(indices, values):
+    out = torch.empty(2, dtype=torch.int64, device=indices.device)
+    with torch.cuda.device(indices.device):
+        _lib.check(_lib.lib().ultra_rspmm_fingerprint(
+            _ptr(indices), indices.stride(0) if indices.shape[1] else 0, _ptr(values), indices.shape[1],
+            _DTYPE_CODE[values.dtype], out.data_ptr(), _stream_handle()), "ultra_rspmm_fingerprint")
+    return tuple(out.tolist())
+
+
+def graph_index(sparse):
+    """The (cached) `GraphIndex` of a sparse COO operand of shape (n_out, n_in, n_rel).
+
+    Lookup order: (1) an index attached to this very tensor object by an earlier call (valid while the
+    indices/values version counters are unchanged); (2) a content fingerprint of (indices, values) computed
+    on the device, looked up in a small LRU - this is what makes the 6 layers of a forward (each passes a
+    fresh `adjacency.transpose(0, 1)`, layer.py:127,328) share one build; (3) build.
+    """
+    indices, values = sparse._indices(), sparse._values()
+    versions = (indices._version, values._version)
+    attached = getattr(sparse, "_ultra_rspmm_index", None)
+    if attached is not None and attached[1] == versions and attached[0].dtype == values.dtype:
+        cache_stats["attached"] += 1
+        return attached[0]
+    if indices.shape[0] != 3:
+        raise RuntimeError("Expect `sparse` to have 3 sparse dims, but found %d" % indices.shape[0])
+    if values.dtype not in _DTYPE_CODE:
+        raise RuntimeError("generalized_rspmm supports float32 and float64, got %s" % values.dtype)
+    if indices.stride(1) != 1:
+        indices = indices.contiguous()
+    values = values.detach().contiguous()
+    key = (_fingerprint(indices, values), tuple(sparse.shape), values.dtype, indices.device, indices.shape[1])
+    index = _index_cache.get(key)
+    if index is None:
+        index = GraphIndex(indices, values, sparse.shape)
+        cache_stats["built"] += 1
+        _index_cache[key] = index
+        while len(_index_cache) > max(INDEX_CACHE_SIZE, 1):
+            _index_cache.popitem(last=False)
+    else:
+        cache_stats["fingerprint_hit"] += 1
+        _index_cache.move_to_end(key)
+    try:
+        sparse._ultra_rspmm_index = (index, versions)
+    except Exception:
+        pass
+    return index
+
+
+def _check_operands(sparse, relation, input):
+    """Argument checks of torchdrug's `rspmm_forward_check` (TORCH_CHECK -> RuntimeError)."""
+    if not isinstance(sparse, torch.Tensor) or sparse.layout != torch.sparse_coo:
+        raise RuntimeError("Expect `sparse` to be a sparse COO tensor")
+    if sparse.sparse_dim() != 3 or sparse.dense_dim() != 0:
+        raise RuntimeError("Expect `sparse` to be a 3D sparse tensor, but found %dD sparse / %dD dense"
+                           % (sparse.sparse_dim(), sparse.dense_dim()))
+    if relation.dim() != 2:
+        raise RuntimeError("Expect `relation` to be a 2D tensor, but found %dD" % relation.dim())
+    if input.dim() != 2:
+        raise RuntimeError("Expect `input` to be a 2D tensor, but found %dD" % input.dim())
+    if not (sparse.dtype == relation.dtype == input.dtype):
+        raise RuntimeError("Expect all tensors to have the same dtype, but found %s, %s and %s"
+                           % (sparse.dtype, relation.dtype, input.dtype))
+    if not (sparse.device == relation.device == input.device):
+        raise RuntimeError("Expect all tensors to be on the same device, but found %s, %s and %s"
+                           % (sparse.device, relation.device, input.device))
+    if not input.is_cuda:
+        raise RuntimeError("generalized_rspmm (B200 build) has no CPU implementation; tensors must be on a CUDA device")
+    if sparse.size(1) != input.size(0):
+        raise RuntimeError("Expect sparse.size(1) == input.size(0), but found %d and %d" % (sparse.size(1), input.size(0)))
+    if sparse.size(2) != relation.size(0):
+        raise RuntimeError("Expect sparse.size(2) == relation.size(0), but found %d and %d"
+                           % (sparse.size(2), relation.size(0)))
+    if relation.size(1) != input.size(1):
+        raise RuntimeError("Expect relation.size(1) == input.size(1), but found %d and %d"
+                           % (relation.size(1), input.size(1)))
+
+
+def _forward(ctx, sum, mul, sparse, relation, input):
+    _check_operands(sparse, relation, input)
+    if sparse.requires_grad:
+        raise RuntimeError("gradient w.r.t. the sparse values is outside the rspmm hot path "
+                           "(reference layer.py:112,299 use message()+aggregate() when graph.requires_grad)")
+    index = graph_index(sparse)
+    relation = relation.contiguous()
+    input = input.contiguous()
+    output = index.forward(relation, input, sum, mul)
+    ctx.index = index
+    if sum == "add":
+        ctx.save_for_backward(relation, input)
+    else:
+        ctx.save_for_backward(relation, input, output)
+    return output
+
+
+def _backward(ctx, sum, mul, output_grad):
+    saved = ctx.saved_tensors
+    relation, input = saved[0], saved[1]
+    output = saved[2] if len(saved) > 2 else None
+    relation_grad, input_grad = ctx.index.backward(
+        relation, input, output, output_grad.contiguous(), sum, mul,
+        need_relation=ctx.needs_input_grad[1], need_input=ctx.needs_input_grad[2])
+    return None, relation_grad, input_grad
+
+
+def _make_function(sum, mul):
+    """RSPMM{Add,Min,Max}{Mul,Add}Function (torchdrug `spmm.py` naming).  forward saves
+    (relation, input[, output]); backward returns (None, relation_grad, input_grad) - the gradient w.r.t.
+    the sparse values is only produced by the reference when `sparse.requires_grad`, which the hot path
+    never requests (layer.py:112,299 route that case to message()+aggregate())."""
+    name = "RSPMM%s%sFunction" % (sum.capitalize(), mul.capitalize())
+
+    def forward(ctx, sparse, relation, input):
+        return _forward(ctx, sum, mul, sparse, relation, input)
+
+    def backward(ctx, output_grad):
+        return _backward(ctx, sum, mul, output_grad)
+
+    function = type(name, (torch.autograd.Function,), {
+        "forward": staticmethod(forward), "backward": staticmethod(backward), "sum": sum, "mul": mul,
+        "__doc__": _make_function.__doc__})
+    return name, function
+
+
+for _sum in _SUM_OPS:
+    for _mul in _MUL_OPS:
+        _name, _function = _make_function(_sum, _mul)
+        globals()[_name] = _function
+        __all__.append(_name)
+
+
+def generalized_rspmm(sparse, relation, input, sum="add", mul="mul"):
+    r"""Generalized relational sparse-dense matrix multiplication (torchdrug semantics).
+
+    .. math:: output_{i,l} = \bigoplus_{(i,j,k) \in sparse} sparse_{i,j,k} \cdot (relation_{k,l} \otimes input_{j,l})
+
+    Parameters:
+        sparse (SparseTensor): 3D sparse COO tensor (n_out, n_in, n_rel); need not be coalesced
+        relation (Tensor): (n_rel, dim)
+        input (Tensor): (n_in, dim)
+        sum (str): "add", "min" or "max"
+        mul (str): "mul" (DistMult) or "add" (TransE)
+    """
+    name = "RSPMM%s%sFunction" % (str(sum).capitalize(), str(mul).capitalize())
+    if sum not in _SUM_OPS or mul not in _MUL_OPS:
+        raise ValueError("No generalized rspmm implementation found for summation `%s` and multiplication `%s`"
+                         % (sum, mul))
+    return globals()[name].apply(sparse, relation, input)
