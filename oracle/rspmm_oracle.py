@@ -70,7 +70,11 @@ def coalesce(indices, values, shape):
     first = np.ones(len(key), dtype=bool)
     first[1:] = key[1:] != key[:-1]
     starts = np.flatnonzero(first)
-    merged = np.add.reduceat(values[order].astype(np.float64), starts).astype(values.dtype)
+    # duplicates are summed sequentially in stable (original) order, in fp64, then rounded once -
+    # np.add.at is unbuffered and in-order (np.add.reduceat may re-associate), the CUDA index build does the same
+    merged = np.zeros(len(starts), dtype=np.float64)
+    np.add.at(merged, np.cumsum(first) - 1, values[order].astype(np.float64))
+    merged = merged.astype(values.dtype)
     return indices[:, order[starts]], merged, order[starts]
 
 

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) probe(const float4 *__restrict__ buf, lon
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             state = state * 6364136223846793005ULL + 1442695040888963407ULL;
-            const long long row = (long long)((state >> 33) % (unsigned long long)rows);
+            const long long row = (long long)__umulhi((unsigned)(state >> 32), (unsigned)rows);  // cheap range reduction
             const float4 *p = buf + row * 32 + lane;
             if (NOALLOC)
                 asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

@@ -106,6 +106,13 @@ template <typename T, int MSG> __device__ __forceinline__ T message(T w, T r, T 
     return w * x;
 }
 
+// unit-weight form: 1 * v == v exactly, so the multiply is dropped
+template <typename T, int MSG> __device__ __forceinline__ T message(T r, T x) {
+    if (MSG == MSG_MUL) return r * x;
+    if (MSG == MSG_ADD) return r + x;
+    return x;
+}
+
 // launch bookkeeping (claimed in bench.py as `gpu_launches`)
 void note_launch();
 // per-thread status plumbing shared by the translation units

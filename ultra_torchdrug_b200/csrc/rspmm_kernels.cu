@@ -45,17 +45,32 @@ template <typename T, int SUM> __device__ __forceinline__ void reduce_into(T &ac
     else acc = acc < m ? acc : m;                                  // torchdrug NaryMin::forward
 }
 
-template <typename T, int VEC, int SUM, int MSG, bool B_TABLE, bool ARG>
+// row address = base + row * row_bytes as one IMAD.WIDE.U32 (row ids are int32 >= 0, row_bytes < 2^32)
+template <typename T> __device__ __forceinline__ const T *row_ptr(const char *base, int row, unsigned row_bytes) {
+    return reinterpret_cast<const T *>(base + (unsigned long long)(unsigned)row * row_bytes);
+}
+
+// The issue-slot budget of the inner loop is what bounds these kernels once the gathers are L2 hits
+// (profiles/r01: 77% issue-active at 46 instructions per edge and slab in the first version).  Per edge
+// and warp the loop below is: 1 LDS.64 (edge ids staged in shared memory by the whole warp, broadcast
+// read), 2 IMAD.WIDE (row addresses), 2 LDG.128, VEC FFMA - no shuffles, no predicates; the ragged tail
+// of a task runs in a separate single-edge loop.
+template <typename T, int VEC, int SUM, int MSG, bool B_TABLE, bool ARG, bool UNIT>
 __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const SegArgs<T> a) {
+    __shared__ int2 s_edge[kWarpsPerBlock][32];
+    __shared__ T s_w[UNIT ? 1 : kWarpsPerBlock][32];
     const int lane = threadIdx.x & 31;
-    const long long gw = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (gw >= (long long)a.n_task * a.n_slab) return;
+    const int warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    if (gw >= (long long)a.n_task * a.n_slab) return;   // warps never meet at a block barrier
     const int slab = (int)(gw / a.n_task);
     const int4 task = __ldg(a.task + (gw - (long long)slab * a.n_task));
     const long long col = (long long)slab * (32 * VEC) + lane * VEC;
     const bool active = col < a.dim;
-    const T *__restrict__ A = a.A + col;
-    const T *__restrict__ B = a.B + col;
+    const long long safe_col = active ? col : 0;   // idle lanes (dim % (32 * VEC) != 0) read column 0, store nothing
+    const unsigned row_bytes = (unsigned)(a.dim * sizeof(T));
+    const char *A = reinterpret_cast<const char *>(a.A + safe_col);
+    const char *B = reinterpret_cast<const char *>(a.B + safe_col);
 
     T acc[VEC];
     int32_t arg[VEC];
@@ -65,46 +80,64 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
         arg[v] = -1;
     }
 
+    auto accumulate = [&](const Vec<T, VEC> &va, const Vec<T, VEC> &vb, T w, int position) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const T m = UNIT ? message<T, MSG>(vb.v[v], va.v[v]) : message<T, MSG>(w, vb.v[v], va.v[v]);
+            if (ARG) {
+                if (SUM == ULTRA_RSPMM_SUM_MAX ? (m > acc[v]) : (m < acc[v])) arg[v] = position;
+            }
+            reduce_into<T, SUM>(acc[v], m);
+        }
+    };
+
+    int2 ahead = make_int2(0, 0);
+    T ahead_w = T(1);
+    if (task.y + lane < task.z) {
+        ahead = __ldg(a.edge + task.y + lane);
+        if (!UNIT) ahead_w = __ldg(a.w + task.y + lane);
+    }
     for (int base = task.y; base < task.z; base += 32) {
         const int n = min(32, task.z - base);
-        int2 mine = make_int2(0, 0);
-        T mine_w = T(1);
-        if (lane < n) {
-            mine = __ldg(a.edge + base + lane);
-            if (a.w) mine_w = __ldg(a.w + base + lane);
+        __syncwarp();
+        s_edge[warp][lane] = ahead;
+        if (!UNIT) s_w[warp][lane] = ahead_w;
+        __syncwarp();
+        if (base + 32 + lane < task.z) {   // next batch's edge ids travel while this batch is reduced
+            ahead = __ldg(a.edge + base + 32 + lane);
+            if (!UNIT) ahead_w = __ldg(a.w + base + 32 + lane);
         }
-        for (int u = 0; u < n; u += kUnroll) {
+        int u = 0;
+        for (; u + kUnroll <= n; u += kUnroll) {
             Vec<T, VEC> va[kUnroll], vb[kUnroll];
             T w[kUnroll];
 #pragma unroll
             for (int q = 0; q < kUnroll; ++q) {
-                const int src = (u + q) & 31;
-                const long long ia = __shfl_sync(kFullMask, mine.x, src);
-                const long long ib = __shfl_sync(kFullMask, mine.y, src);
-                w[q] = shfl_value(mine_w, src);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) va[q].v[v] = vb[q].v[v] = T(0);
-                if (u + q < n && active) {
-                    gather_load(A + ia * a.dim, va[q]);
-                    if (MSG != MSG_COPY) {
-                        if (B_TABLE) table_load(B + ib * a.dim, vb[q]);
-                        else gather_load(B + ib * a.dim, vb[q]);
-                    }
+                const int2 e = s_edge[warp][u + q];
+                w[q] = UNIT ? T(1) : s_w[warp][u + q];
+                gather_load(row_ptr<T>(A, e.x, row_bytes), va[q]);
+                if (MSG != MSG_COPY) {
+                    if (B_TABLE) table_load(row_ptr<T>(B, e.y, row_bytes), vb[q]);
+                    else gather_load(row_ptr<T>(B, e.y, row_bytes), vb[q]);
+                } else {
+                    vb[q] = va[q];
                 }
             }
 #pragma unroll
-            for (int q = 0; q < kUnroll; ++q) {
-                if (u + q < n) {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const T m = message<T, MSG>(w[q], vb[q].v[v], va[q].v[v]);
-                        if (ARG) {
-                            if (SUM == ULTRA_RSPMM_SUM_MAX ? (m > acc[v]) : (m < acc[v])) arg[v] = base + u + q;
-                        }
-                        reduce_into<T, SUM>(acc[v], m);
-                    }
-                }
+            for (int q = 0; q < kUnroll; ++q) accumulate(va[q], vb[q], w[q], base + u + q);
+        }
+        for (; u < n; ++u) {
+            Vec<T, VEC> va, vb;
+            const int2 e = s_edge[warp][u];
+            const T w = UNIT ? T(1) : s_w[warp][u];
+            gather_load(row_ptr<T>(A, e.x, row_bytes), va);
+            if (MSG != MSG_COPY) {
+                if (B_TABLE) table_load(row_ptr<T>(B, e.y, row_bytes), vb);
+                else gather_load(row_ptr<T>(B, e.y, row_bytes), vb);
+            } else {
+                vb = va;
             }
+            accumulate(va, vb, w, base + u);
         }
     }
     if (!active) return;
@@ -145,60 +178,82 @@ template <typename T> struct GatedArgs {
     int n_slab;
 };
 
-template <typename T, int VEC, int MSG, bool P_TABLE>
+template <typename T, int VEC, int MSG, bool P_TABLE, bool UNIT>
 __global__ void __launch_bounds__(kThreadsPerBlock, 3) seg_gated_kernel(const GatedArgs<T> a) {
+    __shared__ int2 s_edge[kWarpsPerBlock][32];
+    __shared__ T s_w[UNIT ? 1 : kWarpsPerBlock][32];
     const int lane = threadIdx.x & 31;
-    const long long gw = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * kWarpsPerBlock + warp;
     if (gw >= (long long)a.n_task * a.n_slab) return;
     const int slab = (int)(gw / a.n_task);
     const int4 task = __ldg(a.task + (gw - (long long)slab * a.n_task));
     const long long col = (long long)slab * (32 * VEC) + lane * VEC;
     const bool active = col < a.dim;
+    const long long safe_col = active ? col : 0;
+    const unsigned row_bytes = (unsigned)(a.dim * sizeof(T));
+    const char *G = reinterpret_cast<const char *>(a.G + safe_col);
+    const char *O = reinterpret_cast<const char *>(a.O + safe_col);
+    const char *P = reinterpret_cast<const char *>(a.P + safe_col);
 
     Vec<T, VEC> own;
     T acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { acc[v] = T(0); own.v[v] = T(0); }
-    if (active && task.z > task.y) gather_load(a.S + (long long)task.x * a.dim + col, own);
+    if (task.z > task.y) gather_load(a.S + (long long)task.x * a.dim + safe_col, own);
 
+    auto accumulate = [&](const Vec<T, VEC> &vg, const Vec<T, VEC> &vo, const Vec<T, VEC> &vp, T w) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const T y = UNIT ? message<T, MSG>(vp.v[v], own.v[v]) : message<T, MSG>(w, vp.v[v], own.v[v]);
+            const T up = UNIT ? vg.v[v] : vg.v[v] * w;
+            const T term = MSG == MSG_MUL ? up * vp.v[v] : up;
+            if (vo.v[v] == y) acc[v] += term;
+        }
+    };
+
+    int2 ahead = make_int2(0, 0);
+    T ahead_w = T(1);
+    if (task.y + lane < task.z) {
+        ahead = __ldg(a.edge + task.y + lane);
+        if (!UNIT) ahead_w = __ldg(a.w + task.y + lane);
+    }
+    constexpr int kGatedUnroll = 2;
     for (int base = task.y; base < task.z; base += 32) {
         const int n = min(32, task.z - base);
-        int2 mine = make_int2(0, 0);
-        T mine_w = T(1);
-        if (lane < n) {
-            mine = __ldg(a.edge + base + lane);
-            if (a.w) mine_w = __ldg(a.w + base + lane);
+        __syncwarp();
+        s_edge[warp][lane] = ahead;
+        if (!UNIT) s_w[warp][lane] = ahead_w;
+        __syncwarp();
+        if (base + 32 + lane < task.z) {
+            ahead = __ldg(a.edge + base + 32 + lane);
+            if (!UNIT) ahead_w = __ldg(a.w + base + 32 + lane);
         }
-        for (int u = 0; u < n; u += kUnroll) {
-            Vec<T, VEC> vg[kUnroll], vo[kUnroll], vp[kUnroll];
-            T w[kUnroll];
+        int u = 0;
+        for (; u + kGatedUnroll <= n; u += kGatedUnroll) {
+            Vec<T, VEC> vg[kGatedUnroll], vo[kGatedUnroll], vp[kGatedUnroll];
+            T w[kGatedUnroll];
 #pragma unroll
-            for (int q = 0; q < kUnroll; ++q) {
-                const int src = (u + q) & 31;
-                const long long ia = __shfl_sync(kFullMask, mine.x, src);
-                const long long ib = __shfl_sync(kFullMask, mine.y, src);
-                w[q] = shfl_value(mine_w, src);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) vg[q].v[v] = vo[q].v[v] = vp[q].v[v] = T(0);
-                if (u + q < n && active) {
-                    gather_load(a.G + ia * a.dim + col, vg[q]);
-                    gather_load(a.O + ia * a.dim + col, vo[q]);
-                    if (P_TABLE) table_load(a.P + ib * a.dim + col, vp[q]);
-                    else gather_load(a.P + ib * a.dim + col, vp[q]);
-                }
+            for (int q = 0; q < kGatedUnroll; ++q) {
+                const int2 e = s_edge[warp][u + q];
+                w[q] = UNIT ? T(1) : s_w[warp][u + q];
+                gather_load(row_ptr<T>(G, e.x, row_bytes), vg[q]);
+                gather_load(row_ptr<T>(O, e.x, row_bytes), vo[q]);
+                if (P_TABLE) table_load(row_ptr<T>(P, e.y, row_bytes), vp[q]);
+                else gather_load(row_ptr<T>(P, e.y, row_bytes), vp[q]);
             }
 #pragma unroll
-            for (int q = 0; q < kUnroll; ++q) {
-                if (u + q < n) {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const T y = message<T, MSG>(w[q], vp[q].v[v], own.v[v]);
-                        const T up = vg[q].v[v] * w[q];
-                        const T term = MSG == MSG_MUL ? up * vp[q].v[v] : up;
-                        if (vo[q].v[v] == y) acc[v] += term;
-                    }
-                }
-            }
+            for (int q = 0; q < kGatedUnroll; ++q) accumulate(vg[q], vo[q], vp[q], w[q]);
+        }
+        for (; u < n; ++u) {
+            Vec<T, VEC> vg, vo, vp;
+            const int2 e = s_edge[warp][u];
+            const T w = UNIT ? T(1) : s_w[warp][u];
+            gather_load(row_ptr<T>(G, e.x, row_bytes), vg);
+            gather_load(row_ptr<T>(O, e.x, row_bytes), vo);
+            if (P_TABLE) table_load(row_ptr<T>(P, e.y, row_bytes), vp);
+            else gather_load(row_ptr<T>(P, e.y, row_bytes), vp);
+            accumulate(vg, vo, vp, w);
         }
     }
     if (!active) return;
@@ -247,8 +302,11 @@ int launch_seg(const SegArgs<T> &args, cudaStream_t stream) {
     const long long warps = (long long)args.n_task * args.n_slab;
     if (warps == 0) return ULTRA_RSPMM_OK;
     const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (blocks > 0x7fffffffLL) return ULTRA_RSPMM_ERR_RANGE;
-    seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    if (blocks > 0x7fffffffLL || args.dim * (long long)sizeof(T) > 0xffffffffLL) return ULTRA_RSPMM_ERR_RANGE;
+    if (args.w)
+        seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    else
+        seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
     note_launch();
     return ULTRA_RSPMM_OK;
 }
@@ -323,9 +381,14 @@ int run_gated(const ultra_rspmm_order_t &order, bool unit_weight, const T *G, co
     const long long warps = (long long)args.n_task * args.n_slab;
     if (warps > 0) {
         const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        if (blocks > 0x7fffffffLL) return ULTRA_RSPMM_ERR_RANGE;
-        if (wide) seg_gated_kernel<T, W, MSG, P_TABLE><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
-        else seg_gated_kernel<T, 1, MSG, P_TABLE><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        if (blocks > 0x7fffffffLL || dim * (long long)sizeof(T) > 0xffffffffLL) return ULTRA_RSPMM_ERR_RANGE;
+        if (wide) {
+            if (args.w) seg_gated_kernel<T, W, MSG, P_TABLE, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+            else seg_gated_kernel<T, W, MSG, P_TABLE, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        } else {
+            if (args.w) seg_gated_kernel<T, 1, MSG, P_TABLE, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+            else seg_gated_kernel<T, 1, MSG, P_TABLE, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        }
         note_launch();
     }
     return launch_combine<T, ULTRA_RSPMM_SUM_ADD, false>(order, args.partial, nullptr, out, nullptr, dim, stream);
