@@ -97,9 +97,11 @@ const char *ultra_rspmm_status_string(int status);
 int64_t ultra_rspmm_launch_count(void);
 void ultra_rspmm_launch_count_reset(void);
 /* tuning knobs (process-wide; 0 keeps the current value).  chunk: edges per task for indexes built
- * afterwards (default 256).  variant: 0 = automatic kernel choice, 1 = force the generic L2-gather
- * kernel, 2 = force the shared-memory-staged relation-table kernel where it is legal. */
-int ultra_rspmm_set_tuning(int32_t chunk, int32_t variant);
+ * afterwards (default 256).  variant: L2 eviction-priority hints of the gather kernels - 0 = automatic
+ * (on when the gathered slab exceeds 24 MiB), 1 = never, 2 = always.
+ * l2_budget_bytes: L2 bytes the gathered operand's slab (rows x slab width) may occupy; the slab width
+ * (512 / 256 / 128 bytes per row) is the widest that fits (default: unlimited, i.e. always 512). */
+int ultra_rspmm_set_tuning(int32_t chunk, int32_t variant, int64_t l2_budget_bytes);
 
 /* ---- index build (replaces sparse.coalesce() + coo2csr3d) ---------- */
 /* Bytes needed for the index arrays (upper bound, from the raw edge count) and for scratch. */

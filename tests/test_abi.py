@@ -53,7 +53,7 @@ def test_version_status_and_argument_validation():
                                        None) == _lib.ERR_DTYPE
     assert library.ultra_rspmm_forward(ctypes.byref(index), None, None, None, None, 4, _lib.F32, 9, 0, None, 0,
                                        None) == _lib.ERR_ARG
-    assert library.ultra_rspmm_set_tuning(-1, 0) == _lib.ERR_ARG
+    assert library.ultra_rspmm_set_tuning(-1, 0, 0) == _lib.ERR_ARG
     assert library.ultra_rspmm_launch_count() >= 0
 
 

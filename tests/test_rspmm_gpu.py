@@ -78,11 +78,11 @@ def test_parity_split_rows(cuda, sum, mul):
     # hub rows: with chunk = 8 most segments are split into partial rows + combine pass
     from ultra_torchdrug_b200 import _lib
     lib = _lib.lib()
-    lib.ultra_rspmm_set_tuning(8, 0)
+    lib.ultra_rspmm_set_tuning(8, 0, 0)
     try:
         _run_case(cuda, 50, 40, 3, 2000, 132, sum, mul, seed=11, duplicates=50, weights="random", skew=True, ties=True)
     finally:
-        lib.ultra_rspmm_set_tuning(256, 0)
+        lib.ultra_rspmm_set_tuning(256, 0, 0)
 
 
 @pytest.mark.parametrize("sum,mul", [("add", "mul"), ("max", "mul"), ("min", "add")])
@@ -244,24 +244,28 @@ def test_gradcheck_float64(cuda, sum, mul):
                                     (relation, input), eps=1e-6, atol=1e-6)
 
 
-def test_host_buffer_ctx(cuda):
-    """The torch-free host-buffer entry points (what a non-Python host binds; bench.py's e2e path)."""
+@pytest.mark.parametrize("dim", [96, 1160])
+def test_host_buffer_ctx(cuda, dim):
+    """The torch-free host-buffer entry points (what a non-Python host binds; bench.py's e2e path).
+    dim = 1160 spans three 512-column chunks of the upload / compute / download pipeline (ragged last chunk)."""
     from ultra_torchdrug_b200 import _lib
     lib = _lib.lib()
     indices, values = util.random_coo(80, 70, 5, 900, seed=12, duplicates=40, weights="random")
     shape = (80, 70, 5)
-    relation, input, grad = util.random_dense(5, 96, 1), util.random_dense(70, 96, 2), util.random_dense(80, 96, 3)
+    relation, input, grad = util.random_dense(5, dim, 1), util.random_dense(70, dim, 2), util.random_dense(80, dim, 3)
     ctx = ctypes.c_void_p()
     _lib.check(lib.ultra_rspmm_ctx_create(ctypes.byref(ctx), 0), "ctx_create")
     try:
         indices = np.ascontiguousarray(indices)
         _lib.check(lib.ultra_rspmm_ctx_set_graph(ctx, indices.ctypes.data, values.ctypes.data, indices.shape[1],
                                                  80, 70, 5, _lib.F32), "ctx_set_graph")
-        out = np.empty((80, 96), dtype=np.float32)
+        assert lib.ultra_rspmm_ctx_nnz(ctx) == len(np.unique(indices, axis=1).T)
+        out = np.empty((80, dim), dtype=np.float32)
         g_rel, g_in = np.empty_like(relation), np.empty_like(input)
-        _lib.check(lib.ultra_rspmm_ctx_forward_backward(
-            ctx, relation.ctypes.data, input.ctypes.data, grad.ctypes.data, out.ctypes.data, g_rel.ctypes.data,
-            g_in.ctypes.data, 96, 0, 0), "ctx_forward_backward")
+        for _ in range(2):   # second call reuses the buffer sets
+            _lib.check(lib.ultra_rspmm_ctx_forward_backward(
+                ctx, relation.ctypes.data, input.ctypes.data, grad.ctypes.data, out.ctypes.data, g_rel.ctypes.data,
+                g_in.ctypes.data, dim, 0, 0), "ctx_forward_backward")
         assert lib.ultra_rspmm_ctx_last_kernel_ms(ctx) > 0
         exp, _ = util.oracle_forward(indices, values, shape, relation, input, "add", "mul", dtype=np.float64)
         e_rel, e_in = util.oracle_backward(indices, values, shape, relation, input, None, grad, "add", "mul",
@@ -270,7 +274,7 @@ def test_host_buffer_ctx(cuda):
         np.testing.assert_allclose(g_rel, e_rel, rtol=1e-4, atol=1e-3)
         np.testing.assert_allclose(g_in, e_in, rtol=1e-4, atol=1e-3)
         out2 = np.empty_like(out)
-        _lib.check(lib.ultra_rspmm_ctx_forward(ctx, relation.ctypes.data, input.ctypes.data, out2.ctypes.data, 96, 2, 1),
+        _lib.check(lib.ultra_rspmm_ctx_forward(ctx, relation.ctypes.data, input.ctypes.data, out2.ctypes.data, dim, 2, 1),
                    "ctx_forward")
         exp2, _ = util.oracle_forward(indices, values, shape, relation, input, "max", "add")
         assert np.array_equal(out2, exp2)

@@ -52,6 +52,8 @@ def main():
     parser.add_argument("--skew", type=float, default=None)
     parser.add_argument("--iters", type=int, default=10)
     parser.add_argument("--chunk", type=int, default=0)
+    parser.add_argument("--l2mb", type=int, default=0, help="L2 budget (MiB) used to pick the slab width")
+    parser.add_argument("--variant", type=int, default=0, help="0 auto, 1 no L2 eviction hints, 2 hints always")
     parser.add_argument("--relgraph", action="store_true", help="dense 4-relation graph over R' nodes instead")
     args = parser.parse_args()
     device = torch.device("cuda", 0)
@@ -60,9 +62,9 @@ def main():
         peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    if args.chunk:
+    if args.chunk or args.l2mb or args.variant:
         from ultra_torchdrug_b200 import _lib
-        _lib.lib().ultra_rspmm_set_tuning(args.chunk, 0)
+        _lib.lib().ultra_rspmm_set_tuning(args.chunk, args.variant, args.l2mb << 20)
     edge_list, n, r = synthetic.named_graph(args.graph, skew=args.skew)
     if args.relgraph:
         nodes = r

@@ -40,7 +40,7 @@ SYMBOLS = {
     "ultra_rspmm_status_string": (ctypes.c_char_p, [ctypes.c_int]),
     "ultra_rspmm_launch_count": (c_int64, []),
     "ultra_rspmm_launch_count_reset": (None, []),
-    "ultra_rspmm_set_tuning": (ctypes.c_int, [c_int32, c_int32]),
+    "ultra_rspmm_set_tuning": (ctypes.c_int, [c_int32, c_int32, c_int64]),
     "ultra_rspmm_index_bytes": (ctypes.c_int, [c_int64, c_int32, c_int32, c_int32, c_int32,
                                                ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),
     "ultra_rspmm_index_build": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,

@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "rspmm_common.cuh"
 
@@ -12,6 +13,7 @@ static std::atomic<long long> g_launches{0};
 static thread_local int t_last_cuda_error = 0;
 int g_chunk = 256;
 int g_variant = 0;
+long long g_l2_budget = 1ll << 40;   // slab narrowing off by default: it lost on every measured shape (profiles/)
 
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -42,10 +44,11 @@ extern "C" const char *ultra_rspmm_status_string(int status) {
     }
 }
 
-extern "C" int ultra_rspmm_set_tuning(int32_t chunk, int32_t variant) {
-    if (chunk < 0 || chunk > (1 << 20) || variant < 0 || variant > 2) return ULTRA_RSPMM_ERR_ARG;
+extern "C" int ultra_rspmm_set_tuning(int32_t chunk, int32_t variant, int64_t l2_budget_bytes) {
+    if (chunk < 0 || chunk > (1 << 20) || variant < 0 || variant > 2 || l2_budget_bytes < 0) return ULTRA_RSPMM_ERR_ARG;
     if (chunk > 0) g_chunk = chunk;
     g_variant = variant;
+    if (l2_budget_bytes > 0) g_l2_budget = l2_budget_bytes;
     return ULTRA_RSPMM_OK;
 }
 
@@ -61,28 +64,41 @@ extern "C" int ultra_rspmm_host_free(void *ptr) {
 }
 
 // ---- host-buffer context ----------------------------------------------------------------------
+// The feature axis is the query batch (feature = b * 64 + c), so a call on host operands is pipelined
+// over column chunks (query groups): chunk c+1 is uploaded (2-D copies, pinned host memory -> compact
+// device buffers) while chunk c is reduced and chunk c-1 is downloaded.  PCIe is full duplex, so the
+// call costs about max(H2D, D2H) instead of H2D + kernels + D2H.
+namespace {
+
+constexpr int kSets = 3;            // buffer sets in flight: upload / compute / download
+constexpr int64_t kChunkCols = 512; // 8 queries of 64 features; a multiple of the 128-feature slab
+
+enum { BUF_REL = 0, BUF_IN, BUF_OUT, BUF_GOUT, BUF_GREL, BUF_GIN, BUF_WS, BUF_KINDS };
+
+}  // namespace
+
 struct ultra_rspmm_ctx {
-    int device;
-    cudaStream_t stream;
-    cudaEvent_t start, stop;
-    float last_ms;
-    bool has_graph;
+    int device = 0;
+    cudaStream_t stream = nullptr, stream_in = nullptr, stream_out = nullptr;
+    float last_ms = 0.f;
+    bool has_graph = false;
     ultra_rspmm_index_t index;
-    void *index_buffer;
-    // grow-only device buffers
-    void *buf[8];
-    size_t cap[8];
+    void *index_buffer = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_cap = 0;
+    void *buf[kSets][BUF_KINDS] = {};
+    size_t cap[kSets][BUF_KINDS] = {};
+    cudaEvent_t uploaded[kSets] = {}, computed[kSets] = {}, downloaded[kSets] = {};
+    std::vector<cudaEvent_t> tick;   // per-chunk kernel timing: 2 events per chunk
 };
 
-enum { BUF_REL = 0, BUF_IN, BUF_OUT, BUF_GOUT, BUF_GREL, BUF_GIN, BUF_WS, BUF_TMP };
-
-static int ctx_reserve(ultra_rspmm_ctx *ctx, int which, size_t bytes) {
-    if (bytes <= ctx->cap[which]) return ULTRA_RSPMM_OK;
-    if (ctx->buf[which]) ULTRA_CUDA_OK(cudaFree(ctx->buf[which]));
-    ctx->buf[which] = nullptr;
-    ctx->cap[which] = 0;
-    ULTRA_CUDA_OK(cudaMalloc(&ctx->buf[which], bytes));
-    ctx->cap[which] = bytes;
+static int reserve(void **ptr, size_t *cap, size_t bytes) {
+    if (bytes <= *cap) return ULTRA_RSPMM_OK;
+    if (*ptr) ULTRA_CUDA_OK(cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    ULTRA_CUDA_OK(cudaMalloc(ptr, bytes));
+    *cap = bytes;
     return ULTRA_RSPMM_OK;
 }
 
@@ -91,11 +107,16 @@ extern "C" int ultra_rspmm_ctx_create(ultra_rspmm_ctx_t **out, int32_t device) {
     ULTRA_CUDA_OK(cudaSetDevice(device));
     ultra_rspmm_ctx *ctx = new (std::nothrow) ultra_rspmm_ctx();
     if (!ctx) return ULTRA_RSPMM_ERR_ARG;
-    memset(ctx, 0, sizeof(*ctx));
+    memset(&ctx->index, 0, sizeof(ctx->index));
     ctx->device = device;
     ULTRA_CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    ULTRA_CUDA_OK(cudaEventCreate(&ctx->start));
-    ULTRA_CUDA_OK(cudaEventCreate(&ctx->stop));
+    ULTRA_CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
+    ULTRA_CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
+    for (int s = 0; s < kSets; ++s) {
+        ULTRA_CUDA_OK(cudaEventCreateWithFlags(&ctx->uploaded[s], cudaEventDisableTiming));
+        ULTRA_CUDA_OK(cudaEventCreateWithFlags(&ctx->computed[s], cudaEventDisableTiming));
+        ULTRA_CUDA_OK(cudaEventCreateWithFlags(&ctx->downloaded[s], cudaEventDisableTiming));
+    }
     *out = ctx;
     return ULTRA_RSPMM_OK;
 }
@@ -103,13 +124,20 @@ extern "C" int ultra_rspmm_ctx_create(ultra_rspmm_ctx_t **out, int32_t device) {
 extern "C" int ultra_rspmm_ctx_destroy(ultra_rspmm_ctx_t *ctx) {
     if (!ctx) return ULTRA_RSPMM_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 8; ++i)
-        if (ctx->buf[i]) cudaFree(ctx->buf[i]);
+    cudaDeviceSynchronize();
+    for (int s = 0; s < kSets; ++s) {
+        for (int k = 0; k < BUF_KINDS; ++k)
+            if (ctx->buf[s][k]) cudaFree(ctx->buf[s][k]);
+        cudaEventDestroy(ctx->uploaded[s]);
+        cudaEventDestroy(ctx->computed[s]);
+        cudaEventDestroy(ctx->downloaded[s]);
+    }
+    for (cudaEvent_t e : ctx->tick) cudaEventDestroy(e);
     if (ctx->index_buffer) cudaFree(ctx->index_buffer);
-    cudaEventDestroy(ctx->start);
-    cudaEventDestroy(ctx->stop);
+    if (ctx->tmp) cudaFree(ctx->tmp);
     cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->stream_in);
+    cudaStreamDestroy(ctx->stream_out);
     delete ctx;
     return ULTRA_RSPMM_OK;
 }
@@ -124,13 +152,13 @@ extern "C" int ultra_rspmm_ctx_set_graph(ultra_rspmm_ctx_t *ctx, const int64_t *
     const size_t elem = dtype == ULTRA_RSPMM_F32 ? 4 : 8;
     const size_t idx_bytes = align_up((size_t)nnz_raw * 3 * sizeof(int64_t));
     const size_t val_bytes = align_up((size_t)nnz_raw * elem);
-    status = ctx_reserve(ctx, BUF_TMP, idx_bytes + val_bytes + scratch_bytes + 256);
+    status = reserve(&ctx->tmp, &ctx->tmp_cap, idx_bytes + val_bytes + scratch_bytes + 256);
     if (status) return status;
     ctx->has_graph = false;
     if (ctx->index_buffer) ULTRA_CUDA_OK(cudaFree(ctx->index_buffer));
     ctx->index_buffer = nullptr;
     ULTRA_CUDA_OK(cudaMalloc(&ctx->index_buffer, index_bytes ? index_bytes : 256));
-    char *tmp = (char *)ctx->buf[BUF_TMP];
+    char *tmp = (char *)ctx->tmp;
     if (nnz_raw > 0) {
         ULTRA_CUDA_OK(cudaMemcpyAsync(tmp, host_indices, (size_t)nnz_raw * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
         ULTRA_CUDA_OK(cudaMemcpyAsync(tmp + idx_bytes, host_values, (size_t)nnz_raw * elem, cudaMemcpyHostToDevice, ctx->stream));
@@ -152,44 +180,84 @@ static int ctx_run(ultra_rspmm_ctx_t *ctx, const void *host_relation, const void
     ULTRA_CUDA_OK(cudaSetDevice(ctx->device));
     const ultra_rspmm_index_t &ix = ctx->index;
     const size_t elem = ix.dtype == ULTRA_RSPMM_F32 ? 4 : 8;
-    const size_t rel_bytes = (size_t)ix.n_rel * dim * elem, in_bytes = (size_t)ix.n_in * dim * elem,
-                 out_bytes = (size_t)ix.n_out * dim * elem;
+    const int64_t chunk_cols = dim < kChunkCols ? dim : kChunkCols;
+    const int n_chunk = dim == 0 ? 0 : (int)((dim + chunk_cols - 1) / chunk_cols);
+    ctx->last_ms = 0.f;
+    if (n_chunk == 0) return ULTRA_RSPMM_OK;
+
     size_t fwd_ws = 0, bwd_ws = 0;
-    int status = ultra_rspmm_workspace_bytes(&ix, dim, ix.dtype, &fwd_ws, &bwd_ws);
+    int status = ultra_rspmm_workspace_bytes(&ix, chunk_cols, ix.dtype, &fwd_ws, &bwd_ws);
     if (status) return status;
     const size_t ws = with_backward && bwd_ws > fwd_ws ? bwd_ws : fwd_ws;
-    if ((status = ctx_reserve(ctx, BUF_REL, rel_bytes + 256))) return status;
-    if ((status = ctx_reserve(ctx, BUF_IN, in_bytes + 256))) return status;
-    if ((status = ctx_reserve(ctx, BUF_OUT, out_bytes + 256))) return status;
-    if ((status = ctx_reserve(ctx, BUF_WS, ws + 256))) return status;
-    if (with_backward) {
-        if ((status = ctx_reserve(ctx, BUF_GOUT, out_bytes + 256))) return status;
-        if ((status = ctx_reserve(ctx, BUF_GREL, rel_bytes + 256))) return status;
-        if ((status = ctx_reserve(ctx, BUF_GIN, in_bytes + 256))) return status;
+    const size_t rel_bytes = (size_t)ix.n_rel * chunk_cols * elem, in_bytes = (size_t)ix.n_in * chunk_cols * elem,
+                 out_bytes = (size_t)ix.n_out * chunk_cols * elem;
+    const int sets = n_chunk < kSets ? n_chunk : kSets;
+    for (int s = 0; s < sets; ++s) {
+        if ((status = reserve(&ctx->buf[s][BUF_REL], &ctx->cap[s][BUF_REL], rel_bytes + 256))) return status;
+        if ((status = reserve(&ctx->buf[s][BUF_IN], &ctx->cap[s][BUF_IN], in_bytes + 256))) return status;
+        if ((status = reserve(&ctx->buf[s][BUF_OUT], &ctx->cap[s][BUF_OUT], out_bytes + 256))) return status;
+        if ((status = reserve(&ctx->buf[s][BUF_WS], &ctx->cap[s][BUF_WS], ws + 256))) return status;
+        if (with_backward) {
+            if ((status = reserve(&ctx->buf[s][BUF_GOUT], &ctx->cap[s][BUF_GOUT], out_bytes + 256))) return status;
+            if ((status = reserve(&ctx->buf[s][BUF_GREL], &ctx->cap[s][BUF_GREL], rel_bytes + 256))) return status;
+            if ((status = reserve(&ctx->buf[s][BUF_GIN], &ctx->cap[s][BUF_GIN], in_bytes + 256))) return status;
+        }
     }
-    cudaStream_t s = ctx->stream;
-    ULTRA_CUDA_OK(cudaMemcpyAsync(ctx->buf[BUF_REL], host_relation, rel_bytes, cudaMemcpyHostToDevice, s));
-    ULTRA_CUDA_OK(cudaMemcpyAsync(ctx->buf[BUF_IN], host_input, in_bytes, cudaMemcpyHostToDevice, s));
-    if (with_backward)
-        ULTRA_CUDA_OK(cudaMemcpyAsync(ctx->buf[BUF_GOUT], host_grad_output, out_bytes, cudaMemcpyHostToDevice, s));
-    ULTRA_CUDA_OK(cudaEventRecord(ctx->start, s));
-    status = ultra_rspmm_forward(&ix, ctx->buf[BUF_REL], ctx->buf[BUF_IN], ctx->buf[BUF_OUT], nullptr, dim, ix.dtype,
-                                 sum_op, mul_op, ctx->buf[BUF_WS], ctx->cap[BUF_WS], s);
-    if (status) return status;
-    if (with_backward) {
-        status = ultra_rspmm_backward(&ix, ctx->buf[BUF_REL], ctx->buf[BUF_IN], ctx->buf[BUF_OUT], ctx->buf[BUF_GOUT],
-                                      ctx->buf[BUF_GREL], ctx->buf[BUF_GIN], dim, ix.dtype, sum_op, mul_op,
-                                      ctx->buf[BUF_WS], ctx->cap[BUF_WS], s);
+    while ((int)ctx->tick.size() < 2 * n_chunk) {
+        cudaEvent_t e;
+        ULTRA_CUDA_OK(cudaEventCreate(&e));
+        ctx->tick.push_back(e);
+    }
+    const size_t host_pitch = (size_t)dim * elem;
+    for (int c = 0; c < n_chunk; ++c) {
+        const int s = c % kSets;
+        const int64_t col0 = (int64_t)c * chunk_cols;
+        const int64_t cols = dim - col0 < chunk_cols ? dim - col0 : chunk_cols;
+        const size_t width = (size_t)cols * elem, offset = (size_t)col0 * elem;
+        void **b = ctx->buf[s];
+        // upload (the set's previous chunk must have been downloaded)
+        if (c >= kSets) ULTRA_CUDA_OK(cudaStreamWaitEvent(ctx->stream_in, ctx->downloaded[s], 0));
+        ULTRA_CUDA_OK(cudaMemcpy2DAsync(b[BUF_REL], width, (const char *)host_relation + offset, host_pitch, width,
+                                        ix.n_rel, cudaMemcpyHostToDevice, ctx->stream_in));
+        ULTRA_CUDA_OK(cudaMemcpy2DAsync(b[BUF_IN], width, (const char *)host_input + offset, host_pitch, width, ix.n_in,
+                                        cudaMemcpyHostToDevice, ctx->stream_in));
+        if (with_backward)
+            ULTRA_CUDA_OK(cudaMemcpy2DAsync(b[BUF_GOUT], width, (const char *)host_grad_output + offset, host_pitch, width,
+                                            ix.n_out, cudaMemcpyHostToDevice, ctx->stream_in));
+        ULTRA_CUDA_OK(cudaEventRecord(ctx->uploaded[s], ctx->stream_in));
+        // compute
+        ULTRA_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->uploaded[s], 0));
+        ULTRA_CUDA_OK(cudaEventRecord(ctx->tick[2 * c], ctx->stream));
+        status = ultra_rspmm_forward(&ix, b[BUF_REL], b[BUF_IN], b[BUF_OUT], nullptr, cols, ix.dtype, sum_op, mul_op,
+                                     b[BUF_WS], ctx->cap[s][BUF_WS], ctx->stream);
         if (status) return status;
+        if (with_backward) {
+            status = ultra_rspmm_backward(&ix, b[BUF_REL], b[BUF_IN], b[BUF_OUT], b[BUF_GOUT], b[BUF_GREL], b[BUF_GIN], cols,
+                                          ix.dtype, sum_op, mul_op, b[BUF_WS], ctx->cap[s][BUF_WS], ctx->stream);
+            if (status) return status;
+        }
+        ULTRA_CUDA_OK(cudaEventRecord(ctx->tick[2 * c + 1], ctx->stream));
+        ULTRA_CUDA_OK(cudaEventRecord(ctx->computed[s], ctx->stream));
+        // download
+        ULTRA_CUDA_OK(cudaStreamWaitEvent(ctx->stream_out, ctx->computed[s], 0));
+        ULTRA_CUDA_OK(cudaMemcpy2DAsync((char *)host_output + offset, host_pitch, b[BUF_OUT], width, width, ix.n_out,
+                                        cudaMemcpyDeviceToHost, ctx->stream_out));
+        if (with_backward) {
+            ULTRA_CUDA_OK(cudaMemcpy2DAsync((char *)host_grad_relation + offset, host_pitch, b[BUF_GREL], width, width,
+                                            ix.n_rel, cudaMemcpyDeviceToHost, ctx->stream_out));
+            ULTRA_CUDA_OK(cudaMemcpy2DAsync((char *)host_grad_input + offset, host_pitch, b[BUF_GIN], width, width, ix.n_in,
+                                            cudaMemcpyDeviceToHost, ctx->stream_out));
+        }
+        ULTRA_CUDA_OK(cudaEventRecord(ctx->downloaded[s], ctx->stream_out));
     }
-    ULTRA_CUDA_OK(cudaEventRecord(ctx->stop, s));
-    ULTRA_CUDA_OK(cudaMemcpyAsync(host_output, ctx->buf[BUF_OUT], out_bytes, cudaMemcpyDeviceToHost, s));
-    if (with_backward) {
-        ULTRA_CUDA_OK(cudaMemcpyAsync(host_grad_relation, ctx->buf[BUF_GREL], rel_bytes, cudaMemcpyDeviceToHost, s));
-        ULTRA_CUDA_OK(cudaMemcpyAsync(host_grad_input, ctx->buf[BUF_GIN], in_bytes, cudaMemcpyDeviceToHost, s));
+    ULTRA_CUDA_OK(cudaStreamSynchronize(ctx->stream_out));
+    ULTRA_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ULTRA_CUDA_OK(cudaStreamSynchronize(ctx->stream_in));
+    for (int c = 0; c < n_chunk; ++c) {
+        float ms = 0.f;
+        ULTRA_CUDA_OK(cudaEventElapsedTime(&ms, ctx->tick[2 * c], ctx->tick[2 * c + 1]));
+        ctx->last_ms += ms;
     }
-    ULTRA_CUDA_OK(cudaStreamSynchronize(s));
-    ULTRA_CUDA_OK(cudaEventElapsedTime(&ctx->last_ms, ctx->start, ctx->stop));
     return ULTRA_RSPMM_OK;
 }
 

@@ -49,6 +49,9 @@ __device__ __forceinline__ void gather_load(const float *p, Vec<float, 4> &out) 
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(out.v[0]), "=f"(out.v[1]), "=f"(out.v[2]), "=f"(out.v[3]) : "l"(p));
 }
+__device__ __forceinline__ void gather_load(const float *p, Vec<float, 2> &out) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(out.v[0]), "=f"(out.v[1]) : "l"(p));
+}
 __device__ __forceinline__ void gather_load(const float *p, Vec<float, 1> &out) {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(out.v[0]) : "l"(p));
 }
@@ -59,9 +62,50 @@ __device__ __forceinline__ void gather_load(const double *p, Vec<double, 1> &out
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(out.v[0]) : "l"(p));
 }
 
+// L2 eviction-priority policies (createpolicy): the gathered slab is marked evict_last, the streams that pass
+// through once (edge ids, result rows) evict_first, so that a slab close to the L2 capacity is not pushed out
+// by them (profiles/r01: C4's 63 MB slab + 63 MB of result rows + 17 MB of edge ids per slab pass).
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+__device__ __forceinline__ void gather_load_keep(const float *p, Vec<float, 4> &out, unsigned long long policy) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(out.v[0]), "=f"(out.v[1]), "=f"(out.v[2]), "=f"(out.v[3]) : "l"(p), "l"(policy));
+}
+__device__ __forceinline__ void gather_load_keep(const float *p, Vec<float, 2> &out, unsigned long long policy) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
+                 : "=f"(out.v[0]), "=f"(out.v[1]) : "l"(p), "l"(policy));
+}
+__device__ __forceinline__ void gather_load_keep(const float *p, Vec<float, 1> &out, unsigned long long policy) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(out.v[0]) : "l"(p), "l"(policy));
+}
+__device__ __forceinline__ void gather_load_keep(const double *p, Vec<double, 2> &out, unsigned long long policy) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                 : "=d"(out.v[0]), "=d"(out.v[1]) : "l"(p), "l"(policy));
+}
+__device__ __forceinline__ void gather_load_keep(const double *p, Vec<double, 1> &out, unsigned long long policy) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(out.v[0]) : "l"(p), "l"(policy));
+}
+__device__ __forceinline__ int2 edge_load_once(const int2 *p, unsigned long long policy) {
+    int2 e;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;" : "=r"(e.x), "=r"(e.y) : "l"(p), "l"(policy));
+    return e;
+}
+
 __device__ __forceinline__ void table_load(const float *p, Vec<float, 4> &out) {
     const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
     out.v[0] = t.x; out.v[1] = t.y; out.v[2] = t.z; out.v[3] = t.w;
+}
+__device__ __forceinline__ void table_load(const float *p, Vec<float, 2> &out) {
+    const float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+    out.v[0] = t.x; out.v[1] = t.y;
 }
 __device__ __forceinline__ void table_load(const float *p, Vec<float, 1> &out) { out.v[0] = __ldg(p); }
 __device__ __forceinline__ void table_load(const double *p, Vec<double, 2> &out) {
@@ -73,6 +117,9 @@ __device__ __forceinline__ void table_load(const double *p, Vec<double, 1> &out)
 // streaming (evict-first) stores for results that are written once and not re-read by this kernel
 __device__ __forceinline__ void stream_store(float *p, const Vec<float, 4> &v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.v[0]), "f"(v.v[1]), "f"(v.v[2]), "f"(v.v[3]) : "memory");
+}
+__device__ __forceinline__ void stream_store(float *p, const Vec<float, 2> &v) {
+    asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.v[0]), "f"(v.v[1]) : "memory");
 }
 __device__ __forceinline__ void stream_store(float *p, const Vec<float, 1> &v) {
     asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v.v[0]) : "memory");
@@ -119,6 +166,7 @@ void note_launch();
 int fail_cuda(cudaError_t error);
 extern int g_chunk;    // edges per task for new indexes
 extern int g_variant;  // 0 auto, 1 generic, 2 staged
+extern long long g_l2_budget;  // bytes of L2 the gathered operand's slab may occupy (slab width is chosen to fit)
 
 #define ULTRA_CUDA_OK(expr)                                      \
     do {                                                         \

@@ -16,6 +16,8 @@
 // any moment read one (rows x SLAB) column block of the gathered operand - it stays in the 126 MB
 // L2 - and one (n_rel x SLAB) block of the relation table, which stays in L1.  HBM traffic is then
 // the compulsory bytes; the gathers are L2 hits.  No atomics anywhere: results are bit-reproducible.
+#include <initializer_list>
+
 #include "rspmm_common.cuh"
 
 namespace ultra {
@@ -37,6 +39,7 @@ template <typename T> struct SegArgs {
     long long dim;
     int n_task;
     int n_slab;
+    int keep;   // 1: mark the gathered slab evict_last in L2 and the edge-id stream evict_first
 };
 
 template <typename T, int SUM> __device__ __forceinline__ void reduce_into(T &acc, T m) {
@@ -55,7 +58,7 @@ template <typename T> __device__ __forceinline__ const T *row_ptr(const char *ba
 // and warp the loop below is: 1 LDS.64 (edge ids staged in shared memory by the whole warp, broadcast
 // read), 2 IMAD.WIDE (row addresses), 2 LDG.128, VEC FFMA - no shuffles, no predicates; the ragged tail
 // of a task runs in a separate single-edge loop.
-template <typename T, int VEC, int SUM, int MSG, bool B_TABLE, bool ARG, bool UNIT>
+template <typename T, int VEC, int SUM, int MSG, bool B_TABLE, bool ARG, bool UNIT, bool KEEP>
 __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const SegArgs<T> a) {
     __shared__ int2 s_edge[kWarpsPerBlock][32];
     __shared__ T s_w[UNIT ? 1 : kWarpsPerBlock][32];
@@ -71,6 +74,13 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
     const unsigned row_bytes = (unsigned)(a.dim * sizeof(T));
     const char *A = reinterpret_cast<const char *>(a.A + safe_col);
     const char *B = reinterpret_cast<const char *>(a.B + safe_col);
+    // KEEP (large slabs): gathered rows are marked evict_last in L2, the edge-id stream evict_first
+    const unsigned long long keep_policy = KEEP ? policy_evict_last() : 0, once_policy = KEEP ? policy_evict_first() : 0;
+    auto gather = [&](const T *p, Vec<T, VEC> &v) {
+        if (KEEP) gather_load_keep(p, v, keep_policy);
+        else gather_load(p, v);
+    };
+    auto edge_ids = [&](const int2 *p) { return KEEP ? edge_load_once(p, once_policy) : __ldg(p); };
 
     T acc[VEC];
     int32_t arg[VEC];
@@ -94,7 +104,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
     int2 ahead = make_int2(0, 0);
     T ahead_w = T(1);
     if (task.y + lane < task.z) {
-        ahead = __ldg(a.edge + task.y + lane);
+        ahead = edge_ids(a.edge + task.y + lane);
         if (!UNIT) ahead_w = __ldg(a.w + task.y + lane);
     }
     for (int base = task.y; base < task.z; base += 32) {
@@ -104,7 +114,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
         if (!UNIT) s_w[warp][lane] = ahead_w;
         __syncwarp();
         if (base + 32 + lane < task.z) {   // next batch's edge ids travel while this batch is reduced
-            ahead = __ldg(a.edge + base + 32 + lane);
+            ahead = edge_ids(a.edge + base + 32 + lane);
             if (!UNIT) ahead_w = __ldg(a.w + base + 32 + lane);
         }
         int u = 0;
@@ -115,10 +125,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
             for (int q = 0; q < kUnroll; ++q) {
                 const int2 e = s_edge[warp][u + q];
                 w[q] = UNIT ? T(1) : s_w[warp][u + q];
-                gather_load(row_ptr<T>(A, e.x, row_bytes), va[q]);
+                gather(row_ptr<T>(A, e.x, row_bytes), va[q]);
                 if (MSG != MSG_COPY) {
                     if (B_TABLE) table_load(row_ptr<T>(B, e.y, row_bytes), vb[q]);
-                    else gather_load(row_ptr<T>(B, e.y, row_bytes), vb[q]);
+                    else gather(row_ptr<T>(B, e.y, row_bytes), vb[q]);
                 } else {
                     vb[q] = va[q];
                 }
@@ -130,10 +140,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
             Vec<T, VEC> va, vb;
             const int2 e = s_edge[warp][u];
             const T w = UNIT ? T(1) : s_w[warp][u];
-            gather_load(row_ptr<T>(A, e.x, row_bytes), va);
+            gather(row_ptr<T>(A, e.x, row_bytes), va);
             if (MSG != MSG_COPY) {
                 if (B_TABLE) table_load(row_ptr<T>(B, e.y, row_bytes), vb);
-                else gather_load(row_ptr<T>(B, e.y, row_bytes), vb);
+                else gather(row_ptr<T>(B, e.y, row_bytes), vb);
             } else {
                 vb = va;
             }
@@ -303,10 +313,17 @@ int launch_seg(const SegArgs<T> &args, cudaStream_t stream) {
     if (warps == 0) return ULTRA_RSPMM_OK;
     const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > 0x7fffffffLL || args.dim * (long long)sizeof(T) > 0xffffffffLL) return ULTRA_RSPMM_ERR_RANGE;
-    if (args.w)
-        seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
-    else
-        seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    if (args.keep) {
+        if (args.w)
+            seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, false, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        else
+            seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, true, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    } else {
+        if (args.w)
+            seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, false, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        else
+            seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, true, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    }
     note_launch();
     return ULTRA_RSPMM_OK;
 }
@@ -332,10 +349,28 @@ int launch_combine(const ultra_rspmm_order_t &order, const T *partial, const int
     return ULTRA_RSPMM_OK;
 }
 
+// Slab width: the widest vector (16 / 8 / 4 bytes per lane) that the operands' shape and alignment allow and whose
+// column block of the gathered operand (rows x 32 lanes x VEC) fits the L2 budget - a slab that does not stay in L2
+// turns every gather into an HBM access (profiles/r01: C4 forward moved 19 GB of DRAM at 512 B slabs).
+template <typename T>
+int pick_vec(long long dim, long long rows, std::initializer_list<const void *> pointers) {
+    int vec = wide_vec<T>();
+    while (vec > 1) {
+        bool ok = dim % vec == 0;
+        for (const void *p : pointers) ok = ok && ((uintptr_t)p % (vec * sizeof(T)) == 0);
+        if (ok) break;
+        vec /= 2;
+    }
+    const int widest = vec;
+    while (vec > 1 && rows * 32 * vec * (long long)sizeof(T) > g_l2_budget) vec /= 2;
+    if (rows * 32 * vec * (long long)sizeof(T) > g_l2_budget) vec = widest;   // nothing fits: HBM-bound, widest rows are best
+    return vec;
+}
+
 // one reduction pass + its combine
 template <typename T, int SUM, int MSG, bool B_TABLE, bool ARG>
-int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, const T *B, T *out, int32_t *arg_out,
-             long long dim, void *workspace, cudaStream_t stream) {
+int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, const T *B, long long rows_gathered, T *out,
+             int32_t *arg_out, long long dim, void *workspace, cudaStream_t stream) {
     SegArgs<T> args;
     args.task = (const int4 *)order.task;
     args.edge = (const int2 *)order.edge;
@@ -348,23 +383,32 @@ int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, con
     args.partial_arg = ARG ? (int32_t *)((char *)workspace + align_up((size_t)order.n_slot * dim * sizeof(T))) : nullptr;
     args.dim = dim;
     args.n_task = order.n_task;
-    constexpr int W = wide_vec<T>();
-    const bool wide = dim % W == 0 && aligned16(A) && aligned16(B) && aligned16(out) && aligned16(workspace);
+    const int vec = pick_vec<T>(dim, rows_gathered, {A, B, out, workspace});
+    args.n_slab = (int)((dim + 32 * vec - 1) / (32 * vec));
+    args.keep = g_variant == 2 || (g_variant == 0 && rows_gathered * 32 * vec * (long long)sizeof(T) > (24ll << 20));
     int status;
-    if (wide) {
-        args.n_slab = (int)((dim + 32 * W - 1) / (32 * W));
-        status = launch_seg<T, W, SUM, MSG, B_TABLE, ARG>(args, stream);
-    } else {
-        args.n_slab = (int)((dim + 31) / 32);
-        status = launch_seg<T, 1, SUM, MSG, B_TABLE, ARG>(args, stream);
-    }
+    if (vec == 4) status = launch_seg<T, sizeof(T) == 4 ? 4 : 2, SUM, MSG, B_TABLE, ARG>(args, stream);
+    else if (vec == 2) status = launch_seg<T, 2, SUM, MSG, B_TABLE, ARG>(args, stream);
+    else status = launch_seg<T, 1, SUM, MSG, B_TABLE, ARG>(args, stream);
     if (status) return status;
     return launch_combine<T, SUM, ARG>(order, args.partial, args.partial_arg, out, arg_out, dim, stream);
 }
 
+template <typename T, int VEC, int MSG, bool P_TABLE>
+int launch_gated(const GatedArgs<T> &args, cudaStream_t stream) {
+    const long long warps = (long long)args.n_task * args.n_slab;
+    if (warps == 0) return ULTRA_RSPMM_OK;
+    const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks > 0x7fffffffLL || args.dim * (long long)sizeof(T) > 0xffffffffLL) return ULTRA_RSPMM_ERR_RANGE;
+    if (args.w) seg_gated_kernel<T, VEC, MSG, P_TABLE, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    else seg_gated_kernel<T, VEC, MSG, P_TABLE, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    note_launch();
+    return ULTRA_RSPMM_OK;
+}
+
 template <typename T, int MSG, bool P_TABLE>
-int run_gated(const ultra_rspmm_order_t &order, bool unit_weight, const T *G, const T *O, const T *P, const T *S, T *out,
-              long long dim, void *workspace, cudaStream_t stream) {
+int run_gated(const ultra_rspmm_order_t &order, bool unit_weight, const T *G, const T *O, const T *P, const T *S,
+              long long rows_gathered, T *out, long long dim, void *workspace, cudaStream_t stream) {
     GatedArgs<T> args;
     args.task = (const int4 *)order.task;
     args.edge = (const int2 *)order.edge;
@@ -374,23 +418,13 @@ int run_gated(const ultra_rspmm_order_t &order, bool unit_weight, const T *G, co
     args.partial = (T *)workspace;
     args.dim = dim;
     args.n_task = order.n_task;
-    constexpr int W = wide_vec<T>();
-    const bool wide = dim % W == 0 && aligned16(G) && aligned16(O) && aligned16(P) && aligned16(S) && aligned16(out) &&
-                      aligned16(workspace);
-    args.n_slab = wide ? (int)((dim + 32 * W - 1) / (32 * W)) : (int)((dim + 31) / 32);
-    const long long warps = (long long)args.n_task * args.n_slab;
-    if (warps > 0) {
-        const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        if (blocks > 0x7fffffffLL || dim * (long long)sizeof(T) > 0xffffffffLL) return ULTRA_RSPMM_ERR_RANGE;
-        if (wide) {
-            if (args.w) seg_gated_kernel<T, W, MSG, P_TABLE, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
-            else seg_gated_kernel<T, W, MSG, P_TABLE, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
-        } else {
-            if (args.w) seg_gated_kernel<T, 1, MSG, P_TABLE, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
-            else seg_gated_kernel<T, 1, MSG, P_TABLE, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
-        }
-        note_launch();
-    }
+    const int vec = pick_vec<T>(dim, 2 * rows_gathered, {G, O, P, S, out, workspace});   // two gathered operands share L2
+    args.n_slab = (int)((dim + 32 * vec - 1) / (32 * vec));
+    int status;
+    if (vec == 4) status = launch_gated<T, sizeof(T) == 4 ? 4 : 2, MSG, P_TABLE>(args, stream);
+    else if (vec == 2) status = launch_gated<T, 2, MSG, P_TABLE>(args, stream);
+    else status = launch_gated<T, 1, MSG, P_TABLE>(args, stream);
+    if (status) return status;
     return launch_combine<T, ULTRA_RSPMM_SUM_ADD, false>(order, args.partial, nullptr, out, nullptr, dim, stream);
 }
 
@@ -400,12 +434,12 @@ int forward_sum(const ultra_rspmm_index_t &ix, const T *relation, const T *input
     const bool unit = ix.unit_weight != 0;
     if (SUM != ULTRA_RSPMM_SUM_ADD && argidx) {
         if (mul_op == ULTRA_RSPMM_MUL_MUL)
-            return run_pass<T, SUM, MSG_MUL, true, true>(ix.csr, unit, input, relation, output, argidx, dim, ws, stream);
-        return run_pass<T, SUM, MSG_ADD, true, true>(ix.csr, unit, input, relation, output, argidx, dim, ws, stream);
+            return run_pass<T, SUM, MSG_MUL, true, true>(ix.csr, unit, input, relation, ix.n_in, output, argidx, dim, ws, stream);
+        return run_pass<T, SUM, MSG_ADD, true, true>(ix.csr, unit, input, relation, ix.n_in, output, argidx, dim, ws, stream);
     }
     if (mul_op == ULTRA_RSPMM_MUL_MUL)
-        return run_pass<T, SUM, MSG_MUL, true, false>(ix.csr, unit, input, relation, output, nullptr, dim, ws, stream);
-    return run_pass<T, SUM, MSG_ADD, true, false>(ix.csr, unit, input, relation, output, nullptr, dim, ws, stream);
+        return run_pass<T, SUM, MSG_MUL, true, false>(ix.csr, unit, input, relation, ix.n_in, output, nullptr, dim, ws, stream);
+    return run_pass<T, SUM, MSG_ADD, true, false>(ix.csr, unit, input, relation, ix.n_in, output, nullptr, dim, ws, stream);
 }
 
 template <typename T>
@@ -432,25 +466,25 @@ int backward_typed(const ultra_rspmm_index_t &ix, const void *relation, const vo
     if (sum_op == ULTRA_RSPMM_SUM_ADD) {
         if (gx) {
             status = mul_op == ULTRA_RSPMM_MUL_MUL
-                         ? run_pass<T, ADD, MSG_MUL, true, false>(ix.csc, unit, g, r, gx, nullptr, dim, ws, stream)
-                         : run_pass<T, ADD, MSG_COPY, true, false>(ix.csc, unit, g, r, gx, nullptr, dim, ws, stream);
+                         ? run_pass<T, ADD, MSG_MUL, true, false>(ix.csc, unit, g, r, ix.n_out, gx, nullptr, dim, ws, stream)
+                         : run_pass<T, ADD, MSG_COPY, true, false>(ix.csc, unit, g, r, ix.n_out, gx, nullptr, dim, ws, stream);
             if (status) return status;
         }
         if (gr) {
             status = mul_op == ULTRA_RSPMM_MUL_MUL
-                         ? run_pass<T, ADD, MSG_MUL, false, false>(ix.rel, unit, g, x, gr, nullptr, dim, ws, stream)
-                         : run_pass<T, ADD, MSG_COPY, true, false>(ix.rel, unit, g, x, gr, nullptr, dim, ws, stream);
+                         ? run_pass<T, ADD, MSG_MUL, false, false>(ix.rel, unit, g, x, (long long)ix.n_out + ix.n_in, gr, nullptr, dim, ws, stream)
+                         : run_pass<T, ADD, MSG_COPY, true, false>(ix.rel, unit, g, x, ix.n_out, gr, nullptr, dim, ws, stream);
         }
         return status;
     }
     if (gx) {
-        status = mul_op == ULTRA_RSPMM_MUL_MUL ? run_gated<T, MSG_MUL, true>(ix.csc, unit, g, o, r, x, gx, dim, ws, stream)
-                                               : run_gated<T, MSG_ADD, true>(ix.csc, unit, g, o, r, x, gx, dim, ws, stream);
+        status = mul_op == ULTRA_RSPMM_MUL_MUL ? run_gated<T, MSG_MUL, true>(ix.csc, unit, g, o, r, x, ix.n_out, gx, dim, ws, stream)
+                                               : run_gated<T, MSG_ADD, true>(ix.csc, unit, g, o, r, x, ix.n_out, gx, dim, ws, stream);
         if (status) return status;
     }
     if (gr) {
-        status = mul_op == ULTRA_RSPMM_MUL_MUL ? run_gated<T, MSG_MUL, false>(ix.rel, unit, g, o, x, r, gr, dim, ws, stream)
-                                               : run_gated<T, MSG_ADD, false>(ix.rel, unit, g, o, x, r, gr, dim, ws, stream);
+        status = mul_op == ULTRA_RSPMM_MUL_MUL ? run_gated<T, MSG_MUL, false>(ix.rel, unit, g, o, x, r, (long long)ix.n_out + ix.n_in, gr, dim, ws, stream)
+                                               : run_gated<T, MSG_ADD, false>(ix.rel, unit, g, o, x, r, (long long)ix.n_out + ix.n_in, gr, dim, ws, stream);
     }
     return status;
 }
