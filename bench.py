@@ -260,11 +260,14 @@ def run_gpu_arm(args):
 
     # ---- end to end through the C ABI with host buffers (H2D + D2H inside the timed region) -------
     e2e_ms, h2d, d2h = e2e_host_buffers(lib, edge_list, n, r, d, local_rank, max(min(args.steps, 5), 2), rank)
+    del sets
+    torch.cuda.empty_cache()
+    queries = ultra_queries(device, rank, steps=max(min(args.steps, 5), 2))
 
     if world > 1:
-        both = torch.tensor([elapsed_ms, e2e_ms], device=device, dtype=torch.float64)
+        both = torch.tensor([elapsed_ms, e2e_ms, queries["ms_per_batch"]], device=device, dtype=torch.float64)
         dist.all_reduce(both, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms = both.tolist()
+        elapsed_ms, e2e_ms, queries["ms_per_batch"] = both.tolist()
 
     if rank == 0:
         peak, peak_source = hbm_peak()
@@ -283,6 +286,11 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                     "api": "ultra_rspmm_ctx_forward_backward (C ABI, pinned host buffers)"},
             "gpu_launches": launches,
+            "ultra_queries": {"value": world * queries["queries_per_batch"] / (queries["ms_per_batch"] * 1e-3),
+                              "unit": "queries/s", "ms_per_batch": queries["ms_per_batch"],
+                              "batch_per_gpu": BATCH, "relation_graph_edges": queries["relation_graph_edges"],
+                              "what": "ULTRA zero-shot tail+head ranking, 6+6 layers x 64-d, all entities as candidates, "
+                                      "fresh batch per step, random-init weights, fp32 (TF32 off)"},
             "roofline": {"bound": "hbm", "kernel": "seg_reduce_kernel<float,4,add,mul> (forward)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_source, "algorithmic_bytes_per_launch": bytes_fwd,
@@ -299,6 +307,37 @@ def run_gpu_arm(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ultra_queries(device, rank, steps, warmup=2):
+    """ULTRA zero-shot ranking throughput (BASELINE.json second metric): one step = `predict` on a fresh batch of
+    64 triples = 128 ranking queries (tail + head) = 1 relation-graph pass + 2 entity-graph passes of 6 layers each
+    (reference ultra/task.py:228-263), random-init weights of the shipped architecture, fp32, TF32 off."""
+    import torch
+    from ultra_torchdrug_b200 import nbf, synthetic
+    from ultra_torchdrug_b200.compat.torchdrug import data
+
+    num_node, num_relation, num_triple = synthetic.SHAPES[GRAPH]
+    triples = synthetic.triples(num_node, num_relation, num_triple)
+    graph = data.Graph(triples, num_node=num_node, num_relation=num_relation).to(device)
+    torch.manual_seed(1024)
+    model, rel_model = nbf.ultra_models(num_relation)
+    ranker = nbf.UltraRanker(model.to(device).eval(), rel_model.to(device).eval(), graph)
+    generator = torch.Generator().manual_seed(4096 + rank)
+    batches = [triples[torch.randint(num_triple, (BATCH,), generator=generator)].to(device) for _ in range(warmup + steps)]
+    with torch.no_grad():
+        for batch in batches[:warmup]:
+            ranker.predict(batch)
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for batch in batches[warmup:]:
+            pred = ranker.predict(batch)     # a fresh batch every step: nothing is replayed from a cache
+        stop.record()
+        torch.cuda.synchronize()
+    ms = start.elapsed_time(stop) / steps
+    return {"ms_per_batch": ms, "queries_per_batch": 2 * BATCH, "relation_graph_edges": int(ranker.rel_graph.num_edge),
+            "score_checksum": float(pred.float().mean())}
 
 
 def e2e_host_buffers(lib, edge_list, n, r, d, device_index, steps, rank):

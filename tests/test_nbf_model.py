@@ -1,0 +1,87 @@
+"""Model-level parity: the host-side mirror (`ultra_torchdrug_b200.nbf`) against outputs of the reference's own
+modules (tests/golden/make_model_golden.py) - scores, relation representations, relation graph, training
+gradients, and ranking metrics.  CPU variant: the mirror runs on the oracle operator (checks the mirror);
+GPU variant: the mirror runs on the CUDA operator (checks the product end to end)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from ultra_torchdrug_b200 import nbf
+from ultra_torchdrug_b200.compat.torchdrug import data
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "model_ultra_small.npz")
+
+
+def _load(device):
+    g = np.load(GOLDEN)
+    num_node, num_relation, hidden, num_layers = (int(x) for x in g["shape"])
+    model, rel_model = nbf.ultra_models(num_relation, hidden=hidden, num_layers=num_layers)
+    for prefix, module in (("model/", model), ("rel_model/", rel_model)):
+        state = {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
+        module.load_state_dict(state, strict=True)      # same parameter names as the reference modules
+    graph = data.Graph(torch.from_numpy(g["edge_list"]), num_node=num_node, num_relation=num_relation).to(device)
+    return g, model.to(device), rel_model.to(device), graph
+
+
+def _check(g, model, rel_model, graph, device, rtol, atol):
+    ranker = nbf.UltraRanker(model, rel_model, graph)
+    want = {tuple(e) for e in g["rel_graph_edge_list"].tolist()}
+    assert {tuple(e) for e in ranker.rel_graph.edge_list.cpu().tolist()} == want
+    batch = torch.from_numpy(g["batch"]).to(device)
+    model.eval()
+    rel_model.eval()
+    with torch.no_grad():
+        rel_input = rel_model(ranker.rel_graph, batch[:, 2])
+        pred = ranker.predict(batch)
+    np.testing.assert_allclose(rel_input.cpu().numpy(), g["rel_input"], rtol=rtol, atol=atol)
+    np.testing.assert_allclose(pred.cpu().numpy(), g["pred"], rtol=rtol, atol=atol)
+    # ranking metrics: identical ranks => MRR / Hits@10 equal to 4 decimals and beyond
+    target = torch.stack([batch[:, 1], batch[:, 0]], dim=1)
+    mask = ranker.filter_mask(batch)
+    rank = ranker.rank(pred, target, mask).cpu()
+    rank_ref = ranker.rank(torch.from_numpy(g["pred"]).to(device), target, mask).cpu()
+    assert torch.equal(rank, rank_ref)
+    got, ref = nbf.metrics(rank), nbf.metrics(rank_ref)
+    assert round(got["mrr"], 4) == round(ref["mrr"], 4) and round(got["hits@10"], 4) == round(ref["hits@10"], 4)
+
+    # training branch: remove_easy_edges + backward through both networks
+    model.train()
+    rel_model.train()
+    h, t, r = (torch.from_numpy(g["train_%s_index" % k]).to(device) for k in "htr")
+    weight = torch.from_numpy(g["train_weight"]).to(device)
+    rel_input = rel_model(ranker.rel_graph, batch[:, 2])
+    train_pred = model(graph, [rel_input], h, t, r, remove_easy_edges=True)
+    np.testing.assert_allclose(train_pred.detach().cpu().numpy(), g["train_pred"], rtol=rtol, atol=atol)
+    (train_pred * weight).sum().backward()
+    checked = 0
+    for prefix, module in (("grad/model/", model), ("grad/rel_model/", rel_model)):
+        for name, parameter in module.named_parameters():
+            key = prefix + name
+            if key in g.files:
+                scale = max(1.0, float(np.abs(g[key]).max()))
+                np.testing.assert_allclose(parameter.grad.cpu().numpy(), g[key], rtol=10 * rtol, atol=10 * atol * scale,
+                                           err_msg=key)
+                checked += 1
+            else:
+                assert parameter.grad is None or float(parameter.grad.abs().max()) == 0.0, key
+    assert checked >= 40
+
+
+def test_mirror_on_oracle_matches_reference_modules(monkeypatch):
+    from oracle.rspmm_oracle import generalized_rspmm_oracle
+    monkeypatch.setattr(nbf, "generalized_rspmm", generalized_rspmm_oracle)
+    g, model, rel_model, graph = _load(torch.device("cpu"))
+    _check(g, model, rel_model, graph, torch.device("cpu"), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_mirror_on_cuda_matches_reference_modules(cuda):
+    from ultra_torchdrug_b200 import functional as F
+    torch.backends.cuda.matmul.allow_tf32 = False     # reference script/run_full.py:19-20
+    torch.backends.cudnn.allow_tf32 = False
+    g, model, rel_model, graph = _load(cuda)
+    before = F.launch_count()
+    _check(g, model, rel_model, graph, cuda, rtol=2e-4, atol=2e-5)
+    assert F.launch_count() > before

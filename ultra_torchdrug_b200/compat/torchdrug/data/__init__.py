@@ -7,6 +7,25 @@ import contextlib
 import torch
 
 
+def _memoise_transpose(sparse):
+    """Make `sparse.transpose(0, 1)` return the same tensor object every time.
+
+    The reference layers call `graph.adjacency.transpose(0, 1)` once per layer (layer.py:127,328); handing
+    back one object lets the operator find the graph index it attached to that object on the first call,
+    without fingerprinting the indices again (ultra_torchdrug_b200.functional.graph_index)."""
+    plain_transpose = sparse.transpose
+    memo = {}
+
+    def transpose(dim0, dim1):
+        key = (min(dim0, dim1), max(dim0, dim1))
+        if key not in memo:
+            memo[key] = plain_transpose(dim0, dim1)
+        return memo[key]
+
+    sparse.transpose = transpose
+    return sparse
+
+
 class Graph(object):
     """Relational graph container.  `edge_list[:, 0]` is the source (node_in), `[:, 1]` the
     destination (node_out), `[:, 2]` the relation type, as consumed at reference layer.py:56,82."""
@@ -108,6 +127,7 @@ class Graph(object):
                                                 check_invariants=False)
             if self._edge_weight.requires_grad:
                 return adjacency
+            _memoise_transpose(adjacency)
             self._cache["adjacency"] = adjacency
         return self._cache["adjacency"]
 

@@ -1,0 +1,368 @@
+"""Host-side mirror of the reference modules that sit directly on the rspmm hot path.
+
+On a machine with the reference tree the *unmodified* `ultra/layer.py`, `ultra/model.py`, `ultra/rel_model.py`
+run on top of the operator through `ultra_torchdrug_b200.compat`.  The GPU box of this project
+has no reference tree, so the callers needed to measure ULTRA queries/sec and to check model-level parity are
+restated here with the reference's names, constructor arguments, state-dict keys and numerics:
+
+  GeneralizedRelationalConvNBF      reference ultra/layer.py:14-190   (relation graph; message_and_aggregate :111-182)
+  GeneralizedRelationalConvNBFMod   reference ultra/layer.py:193-392  (entity graph;   message_and_aggregate :298-384)
+  TransferNBFNet                    reference ultra/model.py:17-194   (bellmanford :101-143, forward :145-194)
+  CustomNBFNetFull / RelNBFNet      reference ultra/rel_model.py:343-416 (bellmanford :351-378)
+  construct_relation_graph          reference ultra/rel_model.py:91-147  (multirelational branch)
+  UltraRanker.predict / rank        reference ultra/task.py:228-277, 307-315 (evaluation branch, full_batch_eval)
+
+Only the rspmm fast path is mirrored (`distmult` / `transe` messages); `rotate` and `graph.requires_grad` use the
+reference's PyTorch fallback, which is out of scope here.  tests/test_nbf_*.py pin this file
+against outputs of the reference's own modules (tests/golden/make_model_golden.py).
+"""
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import functional as rspmm
+from .compat.torchdrug import data
+from .compat.torchdrug.layers import MLP
+
+#: the operator the layers call; tests swap in the CPU oracle here (the product never imports it)
+generalized_rspmm = rspmm.generalized_rspmm
+
+MESSAGE_TO_MUL = {"transe": "add", "distmult": "mul"}
+
+
+def _aggregate(adjacency, relation_input, input, boundary, degree_out, aggregate_func, mul, eps):
+    """The operator calls and post-ops of one message-passing step (reference layer.py:133-180, 335-382)."""
+    def op(sum, rel=relation_input, x=input):
+        return generalized_rspmm(adjacency, rel, x, sum=sum, mul=mul)
+
+    bounded = not aggregate_func.endswith("_nobound")
+    name = aggregate_func[:-len("_nobound")] if not bounded else aggregate_func
+    if name == "sum":
+        update = op("add")
+        return update + boundary if bounded else update
+    if name == "mean":
+        update = op("add")
+        return (update + boundary) / degree_out if bounded else update / degree_out
+    if name == "max":
+        update = op("max")
+        return torch.max(update, boundary) if bounded else update
+    if name == "pna":
+        total, sq_total = op("add"), op("add", relation_input ** 2, input ** 2)
+        maximum, minimum = op("max"), op("min")
+        if bounded:
+            total, sq_total = total + boundary, sq_total + boundary ** 2
+            maximum, minimum = torch.max(maximum, boundary), torch.min(minimum, boundary)
+        mean, sq_mean = total / degree_out, sq_total / degree_out
+        std = (sq_mean - mean ** 2).clamp(min=eps).sqrt()
+        features = torch.stack([mean, maximum, minimum, std], dim=-1).flatten(-2)
+        scale = degree_out.log()
+        scale = scale / scale.mean()
+        scales = torch.cat([torch.ones_like(scale), scale, 1 / scale.clamp(min=1e-2)], dim=-1)
+        return (features.unsqueeze(-1) * scales.unsqueeze(-2)).flatten(-2)
+    raise ValueError("Unknown aggregation function `%s`" % aggregate_func)
+
+
+class _RelationalConvBase(nn.Module):
+    eps = 1e-6
+
+    def _setup(self, input_dim, output_dim, num_relation, query_input_dim, message_func, aggregate_func, layer_norm,
+               activation):
+        self.input_dim = input_dim
+        self.output_dim = output_dim
+        self.num_relation = num_relation
+        self.query_input_dim = query_input_dim
+        self.message_func = message_func
+        self.aggregate_func = aggregate_func
+        self.layer_norm = nn.LayerNorm(output_dim) if layer_norm else None
+        self.activation = getattr(F, activation) if isinstance(activation, str) else activation
+        width = 13 if aggregate_func in ("pna", "pna_nobound") else 2
+        self.linear = nn.Linear(input_dim * width, output_dim)
+
+    def relation_input(self, graph, batch_size):
+        raise NotImplementedError
+
+    def message_and_aggregate(self, graph, input):
+        if self.message_func not in MESSAGE_TO_MUL:
+            raise ValueError("Unknown message function `%s` (only the rspmm fast path is mirrored)" % self.message_func)
+        batch_size = len(graph.query)
+        flat_input = input.flatten(1)
+        boundary = graph.boundary.flatten(1)
+        degree_out = graph.degree_out.unsqueeze(-1) + 1
+        relation_input = self.relation_input(graph, batch_size)
+        adjacency = graph.adjacency.transpose(0, 1)
+        update = _aggregate(adjacency, relation_input, flat_input, boundary, degree_out, self.aggregate_func,
+                            MESSAGE_TO_MUL[self.message_func], self.eps)
+        return update.view(len(update), batch_size, -1)
+
+    def combine(self, input, update):
+        output = self.linear(torch.cat([input, update], dim=-1))
+        if self.layer_norm:
+            output = self.layer_norm(output)
+        if self.activation:
+            output = self.activation(output)
+        return output
+
+    def forward(self, graph, input):
+        return self.combine(input, self.message_and_aggregate(graph, input))
+
+
+class GeneralizedRelationalConvNBF(_RelationalConvBase):
+    """Relation representations from a query-conditioned linear map (`dependent`) or a shared embedding."""
+
+    def __init__(self, input_dim, output_dim, num_relation, query_input_dim, message_func="distmult",
+                 aggregate_func="pna", layer_norm=False, activation="relu", dependent=True):
+        super(GeneralizedRelationalConvNBF, self).__init__()
+        self._setup(input_dim, output_dim, num_relation, query_input_dim, message_func, aggregate_func, layer_norm,
+                    activation)
+        self.dependent = dependent
+        if dependent:
+            self.relation_linear = nn.Linear(query_input_dim, num_relation * input_dim)
+        else:
+            self.relation = nn.Embedding(num_relation, input_dim)
+
+    def relation_input(self, graph, batch_size):
+        assert graph.num_relation == self.num_relation
+        if self.dependent:
+            relation = self.relation_linear(graph.query).view(batch_size, self.num_relation, self.input_dim)
+            return relation.transpose(0, 1).flatten(1)
+        return self.relation.weight.repeat(1, batch_size)
+
+
+class GeneralizedRelationalConvNBFMod(_RelationalConvBase):
+    """Relation representations handed in from the relation model (`self.relation`), projected per layer."""
+
+    def __init__(self, input_dim, output_dim, num_relation, query_input_dim, message_func="distmult",
+                 aggregate_func="pna", layer_norm=False, activation="relu", project=True):
+        super(GeneralizedRelationalConvNBFMod, self).__init__()
+        self._setup(input_dim, output_dim, num_relation, query_input_dim, message_func, aggregate_func, layer_norm,
+                    activation)
+        self.project = project
+        self.relation_projection = MLP(input_dim=query_input_dim, hidden_dims=[input_dim, input_dim])
+        self.relation = None
+
+    def relation_input(self, graph, batch_size):
+        relation = self.relation if isinstance(self.relation, torch.Tensor) else self.relation.weight
+        if self.project:
+            relation = self.relation_projection(relation)
+        if relation.dim() == 2:                      # (R', d): shared by all queries
+            return relation.repeat(1, batch_size)
+        return relation.transpose(1, 0).flatten(1)   # (B, R', d) -> (R', B * d)
+
+
+def _run_layers(layers, graph, boundary, short_cut):
+    hidden = boundary
+    for layer in layers:
+        update = layer(graph, hidden)
+        hidden = update + hidden if short_cut and update.shape == hidden.shape else update
+    return hidden
+
+
+def _one_hot_boundary(num_node, index, query):
+    """(N, B, d) zeros with `query[b]` added at row `index[b]` of column b."""
+    boundary = torch.zeros(num_node, *query.shape, device=query.device, dtype=query.dtype)
+    boundary.scatter_add_(0, index.view(1, -1, 1).expand(1, -1, query.shape[-1]), query.unsqueeze(0))
+    return boundary
+
+
+class TransferNBFNet(nn.Module):
+    """Query-conditioned NBFNet over the entity graph (reference ultra/model.py:17-194, evaluation/training forward)."""
+
+    def __init__(self, input_dim, hidden_dims, num_relation=None, message_func="distmult", aggregate_func="pna",
+                 short_cut=False, layer_norm=False, activation="relu", concat_hidden=False, num_mlp_layer=2,
+                 project=True, mod=False):
+        super(TransferNBFNet, self).__init__()
+        hidden_dims = list(hidden_dims) if isinstance(hidden_dims, (list, tuple)) else [hidden_dims]
+        self.dims = [input_dim] + hidden_dims
+        self.num_relation = None if num_relation is None else int(num_relation)
+        double_relation = 1 if num_relation is None else 2 * self.num_relation
+        self.short_cut = short_cut
+        self.concat_hidden = concat_hidden
+        if concat_hidden:
+            raise NotImplementedError("concat_hidden is not used by the shipped configs")
+        layer_type = GeneralizedRelationalConvNBFMod if mod else GeneralizedRelationalConvNBF
+        self.layers = nn.ModuleList(
+            layer_type(self.dims[i], self.dims[i + 1], double_relation, self.dims[0], message_func, aggregate_func,
+                       layer_norm, activation, project) for i in range(len(self.dims) - 1))
+        feature_dim = hidden_dims[-1] + input_dim
+        self.query = None
+        self.mlp = MLP(feature_dim, [feature_dim] * (num_mlp_layer - 1) + [1])
+        self.dist_embed = nn.Embedding(10, input_dim)   # unused by forward; kept for state-dict parity
+
+    @staticmethod
+    def negative_sample_to_tail(h_index, t_index, r_index, num_relation):
+        """p(h | t, r) -> p(t' | h' = t, r' = r^-1) so that every row shares its head and relation."""
+        is_t_neg = (h_index == h_index[:, [0]]).all(dim=-1, keepdim=True)
+        new_h = torch.where(is_t_neg, h_index, t_index)
+        new_t = torch.where(is_t_neg, t_index, h_index)
+        new_r = torch.where(is_t_neg, r_index, r_index + num_relation)
+        return new_h, new_t, new_r
+
+    def remove_easy_edges(self, graph, h_index, t_index, r_index):
+        pattern = torch.stack([h_index, t_index, r_index], dim=-1).flatten(0, -2)
+        edge_index = graph.match(pattern)[0]
+        keep = torch.ones(graph.num_edge, dtype=torch.bool, device=graph.device)
+        keep[edge_index] = False
+        return graph.edge_mask(keep)
+
+    def bellmanford(self, graph, h_index, r_index):
+        batch = torch.arange(h_index.shape[0], device=h_index.device)
+        query = self.query[r_index] if self.query.dim() == 2 else self.query[batch, r_index]
+        boundary = _one_hot_boundary(graph.num_node, h_index, query)
+        with graph.graph():
+            graph.query = query
+        with graph.node():
+            graph.boundary = boundary
+        hidden = _run_layers(self.layers, graph, boundary, self.short_cut)
+        return torch.cat([hidden, query.expand(graph.num_node, -1, -1)], dim=-1)
+
+    def forward(self, graph, rel_query_list, h_index, t_index, r_index, remove_easy_edges=False):
+        if remove_easy_edges:
+            graph = self.remove_easy_edges(graph, h_index, t_index, r_index)
+        self.query = rel_query_list[0]
+        for i, layer in enumerate(self.layers):
+            layer.relation = rel_query_list[i + 1] if len(rel_query_list) > 1 else rel_query_list[0]
+        shape = h_index.shape
+        num_relation = graph.num_relation
+        graph = graph.undirected(add_inverse=True)
+        h_index, t_index, r_index = self.negative_sample_to_tail(h_index, t_index, r_index, num_relation)
+        assert (h_index[:, [0]] == h_index).all() and (r_index[:, [0]] == r_index).all()
+        feature = self.bellmanford(graph, h_index[:, 0], r_index[:, 0]).transpose(0, 1)
+        feature = feature.gather(1, t_index.unsqueeze(-1).expand(-1, -1, feature.shape[-1]))
+        return self.mlp(feature).squeeze(-1).view(shape)
+
+
+class CustomNBFNetFull(nn.Module):
+    """NBFNet over the relation graph: one labelled graph per query relation, all-ones query
+    (reference ultra/rel_model.py:227-263, 343-378)."""
+
+    def __init__(self, input_dim, hidden_dims, num_relation=None, message_func="distmult", aggregate_func="pna",
+                 short_cut=False, layer_norm=False, activation="relu", num_mlp_layer=2, dependent=False):
+        super(CustomNBFNetFull, self).__init__()
+        hidden_dims = list(hidden_dims)
+        self.dims = [input_dim] + hidden_dims
+        self.num_relation = 1 if num_relation is None else int(num_relation)
+        self.short_cut = short_cut
+        self.layers = nn.ModuleList(
+            GeneralizedRelationalConvNBF(self.dims[i], self.dims[i + 1], self.num_relation, self.dims[0], message_func,
+                                         aggregate_func, layer_norm, activation, dependent)
+            for i in range(len(self.dims) - 1))
+        feature_dim = hidden_dims[-1] + input_dim
+        self.mlp = MLP(feature_dim, [feature_dim] * (num_mlp_layer - 1) + [hidden_dims[-1]])   # unused; state-dict parity
+
+    def forward(self, graph, h_index):
+        query = torch.ones(h_index.shape[0], self.dims[0], device=h_index.device, dtype=torch.float)
+        boundary = _one_hot_boundary(graph.num_node, h_index, query)
+        with graph.graph():
+            graph.query = query
+        with graph.node():
+            graph.boundary = boundary
+        return _run_layers(self.layers, graph, boundary, self.short_cut).transpose(1, 0)   # (B, num_rel, dim)
+
+
+class RelNBFNet(nn.Module):
+    """Relation model of the shipped configs: 6-layer sum-aggregation NBFNet over the 4-relation graph of relations."""
+
+    def __init__(self, input_dim, hidden, num_layers=6, **unused):
+        super(RelNBFNet, self).__init__()
+        self.input_dim = input_dim
+        self.hidden_dim = hidden
+        self.model = CustomNBFNetFull(input_dim=input_dim, hidden_dims=[hidden] * num_layers, num_relation=4,
+                                      aggregate_func="sum", layer_norm=True, short_cut=True)
+        if hidden != input_dim:
+            self.input_transform_linear = nn.Linear(input_dim, hidden)
+
+    construct_relation_graph = staticmethod(lambda graph: construct_relation_graph(graph))
+
+    def forward(self, graph, r_idx):
+        return self.model(graph, r_idx)
+
+
+def construct_relation_graph(graph):
+    """Graph of relations with 4 edge types h2h, t2t, h2t, t2h (reference ultra/rel_model.py:91-147,
+    multirelational branch): relations r, s are linked when some entity is a head (tail) of both."""
+    graph = graph.undirected(add_inverse=True)
+    device = graph.device
+    num_node, num_relation = graph.num_node, graph.num_relation
+
+    def incidence(column):
+        pairs = graph.edge_list[:, [column, 2]].unique(dim=0)                       # (entity, relation)
+        degree = torch.zeros(num_node, dtype=torch.long, device=device).index_add_(0, pairs[:, 0],
+                                                                                    torch.ones_like(pairs[:, 1]))
+        normalised = torch.sparse_coo_tensor(pairs.flip(1).t(), torch.ones(len(pairs), device=device) / degree[pairs[:, 0]],
+                                             (num_relation, num_node))
+        plain = torch.sparse_coo_tensor(pairs.t(), torch.ones(len(pairs), device=device), (num_node, num_relation))
+        return normalised, plain
+
+    head_t, head = incidence(0)
+    tail_t, tail = incidence(1)
+    blocks = [torch.sparse.mm(head_t, head), torch.sparse.mm(tail_t, tail), torch.sparse.mm(head_t, tail),
+              torch.sparse.mm(tail_t, head)]
+    edges = []
+    for kind, block in enumerate(blocks):
+        pairs = block.coalesce().indices().t()
+        edges.append(torch.cat([pairs, torch.full((len(pairs), 1), kind, dtype=torch.long, device=device)], dim=1))
+    return data.Graph(torch.cat(edges, dim=0), num_node=num_relation, num_relation=4)
+
+
+class UltraRanker(nn.Module):
+    """Evaluation-time `predict` of KnowledgeGraphCompletionAdapted (reference ultra/task.py:228-263, full_batch_eval):
+    per batch of B triples one relation-model pass and two entity-model passes -> (B, 2, N) scores."""
+
+    def __init__(self, model, rel_model, graph):
+        super(UltraRanker, self).__init__()
+        self.model = model
+        self.rel_model = rel_model
+        self.graph = graph
+        self.rel_graph = construct_relation_graph(graph)
+        self.num_entity = graph.num_node
+
+    def predict(self, batch):
+        pos_h, pos_t, pos_r = batch.t()
+        rel_input = self.rel_model(self.rel_graph, pos_r)
+        candidates = torch.arange(self.num_entity, device=batch.device)
+        r_index = pos_r.unsqueeze(-1).expand(-1, self.num_entity)
+        h_index, t_index = torch.meshgrid(pos_h, candidates, indexing="ij")
+        t_pred = self.model(self.graph, [rel_input], h_index, t_index, r_index)
+        t_index, h_index = torch.meshgrid(pos_t, candidates, indexing="ij")
+        h_pred = self.model(self.graph, [rel_input], h_index, t_index, r_index)
+        return torch.stack([t_pred, h_pred], dim=1)
+
+    @staticmethod
+    def rank(pred, target, mask=None):
+        """Rank of the true entity among all candidates (reference task.py:307-315); `mask` = filtered ranking."""
+        pos_pred = pred.gather(-1, target.unsqueeze(-1))
+        better = pos_pred <= pred
+        if mask is not None:
+            better = better & mask
+        return better.sum(dim=-1) + 1
+
+    def filter_mask(self, batch, graph=None):
+        """True for candidates that are NOT known answers (reference task.py:65-100)."""
+        graph = graph or self.graph
+        pos_h, pos_t, pos_r = batch.t()
+        wildcard = -torch.ones_like(pos_h)
+        masks = []
+        for pattern, column in ((torch.stack([pos_h, wildcard, pos_r], dim=-1), 1),
+                                (torch.stack([wildcard, pos_t, pos_r], dim=-1), 0)):
+            edge_index, count = graph.match(pattern)
+            mask = torch.ones(len(pattern), graph.num_node, dtype=torch.bool, device=batch.device)
+            mask[torch.repeat_interleave(count), graph.edge_list[edge_index, column]] = False
+            masks.append(mask)
+        return torch.stack(masks, dim=1)
+
+
+def metrics(ranking):
+    """MR / MRR / Hits@k of a tensor of ranks (reference task.py:317-351)."""
+    ranking = ranking.float()
+    return {"mr": ranking.mean().item(), "mrr": (1 / ranking).mean().item(),
+            "hits@1": (ranking <= 1).float().mean().item(), "hits@3": (ranking <= 3).float().mean().item(),
+            "hits@10": (ranking <= 10).float().mean().item()}
+
+
+def ultra_models(num_relation, hidden=64, num_layers=6):
+    """The two networks with the hyper-parameters of reference config/transductive/inference.yaml:9-33."""
+    model = TransferNBFNet(input_dim=hidden, hidden_dims=[hidden] * num_layers, num_relation=num_relation,
+                           message_func="distmult", aggregate_func="sum", short_cut=True, layer_norm=True, project=True,
+                           mod=True)
+    rel_model = RelNBFNet(input_dim=hidden, hidden=hidden, num_layers=num_layers)
+    return model, rel_model
