@@ -127,6 +127,7 @@ def cpu_reference_sample(sample_batch, steps=1, warmup=0):
     from oracle import cpu_ref
     from ultra_torchdrug_b200 import synthetic
 
+    cpu_ref.use_all_cores()
     edge_list, n, r = synthetic.named_graph(GRAPH)
     indices = edge_list[:, [1, 0, 2]].t().contiguous().numpy()
     values = np.ones(indices.shape[1], dtype=np.float32)

@@ -165,6 +165,15 @@ int64_t ultra_rspmm_ctx_nnz(const ultra_rspmm_ctx_t *ctx);
 int ultra_rspmm_host_alloc(void **ptr, size_t bytes);
 int ultra_rspmm_host_free(void *ptr);
 
+/* ---- layer epilogue (reference layer.py:184-190, 386-392 + model.py:126-127) ---- */
+/* out = relu(layer_norm(x + linear_bias; eps) * gamma + beta) + residual over `rows` rows of `dim` fp32
+ * features (dim in {4, 8, ..., 128}); linear_bias, gamma/beta (both or neither) and residual may be NULL;
+ * relu = 0 skips the activation.  x is the output of the layer's Linear without its bias (a cuBLAS GEMM
+ * that stays in PyTorch).  Inference only. */
+int ultra_layer_norm_relu_residual(const float *dev_x, const float *dev_linear_bias, const float *dev_gamma, const float *dev_beta,
+                                   const float *dev_residual, float *dev_out, int64_t rows, int32_t dim, float eps,
+                                   int32_t relu, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

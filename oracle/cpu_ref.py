@@ -89,3 +89,10 @@ def backward(csr, relation, input, output, grad_output, sum="add", mul="mul"):
 
 def num_threads():
     return int(lib().rspmm_ref_num_threads())
+
+
+def use_all_cores():
+    """Use every core this process may run on (torchrun exports OMP_NUM_THREADS=1 for its workers)."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().rspmm_ref_set_num_threads(ctypes.c_int(cores))
+    return num_threads()

@@ -280,3 +280,22 @@ def test_host_buffer_ctx(cuda, dim):
         assert np.array_equal(out2, exp2)
     finally:
         lib.ultra_rspmm_ctx_destroy(ctx)
+
+
+@pytest.mark.parametrize("dim", [4, 16, 64, 128])
+def test_layer_epilogue_matches_torch(cuda, dim):
+    """Fused relu(layer_norm(x) * g + b) + residual vs the reference's separate PyTorch ops (layer.py:386-392)."""
+    from ultra_torchdrug_b200 import functional as F
+    torch.manual_seed(dim)
+    x = torch.randn(1000 + dim, 3, dim, device=cuda) * 3 + 1
+    residual = torch.randn_like(x)
+    weight, bias = torch.randn(dim, device=cuda), torch.randn(dim, device=cuda)
+    shift = torch.randn(dim, device=cuda)
+    want = torch.relu(torch.nn.functional.layer_norm(x + shift, (dim,), weight, bias, 1e-5)) + residual
+    got = F.layer_norm_relu_residual(x, weight, bias, residual, 1e-5, relu=True, linear_bias=shift)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-6)
+    want = torch.nn.functional.layer_norm(x, (dim,), None, None, 1e-5)
+    torch.testing.assert_close(F.layer_norm_relu_residual(x, None, None, None, 1e-5, relu=False), want, rtol=1e-5, atol=2e-6)
+    assert not F.layer_epilogue_supported(x, 48) and not F.layer_epilogue_supported(x.cpu(), dim)
+    with pytest.raises(RuntimeError):
+        F.layer_norm_relu_residual(x.requires_grad_(), weight, bias)

@@ -62,6 +62,8 @@ SYMBOLS = {
     "ultra_rspmm_ctx_nnz": (c_int64, [c_void_p]),
     "ultra_rspmm_host_alloc": (ctypes.c_int, [ctypes.POINTER(c_void_p), c_size_t]),
     "ultra_rspmm_host_free": (ctypes.c_int, [c_void_p]),
+    "ultra_layer_norm_relu_residual": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                                      ctypes.c_float, c_int32, c_void_p]),
 }
 
 _lib = None

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libultra_rspmm.so")
-SOURCES = ["rspmm_api.cu", "rspmm_index.cu", "rspmm_kernels.cu", "rspmm_staged.cu"]
+SOURCES = ["rspmm_api.cu", "rspmm_index.cu", "rspmm_kernels.cu", "layer_epilogue.cu"]
 HEADERS = ["rspmm_common.cuh", os.path.join(ROOT, "include", "ultra_rspmm.h")]
 
 NVCC_FLAGS = [

@@ -170,7 +170,28 @@ class Graph(object):
                           edge_index=slice(None))
 
     def undirected(self, add_inverse=False):
-        """Interleave every edge with its flip; with `add_inverse` the flip gets relation r + R."""
+        """Interleave every edge with its flip; with `add_inverse` the flip gets relation r + R.
+        The result is memoised per (immutable) graph object: the reference rebuilds it on every forward
+        (model.py:166), which would also rebuild the adjacency and make the operator re-identify the edge set."""
+        key = ("undirected", bool(add_inverse))
+        if key in self._cache and not self._edge_weight.requires_grad and not any(
+                kind == "edge" for kind in self.meta_dict.values()):
+            return self._cache[key]._fresh_view()
+        result = self._undirected(add_inverse)
+        if not self._edge_weight.requires_grad:
+            self._cache[key] = result
+            return result._fresh_view()
+        return result
+
+    def _fresh_view(self):
+        """A new Graph object sharing this one's tensors and derived-tensor cache (callers attach `query` /
+        `boundary` attributes to the graph they get back; those must not leak between calls)."""
+        view = type(self)(self._edge_list, edge_weight=self._edge_weight, num_node=self.num_node,
+                          num_relation=self.num_relation)
+        view._cache = self._cache
+        return view
+
+    def _undirected(self, add_inverse=False):
         flipped = self._edge_list[:, [1, 0] + list(range(2, self._edge_list.shape[1]))].clone()
         num_relation = self.num_relation
         if add_inverse:

@@ -18,7 +18,8 @@ import torch
 
 from . import _lib
 
-__all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count"]
+__all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
+           "layer_norm_relu_residual", "layer_epilogue_supported"]
 
 _SUM_OPS = ("add", "min", "max")
 _MUL_OPS = ("mul", "add")
@@ -132,6 +133,33 @@ def launch_count(reset=False):
     if reset:
         lib.ultra_rspmm_launch_count_reset()
     return count
+
+
+def layer_epilogue_supported(x, normalized_dim):
+    """The fused epilogue covers fp32 CUDA tensors with 4..128 (power of two) features per row, outside autograd."""
+    return (x.is_cuda and x.dtype == torch.float32 and normalized_dim % 4 == 0 and normalized_dim <= 128
+            and normalized_dim & (normalized_dim - 1) == 0 and not (torch.is_grad_enabled() and x.requires_grad))
+
+
+def layer_norm_relu_residual(x, weight=None, bias=None, residual=None, eps=1e-5, relu=True, linear_bias=None):
+    """relu(layer_norm(x + linear_bias) * weight + bias) + residual in one pass (reference layer.py:386-392 +
+    model.py:126-127).  Inference only: raises if `x` requires grad."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        raise RuntimeError("layer_norm_relu_residual is an inference-only kernel (no backward)")
+    dim = x.shape[-1]
+    x = x.contiguous()
+    if residual is not None:
+        if residual.shape != x.shape:
+            raise RuntimeError("residual shape %s != input shape %s" % (tuple(residual.shape), tuple(x.shape)))
+        residual = residual.contiguous()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().ultra_layer_norm_relu_residual(
+            _ptr(x), _ptr(linear_bias.contiguous() if linear_bias is not None else None),
+            _ptr(weight.contiguous() if weight is not None else None),
+            _ptr(bias.contiguous() if bias is not None else None), _ptr(residual), _ptr(out), x.numel() // max(dim, 1), dim,
+            float(eps), int(bool(relu)), _stream_handle()), "ultra_layer_norm_relu_residual")
+    return out
 
 
 def _fingerprint(indices, values):

@@ -94,16 +94,28 @@ class _RelationalConvBase(nn.Module):
                             MESSAGE_TO_MUL[self.message_func], self.eps)
         return update.view(len(update), batch_size, -1)
 
-    def combine(self, input, update):
-        output = self.linear(torch.cat([input, update], dim=-1))
+    def combine(self, input, update, residual=None):
+        """relu(layer_norm(linear(cat[input, update]))) (+ residual: the caller's short-cut, model.py:126-127).
+        Outside autograd the normalisation, activation and short-cut run as one fused pass (SURVEY 8 row f1);
+        under autograd they are the reference's separate PyTorch ops."""
+        joined = torch.cat([input, update], dim=-1)
+        fusable = self.layer_norm is not None and self.activation in (F.relu, None)
+        needs_grad = torch.is_grad_enabled() and (joined.requires_grad or self.linear.weight.requires_grad or
+                                                  self.layer_norm is not None and self.layer_norm.weight.requires_grad)
+        if fusable and not needs_grad and rspmm.layer_epilogue_supported(joined, self.output_dim):
+            output = F.linear(joined, self.linear.weight)      # bias, normalisation, activation, short-cut: one pass
+            return rspmm.layer_norm_relu_residual(output, self.layer_norm.weight, self.layer_norm.bias, residual,
+                                                  self.layer_norm.eps, relu=self.activation is not None,
+                                                  linear_bias=self.linear.bias)
+        output = self.linear(joined)
         if self.layer_norm:
             output = self.layer_norm(output)
         if self.activation:
             output = self.activation(output)
-        return output
+        return output if residual is None else output + residual
 
-    def forward(self, graph, input):
-        return self.combine(input, self.message_and_aggregate(graph, input))
+    def forward(self, graph, input, residual=None):
+        return self.combine(input, self.message_and_aggregate(graph, input), residual)
 
 
 class GeneralizedRelationalConvNBF(_RelationalConvBase):
@@ -152,8 +164,8 @@ class GeneralizedRelationalConvNBFMod(_RelationalConvBase):
 def _run_layers(layers, graph, boundary, short_cut):
     hidden = boundary
     for layer in layers:
-        update = layer(graph, hidden)
-        hidden = update + hidden if short_cut and update.shape == hidden.shape else update
+        skip = hidden if short_cut and layer.output_dim == hidden.shape[-1] else None
+        hidden = layer(graph, hidden, residual=skip)
     return hidden
 
 
@@ -225,7 +237,10 @@ class TransferNBFNet(nn.Module):
         num_relation = graph.num_relation
         graph = graph.undirected(add_inverse=True)
         h_index, t_index, r_index = self.negative_sample_to_tail(h_index, t_index, r_index, num_relation)
-        assert (h_index[:, [0]] == h_index).all() and (r_index[:, [0]] == r_index).all()
+        # the reference asserts here that every row shares its head and relation (model.py:174-175); on CUDA
+        # tensors that is two host synchronisations per pass, so the mirror only checks host tensors
+        if not h_index.is_cuda:
+            assert (h_index[:, [0]] == h_index).all() and (r_index[:, [0]] == r_index).all()
         feature = self.bellmanford(graph, h_index[:, 0], r_index[:, 0]).transpose(0, 1)
         feature = feature.gather(1, t_index.unsqueeze(-1).expand(-1, -1, feature.shape[-1]))
         return self.mlp(feature).squeeze(-1).view(shape)
