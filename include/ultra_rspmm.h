@@ -63,13 +63,15 @@ typedef struct ultra_rspmm_order {
     int32_t n_slot;       /* partial rows needed by the split segments                                  */
     int32_t n_split;      /* number of split segments                                                   */
     int32_t max_seg_nnz;  /* longest segment                                                            */
-    int32_t reserved;
+    int32_t pack_shift;   /* > 0: `packed` holds edge.x | edge.y << pack_shift; 0: ids do not fit 32 bits      */
     const int32_t *ptr;   /* n_seg + 1: edges of segment s are [ptr[s], ptr[s+1])                        */
     const int32_t *edge;  /* M x int2: the two row ids each edge gathers from (see ultra_rspmm_index_t)  */
     const void *w;        /* M merged values, element type = index dtype                                */
     const int32_t *eid;   /* M: position of the edge in coalesced (CSR) order; NULL for the CSR itself   */
-    const int32_t *task;  /* n_task x int4 {seg, begin, end, slot}; slot = -1: writes the result row.
-                             Sorted by descending edge count (longest first).                           */
+    const uint32_t *packed; /* M: both ids of an edge in one word (see pack_shift)                        */
+    const int32_t *task;  /* n_task x int4 {seg, begin, end, (slot + 1) | 0x40000000 if any edge weight != 1};
+                             slot = -1: the task writes the result row itself.  Sorted by descending edge
+                             count (longest first).                                                     */
     const int32_t *split; /* n_split x int4 {seg, first_slot, n_slots, 0}                                */
 } ultra_rspmm_order_t;
 

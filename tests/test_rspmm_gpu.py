@@ -149,9 +149,17 @@ def test_index_matches_coalesce(cuda):
     order = np.argsort(exp_index[2], kind="stable")
     assert np.array_equal(rel_eid, order)
     assert np.array_equal(rel_edge[:, 0], exp_index[0][order]) and np.array_equal(rel_edge[:, 1], exp_index[1][order])
-    # tasks cover every segment exactly once, longest first
+    # tasks cover every segment exactly once, longest first; ids are also stored packed; non-unit tasks are flagged
     for order_c, n_seg in ((index.c.csr, shape[0]), (index.c.csc, shape[1]), (index.c.rel, shape[2])):
         task = view(order_c.task, 4 * order_c.n_task, torch.int32).reshape(-1, 4)
+        edges = view(order_c.edge, 2 * m, torch.int32).reshape(m, 2).astype(np.int64)
+        weights = view(order_c.w, m, torch.float32)
+        assert order_c.pack_shift > 0
+        packed = view(order_c.packed, m, torch.int32).astype(np.int64) & 0xffffffff
+        assert np.array_equal(packed, edges[:, 0] | (edges[:, 1] << order_c.pack_shift))
+        for seg, begin, end, encoded in task:
+            assert bool(encoded & 0x40000000) == bool((weights[begin:end] != 1).any())
+            assert (encoded & 0x3fffffff) - 1 == -1   # no split segments at this size
         seg_ptr = view(order_c.ptr, n_seg + 1, torch.int32)
         length = task[:, 2] - task[:, 1]
         assert (np.diff(length) <= 0).all()

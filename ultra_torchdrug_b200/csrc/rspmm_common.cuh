@@ -93,6 +93,11 @@ __device__ __forceinline__ void gather_load_keep(const double *p, Vec<double, 2>
 __device__ __forceinline__ void gather_load_keep(const double *p, Vec<double, 1> &out, unsigned long long policy) {
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(out.v[0]) : "l"(p), "l"(policy));
 }
+__device__ __forceinline__ unsigned edge_load_once(const unsigned *p, unsigned long long policy) {
+    unsigned e;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(e) : "l"(p), "l"(policy));
+    return e;
+}
 __device__ __forceinline__ int2 edge_load_once(const int2 *p, unsigned long long policy) {
     int2 e;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;" : "=r"(e.x), "=r"(e.y) : "l"(p), "l"(policy));
@@ -159,6 +164,11 @@ template <typename T, int MSG> __device__ __forceinline__ T message(T r, T x) {
     if (MSG == MSG_ADD) return r + x;
     return x;
 }
+
+// task.w = (slot + 1) | kNonUnitTask: slot of the partial row the task writes (-1 = the result row itself) and
+// whether any of its edges has a merged weight different from 1
+constexpr int kNonUnitTask = 0x40000000;
+__host__ __device__ __forceinline__ int task_slot(int encoded) { return (encoded & (kNonUnitTask - 1)) - 1; }
 
 // launch bookkeeping (claimed in bench.py as `gpu_launches`)
 void note_launch();

@@ -111,6 +111,21 @@ __global__ void permute_kernel(const int32_t *__restrict__ perm, int32_t nnz, co
     eid[p] = m;
 }
 
+// both ids of an edge in one word, and a 0/1 flag per edge for "weight differs from 1" (n + 1 entries, last = 0)
+template <typename T>
+__global__ void pack_kernel(const int2 *__restrict__ edge, const T *__restrict__ w, int32_t nnz, int shift,
+                            uint32_t *__restrict__ packed, int32_t *__restrict__ nonunit) {
+    const int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > nnz) return;
+    if (p == nnz) {
+        nonunit[p] = 0;
+        return;
+    }
+    const int2 e = edge[p];
+    if (shift > 0) packed[p] = (uint32_t)e.x | ((uint32_t)e.y << shift);
+    nonunit[p] = w[p] != T(1) ? 1 : 0;
+}
+
 // ptr[s] = first position whose segment id is >= s   (s in [0, n_seg])
 __global__ void segment_ptr_kernel(const int32_t *__restrict__ seg_of, int32_t nnz, int32_t n_seg,
                                    int32_t *__restrict__ ptr) {
@@ -151,7 +166,8 @@ __global__ void gather_totals_kernel(const int32_t *__restrict__ off_task, const
 
 __global__ void task_emit_kernel(const int32_t *__restrict__ ptr, int32_t n_seg, int32_t chunk,
                                  const int32_t *__restrict__ off_task, const int32_t *__restrict__ off_slot,
-                                 const int32_t *__restrict__ off_split, int4 *__restrict__ task,
+                                 const int32_t *__restrict__ off_split, const int32_t *__restrict__ nonunit_before,
+                                 int4 *__restrict__ task,
                                  uint32_t *__restrict__ task_key, int32_t *__restrict__ task_val,
                                  int4 *__restrict__ split) {
     const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,8 +175,12 @@ __global__ void task_emit_kernel(const int32_t *__restrict__ ptr, int32_t n_seg,
     const int32_t begin = ptr[s], end = ptr[s + 1];
     const int32_t deg = end - begin;
     const int32_t t0 = off_task[s];
+    auto encode = [&](int32_t slot, int32_t from, int32_t to) {
+        const bool nonunit = nonunit_before && nonunit_before[to] != nonunit_before[from];
+        return (slot + 1) | (nonunit ? kNonUnitTask : 0);
+    };
     if (deg <= chunk) {
-        task[t0] = make_int4(s, begin, end, -1);
+        task[t0] = make_int4(s, begin, end, encode(-1, begin, end));
         task_key[t0] = (uint32_t)(chunk - deg);
         task_val[t0] = t0;
         return;
@@ -172,7 +192,7 @@ __global__ void task_emit_kernel(const int32_t *__restrict__ ptr, int32_t n_seg,
     int32_t at = begin;
     for (int32_t q = 0; q < c; ++q) {
         const int32_t len = base + (q < extra ? 1 : 0);
-        task[t0 + q] = make_int4(s, at, at + len, slot0 + q);
+        task[t0 + q] = make_int4(s, at, at + len, encode(slot0 + q, at, at + len));
         task_key[t0 + q] = (uint32_t)(chunk - len);
         task_val[t0 + q] = t0 + q;
         at += len;
@@ -226,7 +246,7 @@ int bit_length(unsigned long long v) {
 }
 
 struct OrderLayout {
-    size_t ptr, edge, w, eid, task, split;
+    size_t ptr, edge, w, eid, packed, task, split;
 };
 
 struct IndexLayout {
@@ -236,7 +256,7 @@ struct IndexLayout {
 
 struct ScratchLayout {
     size_t keys_a, keys_b, vals_a, vals_b, pos, row_of, seg_of, cnt, off, task_tmp, tkey_a, tkey_b, tval_a, tval_b,
-        counters, cub, cub_bytes, total;
+        nonunit, counters, cub, cub_bytes, total;
 };
 
 int64_t task_upper(int64_t nnz_raw, int64_t n_seg, int chunk) { return n_seg + nnz_raw / chunk + 2; }
@@ -252,6 +272,7 @@ IndexLayout index_layout(int64_t nnz_raw, const int32_t n_seg[3], size_t elem, i
         q.edge = at; at = align_up(at + sizeof(int2) * e);
         q.w = at; at = align_up(at + elem * e);
         q.eid = at; at = align_up(at + (o == 0 ? 0 : sizeof(int32_t) * e));
+        q.packed = at; at = align_up(at + sizeof(uint32_t) * e);
         q.task = at; at = align_up(at + sizeof(int4) * task_upper(nnz_raw, n_seg[o], chunk));
         q.split = at; at = align_up(at + sizeof(int4) * split_upper(nnz_raw, chunk));
     }
@@ -278,6 +299,7 @@ ScratchLayout scratch_layout(int64_t nnz_raw, int32_t n_seg_max, int chunk) {
     S.tkey_b = at; at = align_up(at + 4 * nt);
     S.tval_a = at; at = align_up(at + 4 * nt);
     S.tval_b = at; at = align_up(at + 4 * nt);
+    S.nonunit = at; at = align_up(at + 3 * 4 * (e + 1));
     S.counters = at; at = align_up(at + 4 * CNT_SIZE);
     S.cub = at;
     // CUB temporary storage: radix sort / scan need O(tiles) words; provision generously and verify at build time
@@ -341,6 +363,8 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
     }
 
     // ---- the two other orders -------------------------------------------------------------------
+    int pack_shift[3] = {0, 0, 0};
+    const bool any_nonunit = host_counters[CNT_NONUNIT] != 0;
     for (int o = 0; o < 3; ++o) {
         int32_t *ptr = (int32_t *)(ibuf + L.order[o].ptr);
         const int32_t *segments = row_of;
@@ -371,6 +395,23 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
         }
         segment_ptr_kernel<<<blocks_for((int64_t)n_seg[o] + 1), kBuildThreads, 0, stream>>>(segments, nnz, n_seg[o], ptr);
         note_launch();
+        {   // packed edge ids and the running count of non-unit weights (for the per-task flag)
+            const int32_t x_range = o == 0 ? n_in : n_out, y_range = o == 2 ? n_in : n_rel;
+            const int x_bits = bit_length(x_range > 1 ? (unsigned long long)x_range - 1 : 1);
+            const int y_bits = bit_length(y_range > 1 ? (unsigned long long)y_range - 1 : 1);
+            pack_shift[o] = x_bits + y_bits <= 32 ? x_bits : 0;
+            int32_t *flags = vals_a;
+            int32_t *before = (int32_t *)(sbuf + S.nonunit) + (size_t)o * ((size_t)(nnz_raw > 0 ? nnz_raw : 1) + 1);
+            pack_kernel<T><<<blocks_for((int64_t)nnz + 1), kBuildThreads, 0, stream>>>(
+                (const int2 *)(ibuf + L.order[o].edge), (const T *)(ibuf + L.order[o].w), nnz, pack_shift[o],
+                (uint32_t *)(ibuf + L.order[o].packed), flags);
+            note_launch();
+            if (host_counters[CNT_NONUNIT]) {
+                need = S.cub_bytes;
+                ULTRA_CUDA_OK(cub::DeviceScan::ExclusiveSum(cub_tmp, need, flags, before, nnz + 1, stream));
+                note_launch();
+            }
+        }
         int32_t *cnt = (int32_t *)(sbuf + S.cnt);
         int32_t *off = (int32_t *)(sbuf + S.off) + (size_t)o * 3 * ((size_t)n_seg_max + 1);
         const size_t span = (size_t)n_seg_max + 1;
@@ -399,7 +440,8 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
         out.n_slot = host_counters[CNT_TOTALS + 3 * o + 1];
         out.n_split = host_counters[CNT_TOTALS + 3 * o + 2];
         out.max_seg_nnz = host_counters[CNT_MAXSEG + o];
-        out.reserved = 0;
+        out.pack_shift = pack_shift[o];
+        out.packed = (const uint32_t *)(ibuf + L.order[o].packed);
         out.ptr = (const int32_t *)(ibuf + L.order[o].ptr);
         out.edge = (const int32_t *)(ibuf + L.order[o].edge);
         out.w = ibuf + L.order[o].w;
@@ -413,7 +455,9 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
         uint32_t *tkey_a = (uint32_t *)(sbuf + S.tkey_a), *tkey_b = (uint32_t *)(sbuf + S.tkey_b);
         int32_t *tval_a = (int32_t *)(sbuf + S.tval_a), *tval_b = (int32_t *)(sbuf + S.tval_b);
         task_emit_kernel<<<blocks_for(n_seg[o]), kBuildThreads, 0, stream>>>(
-            out.ptr, n_seg[o], chunk, off, off + span, off + 2 * span, task_tmp, tkey_a, tval_a, (int4 *)(ibuf + L.order[o].split));
+            out.ptr, n_seg[o], chunk, off, off + span, off + 2 * span,
+            any_nonunit ? (const int32_t *)(sbuf + S.nonunit) + (size_t)o * ((size_t)(nnz_raw > 0 ? nnz_raw : 1) + 1) : nullptr,
+            task_tmp, tkey_a, tval_a, (int4 *)(ibuf + L.order[o].split));
         note_launch();
         need = S.cub_bytes;
         ULTRA_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, need, tkey_a, tkey_b, tval_a, tval_b, out.n_task, 0,

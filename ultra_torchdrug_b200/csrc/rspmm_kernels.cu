@@ -17,6 +17,7 @@
 // L2 - and one (n_rel x SLAB) block of the relation table, which stays in L1.  HBM traffic is then
 // the compulsory bytes; the gathers are L2 hits.  No atomics anywhere: results are bit-reproducible.
 #include <initializer_list>
+#include <type_traits>
 
 #include "rspmm_common.cuh"
 
@@ -29,6 +30,8 @@ constexpr int kUnroll = 4;
 template <typename T> struct SegArgs {
     const int4 *task;
     const int2 *edge;
+    const unsigned *packed;   // edge ids packed as x | y << pack_shift (null when they do not fit 32 bits)
+    int pack_shift;
     const T *w;        // null when all weights are 1
     const T *A;
     const T *B;
@@ -48,39 +51,53 @@ template <typename T, int SUM> __device__ __forceinline__ void reduce_into(T &ac
     else acc = acc < m ? acc : m;                                  // torchdrug NaryMin::forward
 }
 
+__device__ __forceinline__ int id_x(const int2 &e) { return e.x; }
+__device__ __forceinline__ int id_y(const int2 &e) { return e.y; }
+__device__ __forceinline__ int id_x(const unsigned &) { return 0; }
+__device__ __forceinline__ int id_y(const unsigned &) { return 0; }
+__device__ __forceinline__ unsigned id_bits(const unsigned &e) { return e; }
+__device__ __forceinline__ unsigned id_bits(const int2 &) { return 0; }
+
 // row address = base + row * row_bytes as one IMAD.WIDE.U32 (row ids are int32 >= 0, row_bytes < 2^32)
 template <typename T> __device__ __forceinline__ const T *row_ptr(const char *base, int row, unsigned row_bytes) {
     return reinterpret_cast<const T *>(base + (unsigned long long)(unsigned)row * row_bytes);
 }
 
-// The issue-slot budget of the inner loop is what bounds these kernels once the gathers are L2 hits
-// (profiles/r01: 77% issue-active at 46 instructions per edge and slab in the first version).  Per edge
-// and warp the loop below is: 1 LDS.64 (edge ids staged in shared memory by the whole warp, broadcast
-// read), 2 IMAD.WIDE (row addresses), 2 LDG.128, VEC FFMA - no shuffles, no predicates; the ragged tail
-// of a task runs in a separate single-edge loop.
-template <typename T, int VEC, int SUM, int MSG, bool B_TABLE, bool ARG, bool UNIT, bool KEEP>
+// The issue-slot and L1-data-pipe budgets of the inner loop are what bound these kernels once the gathers are L2
+// hits (profiles/README.md).  Per edge and warp the loop below is: a broadcast shared-memory read of the edge
+// ids (staged by the whole warp; one LDS.128 serves 4 edges when the two ids pack into 32 bits), 2 IMAD.WIDE
+// (row addresses), 2 LDG.128, VEC FFMA - no shuffles, no predicates; the ragged tail of a task runs in a separate
+// single-edge loop.  Tasks whose edges all have weight 1 (flag in task.w) skip the weight stream and multiply.
+template <typename T, int VEC, int SUM, int MSG, bool B_TABLE, bool ARG, bool PACKED, bool KEEP>
 __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const SegArgs<T> a) {
-    __shared__ int2 s_edge[kWarpsPerBlock][32];
-    __shared__ T s_w[UNIT ? 1 : kWarpsPerBlock][32];
+    using Ids = typename std::conditional<PACKED, unsigned, int2>::type;
+    __shared__ __align__(16) Ids s_edge[kWarpsPerBlock][32];
+    __shared__ __align__(16) T s_w[kWarpsPerBlock][32];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long gw = (long long)blockIdx.x * kWarpsPerBlock + warp;
     if (gw >= (long long)a.n_task * a.n_slab) return;   // warps never meet at a block barrier
     const int slab = (int)(gw / a.n_task);
     const int4 task = __ldg(a.task + (gw - (long long)slab * a.n_task));
+    const int slot = task_slot(task.w);
     const long long col = (long long)slab * (32 * VEC) + lane * VEC;
     const bool active = col < a.dim;
     const long long safe_col = active ? col : 0;   // idle lanes (dim % (32 * VEC) != 0) read column 0, store nothing
     const unsigned row_bytes = (unsigned)(a.dim * sizeof(T));
     const char *A = reinterpret_cast<const char *>(a.A + safe_col);
     const char *B = reinterpret_cast<const char *>(a.B + safe_col);
+    const Ids *ids = reinterpret_cast<const Ids *>(PACKED ? (const void *)a.packed : (const void *)a.edge);
+    const int shift = a.pack_shift;
+    const unsigned low = PACKED ? (shift >= 32 ? 0xffffffffu : ((1u << shift) - 1u)) : 0u;
     // KEEP (large slabs): gathered rows are marked evict_last in L2, the edge-id stream evict_first
     const unsigned long long keep_policy = KEEP ? policy_evict_last() : 0, once_policy = KEEP ? policy_evict_first() : 0;
     auto gather = [&](const T *p, Vec<T, VEC> &v) {
         if (KEEP) gather_load_keep(p, v, keep_policy);
         else gather_load(p, v);
     };
-    auto edge_ids = [&](const int2 *p) { return KEEP ? edge_load_once(p, once_policy) : __ldg(p); };
+    auto load_ids = [&](const Ids *p) { return KEEP ? edge_load_once(p, once_policy) : __ldg(p); };
+    auto first_id = [&](const Ids &e) { return PACKED ? (int)(id_bits(e) & low) : id_x(e); };
+    auto second_id = [&](const Ids &e) { return PACKED ? (int)(id_bits(e) >> shift) : id_y(e); };
 
     T acc[VEC];
     int32_t arg[VEC];
@@ -90,80 +107,79 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
         arg[v] = -1;
     }
 
-    auto accumulate = [&](const Vec<T, VEC> &va, const Vec<T, VEC> &vb, T w, int position) {
+    auto reduce_task = [&](auto unit_tag) {
+        constexpr bool UNIT = decltype(unit_tag)::value;
+        auto accumulate = [&](const Vec<T, VEC> &va, const Vec<T, VEC> &vb, T w, int position) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const T m = UNIT ? message<T, MSG>(vb.v[v], va.v[v]) : message<T, MSG>(w, vb.v[v], va.v[v]);
-            if (ARG) {
-                if (SUM == ULTRA_RSPMM_SUM_MAX ? (m > acc[v]) : (m < acc[v])) arg[v] = position;
-            }
-            reduce_into<T, SUM>(acc[v], m);
-        }
-    };
-
-    int2 ahead = make_int2(0, 0);
-    T ahead_w = T(1);
-    if (task.y + lane < task.z) {
-        ahead = edge_ids(a.edge + task.y + lane);
-        if (!UNIT) ahead_w = __ldg(a.w + task.y + lane);
-    }
-    for (int base = task.y; base < task.z; base += 32) {
-        const int n = min(32, task.z - base);
-        __syncwarp();
-        s_edge[warp][lane] = ahead;
-        if (!UNIT) s_w[warp][lane] = ahead_w;
-        __syncwarp();
-        if (base + 32 + lane < task.z) {   // next batch's edge ids travel while this batch is reduced
-            ahead = edge_ids(a.edge + base + 32 + lane);
-            if (!UNIT) ahead_w = __ldg(a.w + base + 32 + lane);
-        }
-        int u = 0;
-        for (; u + kUnroll <= n; u += kUnroll) {
-            Vec<T, VEC> va[kUnroll], vb[kUnroll];
-            T w[kUnroll];
-#pragma unroll
-            for (int q = 0; q < kUnroll; ++q) {
-                const int2 e = s_edge[warp][u + q];
-                w[q] = UNIT ? T(1) : s_w[warp][u + q];
-                gather(row_ptr<T>(A, e.x, row_bytes), va[q]);
-                if (MSG != MSG_COPY) {
-                    if (B_TABLE) table_load(row_ptr<T>(B, e.y, row_bytes), vb[q]);
-                    else gather(row_ptr<T>(B, e.y, row_bytes), vb[q]);
-                } else {
-                    vb[q] = va[q];
+            for (int v = 0; v < VEC; ++v) {
+                const T m = UNIT ? message<T, MSG>(vb.v[v], va.v[v]) : message<T, MSG>(w, vb.v[v], va.v[v]);
+                if (ARG) {
+                    if (SUM == ULTRA_RSPMM_SUM_MAX ? (m > acc[v]) : (m < acc[v])) arg[v] = position;
                 }
+                reduce_into<T, SUM>(acc[v], m);
             }
-#pragma unroll
-            for (int q = 0; q < kUnroll; ++q) accumulate(va[q], vb[q], w[q], base + u + q);
-        }
-        for (; u < n; ++u) {
-            Vec<T, VEC> va, vb;
-            const int2 e = s_edge[warp][u];
-            const T w = UNIT ? T(1) : s_w[warp][u];
-            gather(row_ptr<T>(A, e.x, row_bytes), va);
+        };
+        auto load_pair = [&](const Ids &e, Vec<T, VEC> &va, Vec<T, VEC> &vb) {
+            gather(row_ptr<T>(A, first_id(e), row_bytes), va);
             if (MSG != MSG_COPY) {
-                if (B_TABLE) table_load(row_ptr<T>(B, e.y, row_bytes), vb);
-                else gather(row_ptr<T>(B, e.y, row_bytes), vb);
+                if (B_TABLE) table_load(row_ptr<T>(B, second_id(e), row_bytes), vb);
+                else gather(row_ptr<T>(B, second_id(e), row_bytes), vb);
             } else {
                 vb = va;
             }
-            accumulate(va, vb, w, base + u);
+        };
+        Ids ahead = Ids();
+        T ahead_w = T(1);
+        if (task.y + lane < task.z) {
+            ahead = load_ids(ids + task.y + lane);
+            if (!UNIT) ahead_w = __ldg(a.w + task.y + lane);
         }
-    }
+        for (int base = task.y; base < task.z; base += 32) {
+            const int n = min(32, task.z - base);
+            __syncwarp();
+            s_edge[warp][lane] = ahead;
+            if (!UNIT) s_w[warp][lane] = ahead_w;
+            __syncwarp();
+            if (base + 32 + lane < task.z) {   // next batch's edge ids travel while this batch is reduced
+                ahead = load_ids(ids + base + 32 + lane);
+                if (!UNIT) ahead_w = __ldg(a.w + base + 32 + lane);
+            }
+            int u = 0;
+            for (; u + kUnroll <= n; u += kUnroll) {
+                Vec<T, VEC> va[kUnroll], vb[kUnroll];
+                T w[kUnroll];
+#pragma unroll
+                for (int q = 0; q < kUnroll; ++q) {
+                    w[q] = UNIT ? T(1) : s_w[warp][u + q];
+                    load_pair(s_edge[warp][u + q], va[q], vb[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < kUnroll; ++q) accumulate(va[q], vb[q], w[q], base + u + q);
+            }
+            for (; u < n; ++u) {
+                Vec<T, VEC> va, vb;
+                const T w = UNIT ? T(1) : s_w[warp][u];
+                load_pair(s_edge[warp][u], va, vb);
+                accumulate(va, vb, w, base + u);
+            }
+        }
+    };
+    if (a.w == nullptr || !(task.w & kNonUnitTask)) reduce_task(std::true_type());
+    else reduce_task(std::false_type());
+
     if (!active) return;
     Vec<T, VEC> r;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) r.v[v] = acc[v];
-    if (task.w < 0) {
+    if (slot < 0) {
         stream_store(a.out + (long long)task.x * a.dim + col, r);
     } else {
-        T *p = a.partial + (long long)task.w * a.dim + col;   // re-read soon by the combine pass: default policy
+        T *p = a.partial + (long long)slot * a.dim + col;   // re-read soon by the combine pass: default policy
 #pragma unroll
         for (int v = 0; v < VEC; ++v) p[v] = r.v[v];
     }
     if (ARG) {
-        int32_t *p = task.w < 0 ? a.arg_out + (long long)task.x * a.dim + col
-                                : a.partial_arg + (long long)task.w * a.dim + col;
+        int32_t *p = slot < 0 ? a.arg_out + (long long)task.x * a.dim + col : a.partial_arg + (long long)slot * a.dim + col;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) p[v] = arg[v];
     }
@@ -198,6 +214,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 3) seg_gated_kernel(const Ga
     if (gw >= (long long)a.n_task * a.n_slab) return;
     const int slab = (int)(gw / a.n_task);
     const int4 task = __ldg(a.task + (gw - (long long)slab * a.n_task));
+    const int slot = task_slot(task.w);
     const long long col = (long long)slab * (32 * VEC) + lane * VEC;
     const bool active = col < a.dim;
     const long long safe_col = active ? col : 0;
@@ -267,11 +284,11 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 3) seg_gated_kernel(const Ga
         }
     }
     if (!active) return;
-    T *p = task.w < 0 ? a.out + (long long)task.x * a.dim + col : a.partial + (long long)task.w * a.dim + col;
+    T *p = slot < 0 ? a.out + (long long)task.x * a.dim + col : a.partial + (long long)slot * a.dim + col;
     Vec<T, VEC> r;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) r.v[v] = acc[v];
-    if (task.w < 0) stream_store(p, r);
+    if (slot < 0) stream_store(p, r);
     else {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) p[v] = r.v[v];
@@ -314,15 +331,15 @@ int launch_seg(const SegArgs<T> &args, cudaStream_t stream) {
     const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > 0x7fffffffLL || args.dim * (long long)sizeof(T) > 0xffffffffLL) return ULTRA_RSPMM_ERR_RANGE;
     if (args.keep) {
-        if (args.w)
-            seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, false, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
-        else
+        if (args.packed)
             seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, true, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
-    } else {
-        if (args.w)
-            seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, false, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
         else
+            seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, false, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    } else {
+        if (args.packed)
             seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, true, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        else
+            seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, false, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
     }
     note_launch();
     return ULTRA_RSPMM_OK;
@@ -374,6 +391,8 @@ int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, con
     SegArgs<T> args;
     args.task = (const int4 *)order.task;
     args.edge = (const int2 *)order.edge;
+    args.packed = order.pack_shift > 0 ? (const unsigned *)order.packed : nullptr;
+    args.pack_shift = order.pack_shift;
     args.w = unit_weight ? nullptr : (const T *)order.w;
     args.A = A;
     args.B = B;
