@@ -85,12 +85,14 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    try:
-        path = _build.build()
-    except Exception:
-        if not os.path.exists(path):
-            raise
+    path = os.environ.get("ULTRA_RSPMM_LIB")   # development: load an alternative build of the library
+    if not path:
+        path = _build.LIB_PATH
+        try:
+            path = _build.build()
+        except Exception:
+            if not os.path.exists(path):
+                raise
     handle = ctypes.CDLL(path)
     for name, (restype, argtypes) in SYMBOLS.items():
         function = getattr(handle, name)  # AttributeError when the library does not export a declared symbol

@@ -25,7 +25,7 @@ namespace ultra {
 
 namespace {
 
-constexpr int kUnroll = 4;
+constexpr int kUnroll = 4;   // 4 edges in flight per warp at 4 CTAs/SM beat 2x5, 6x3, 8x3, 8x2 (profiles/README.md)
 
 template <typename T> struct SegArgs {
     const int4 *task;
