@@ -33,8 +33,12 @@ from ultra_torchdrug_b200 import compat  # noqa: E402
 compat.install()
 compat.add_reference_to_path("/root/reference")
 
+import torchdrug.layers.functional as td_functional  # noqa: E402  (the shim)
+from oracle.rspmm_oracle import generalized_rspmm_oracle  # noqa: E402
 from torchdrug import data  # noqa: E402  (the shim)
 from ultra import layer as ref_layer  # noqa: E402  (the unmodified reference module)
+
+td_functional.generalized_rspmm = generalized_rspmm_oracle   # the reference's fast path runs on the CPU oracle here
 
 FLT_MAX = float(np.finfo(np.float32).max)
 
@@ -121,7 +125,55 @@ def one_case(kind, message_func, seed, duplicates):
     return record
 
 
+def layer_case(kind, message_func, aggregate_func, seed):
+    """Full `message_and_aggregate` of the reference layer through its fallback (message + aggregate with the
+    boundary as a self-loop message, layer.py:77, 83-84) - what the fast path's operator call + post-ops
+    (layer.py:154-180, 356-382) must reproduce.  No duplicate triples (see module docstring)."""
+    torch.manual_seed(seed)
+    num_node, num_relation, batch, dim = 30, 5, 2, 8
+    edge_list = make_graph(num_node, num_relation, 150, seed, duplicates=0)
+    graph = data.Graph(edge_list, num_node=num_node, num_relation=num_relation)
+    query = torch.randn(batch, dim)
+    input = torch.randn(num_node, batch, dim)
+    boundary = torch.randn(num_node, batch, dim)
+    if kind == "nbf":
+        layer = ref_layer.GeneralizedRelationalConvNBF(dim, dim, num_relation, dim, message_func, aggregate_func,
+                                                       dependent=True)
+    else:
+        layer = ref_layer.GeneralizedRelationalConvNBFMod(dim, dim, num_relation, dim, message_func, aggregate_func,
+                                                          project=True)
+        layer.relation = torch.randn(batch, num_relation, dim)
+    with torch.no_grad():
+        update = run_fallback(layer, graph, input, boundary, query)
+        with graph.graph():
+            graph.query = query
+        with graph.node():
+            graph.boundary = boundary
+        output = layer.combine(input, update)
+        # the reference's own fast path (layer.py:111-182 / 298-384) on the oracle operator.  For pna x transe it
+        # differs from the fallback by construction: it squares the operands (rel^2 + in^2), the fallback squares
+        # the message ((rel + in)^2) - a property of the reference, kept as is.
+        fast_update = layer.message_and_aggregate(graph, input)
+        fast_output = layer.combine(input, fast_update)
+    record = {"edge_list": edge_list.numpy(), "shape": np.array([num_node, num_relation, batch, dim]),
+              "query": query.numpy(), "input": input.numpy(), "boundary": boundary.numpy(),
+              "update": update.numpy().copy(), "output": output.numpy().copy(),
+              "fast_update": fast_update.numpy().copy(), "fast_output": fast_output.numpy().copy()}
+    if kind == "nbfmod":
+        record["relation"] = layer.relation.numpy().copy()
+    for name, tensor in layer.state_dict().items():
+        record["state/" + name] = tensor.numpy().copy()
+    return record
+
+
 def main():
+    for kind in ("nbf", "nbfmod"):
+        for message_func in ("distmult", "transe"):
+            for aggregate_func in ("sum", "mean", "max", "pna"):
+                record = layer_case(kind, message_func, aggregate_func, seed=7)
+                name = "layer_full_%s_%s_%s.npz" % (kind, message_func, aggregate_func)
+                np.savez_compressed(os.path.join(HERE, name), **record)
+                print("wrote", name)
     for kind in ("nbf", "nbfmod"):
         for message_func in ("distmult", "transe"):
             for duplicates in (0, 25):
