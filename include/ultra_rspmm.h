@@ -21,7 +21,8 @@
  *     coalesced - ultra_rspmm_index_build sorts by (row, col, layer) and merges duplicates by summing
  *     their values, exactly what `sparse.coalesce()` does before torchdrug's coo2csr3d;
  *   - empty rows produce the reduction identity: 0 (add), -FLT_MAX / -DBL_MAX (max), +FLT_MAX / +DBL_MAX (min);
- *   - arg-index = position (in coalesced order) of the first edge attaining the extremum, -1 for empty rows;
+ *   - arg-index = position in coalesce() order (dst, src, rel) of the first edge attaining the extremum,
+ *     -1 for empty rows;
  *   - max/min backward follows the reference's all-ties rule (gate `output == message`).
  */
 #ifndef ULTRA_RSPMM_H_
@@ -67,7 +68,7 @@ typedef struct ultra_rspmm_order {
     const int32_t *ptr;   /* n_seg + 1: edges of segment s are [ptr[s], ptr[s+1])                        */
     const int32_t *edge;  /* M x int2: the two row ids each edge gathers from (see ultra_rspmm_index_t)  */
     const void *w;        /* M merged values, element type = index dtype                                */
-    const int32_t *eid;   /* M: position of the edge in coalesced (CSR) order; NULL for the CSR itself   */
+    const int32_t *eid;   /* M: position of the edge in canonical coalesce() order (dst, src, rel)        */
     const uint32_t *packed; /* M: both ids of an edge in one word (see pack_shift)                        */
     const int32_t *task;  /* n_task x int4 {seg, begin, end, (slot + 1) | 0x40000000 if any edge weight != 1};
                              slot = -1: the task writes the result row itself.  Sorted by descending edge
@@ -86,9 +87,9 @@ typedef struct ultra_rspmm_index {
     int32_t dtype;        /* ULTRA_RSPMM_F32 / F64: element type of the w arrays                          */
     int32_t unit_weight;  /* 1 if every merged value == 1 (the w stream is not read)                    */
     int32_t chunk;        /* maximum edges per task                                                     */
-    ultra_rspmm_order_t csr;  /* forward: segments = destination rows, sorted (dst, src, rel); edge = {src, rel} */
-    ultra_rspmm_order_t csc;  /* backward w.r.t. input: segments = source rows, sorted (src, dst, rel); edge = {dst, rel} */
-    ultra_rspmm_order_t rel;  /* backward w.r.t. relation: segments = relations, stable by coalesced position; edge = {dst, src} */
+    ultra_rspmm_order_t csr;  /* forward: segments = destination rows, sorted (dst, rel, src); edge = {src, rel} */
+    ultra_rspmm_order_t csc;  /* backward w.r.t. input: segments = source rows, sorted (src, rel, dst); edge = {dst, rel} */
+    ultra_rspmm_order_t rel;  /* backward w.r.t. relation: segments = relations, sorted (rel, dst, src); edge = {dst, src} */
 } ultra_rspmm_index_t;
 
 /* ---- version / diagnostics ------------------------------------------------------------------- */

@@ -111,13 +111,15 @@ def test_empty_and_degenerate(cuda):
 
 
 def test_index_matches_coalesce(cuda):
-    """The CSR order is exactly `coalesce()` order: sorted by (row, col, layer), duplicates merged by sum."""
+    """The index holds exactly the `coalesce()`d edges (sorted, duplicates merged by sum), numbered by their position
+    in coalesce() order (`eid`), in three orders: CSR (dst, rel, src), CSC (src, rel, dst), by relation (rel, dst, src)."""
     from oracle import rspmm_oracle
     from ultra_torchdrug_b200 import functional as F
     indices, values = util.random_coo(40, 30, 6, 500, seed=2, duplicates=80, weights="random")
     shape = (40, 30, 6)
     index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), shape)
     exp_index, exp_w, _ = rspmm_oracle.coalesce(indices, values, shape)
+    row, col, rel = exp_index
     m = exp_index.shape[1]
     assert index.nnz == m and index.c.nnz_raw == indices.shape[1] and index.c.unit_weight == 0
 
@@ -128,27 +130,17 @@ def test_index_matches_coalesce(cuda):
         offset = ptr - base
         return index.buffer[offset:offset + count * torch.tensor([], dtype=dtype).element_size()].view(dtype).cpu().numpy()
 
-    ptr = view(index.c.csr.ptr, shape[0] + 1, torch.int32)
-    edge = view(index.c.csr.edge, 2 * m, torch.int32).reshape(m, 2)
-    w = view(index.c.csr.w, m, torch.float32)
-    exp_ptr = np.searchsorted(exp_index[0], np.arange(shape[0] + 1))
-    assert np.array_equal(ptr, exp_ptr)
-    assert np.array_equal(edge[:, 0], exp_index[1]) and np.array_equal(edge[:, 1], exp_index[2])
-    np.testing.assert_allclose(w, exp_w, rtol=1e-6)
-    # CSC: same multiset of edges, sorted by (src, dst, rel); eid maps back to CSR positions
-    csc_edge = view(index.c.csc.edge, 2 * m, torch.int32).reshape(m, 2)
-    csc_eid = view(index.c.csc.eid, m, torch.int32)
-    csc_ptr = view(index.c.csc.ptr, shape[1] + 1, torch.int32)
-    order = np.lexsort((exp_index[2], exp_index[0], exp_index[1]))
-    assert np.array_equal(csc_eid, order)
-    assert np.array_equal(csc_edge[:, 0], exp_index[0][order]) and np.array_equal(csc_edge[:, 1], exp_index[2][order])
-    assert np.array_equal(csc_ptr, np.searchsorted(exp_index[1][order], np.arange(shape[1] + 1)))
-    # relation order: stable by coalesced position
-    rel_eid = view(index.c.rel.eid, m, torch.int32)
-    rel_edge = view(index.c.rel.edge, 2 * m, torch.int32).reshape(m, 2)
-    order = np.argsort(exp_index[2], kind="stable")
-    assert np.array_equal(rel_eid, order)
-    assert np.array_equal(rel_edge[:, 0], exp_index[0][order]) and np.array_equal(rel_edge[:, 1], exp_index[1][order])
+    def check(order_c, order, seg, first, second, n_seg):
+        assert np.array_equal(view(order_c.eid, m, torch.int32), order)
+        edge = view(order_c.edge, 2 * m, torch.int32).reshape(m, 2)
+        assert np.array_equal(edge[:, 0], first[order]) and np.array_equal(edge[:, 1], second[order])
+        np.testing.assert_allclose(view(order_c.w, m, torch.float32), exp_w[order], rtol=1e-6)
+        assert np.array_equal(view(order_c.ptr, n_seg + 1, torch.int32), np.searchsorted(seg[order], np.arange(n_seg + 1)))
+
+    csr_order = np.lexsort((col, rel, row))
+    check(index.c.csr, csr_order, row, col, rel, shape[0])
+    check(index.c.csc, np.lexsort((row, rel, col)), col, row, rel, shape[1])
+    check(index.c.rel, csr_order[np.argsort(rel[csr_order], kind="stable")], rel, row, col, shape[2])
     # tasks cover every segment exactly once, longest first; ids are also stored packed; non-unit tasks are flagged
     for order_c, n_seg in ((index.c.csr, shape[0]), (index.c.csc, shape[1]), (index.c.rel, shape[2])):
         task = view(order_c.task, 4 * order_c.n_task, torch.int32).reshape(-1, 4)

@@ -4,9 +4,11 @@
 // (reference ultra/layer.py:127,328), `sparse.coalesce()` and torchdrug's `coo2csr3d`
 // (SURVEY.md section 8 row a5).  Done once per distinct edge set and cached by the caller.
 //
-//   1. key = (row * n_in + col) * n_rel + rel  (row = node_out, col = node_in), stable radix sort
-//   2. runs of equal keys are merged, values summed in fp64   ->  coalesced order = CSR order
-//   3. second sort by (col, row, rel)  -> CSC order (backward w.r.t. input)
+//   1. key = (row * n_rel + rel) * n_in + col  (row = node_out, col = node_in), stable radix sort
+//   2. runs of equal keys are merged, values summed in fp64   ->  CSR order (dst, rel, src): the edges of a
+//      destination are grouped by relation so that the kernel can keep a relation row in registers across
+//      consecutive edges; eid = the edge's position in canonical coalesce() order (dst, src, rel)
+//   3. second sort by (col, rel, row)  -> CSC order (backward w.r.t. input), same grouping
 //   4. third, stable sort by rel        -> relation order (backward w.r.t. relation)
 //   5. per order: segment pointers by binary search, tasks of <= chunk edges, split-segment slots,
 //      tasks sorted longest first
@@ -42,7 +44,7 @@ __global__ void make_keys_kernel(const int64_t *__restrict__ indices, int64_t st
         atomicOr(&counters[CNT_ERROR], 1);
         keys[e] = 0;
     } else {
-        keys[e] = ((unsigned long long)r * n_in + c) * n_rel + k;
+        keys[e] = ((unsigned long long)r * n_rel + k) * n_in + c;
     }
     vals[e] = (int32_t)e;
 }
@@ -67,10 +69,10 @@ __global__ void merge_kernel(const unsigned long long *__restrict__ keys, const 
     for (int64_t q = e; q < nnz && keys[q] == key; ++q) total += (double)values[vals[q]];
     const T w = (T)total;
     const int32_t m = pos[e];
-    const unsigned long long rc = key / (unsigned long long)n_rel;
-    csr_edge[m] = make_int2((int32_t)(rc % (unsigned long long)n_in), (int32_t)(key % (unsigned long long)n_rel));
+    const unsigned long long rk = key / (unsigned long long)n_in;
+    csr_edge[m] = make_int2((int32_t)(key % (unsigned long long)n_in), (int32_t)(rk % (unsigned long long)n_rel));
     csr_w[m] = w;
-    row_of[m] = (int32_t)(rc / (unsigned long long)n_in);
+    row_of[m] = (int32_t)(rk / (unsigned long long)n_rel);
     if (w != T(1)) atomicOr(&counters[CNT_NONUNIT], 1);
     if (e == 0) counters[CNT_NNZ] = pos[nnz];
 }
@@ -81,8 +83,24 @@ __global__ void csc_keys_kernel(const int2 *__restrict__ csr_edge, const int32_t
     const int32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nnz) return;
     const int2 e = csr_edge[m];
-    keys[m] = ((unsigned long long)e.x * n_out + row_of[m]) * n_rel + e.y;
+    keys[m] = ((unsigned long long)e.x * n_rel + e.y) * n_out + row_of[m];
     vals[m] = m;
+}
+
+// canonical coalesce() order (row, col, rel): used only to number the edges (eid)
+__global__ void canonical_keys_kernel(const int2 *__restrict__ csr_edge, const int32_t *__restrict__ row_of, int32_t nnz,
+                                      int64_t n_in, int64_t n_rel, unsigned long long *__restrict__ keys,
+                                      int32_t *__restrict__ vals) {
+    const int32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nnz) return;
+    const int2 e = csr_edge[m];
+    keys[m] = ((unsigned long long)row_of[m] * n_in + e.x) * n_rel + e.y;
+    vals[m] = m;
+}
+
+__global__ void rank_scatter_kernel(const int32_t *__restrict__ sorted_positions, int32_t nnz, int32_t *__restrict__ eid) {
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nnz) eid[sorted_positions[r]] = r;
 }
 
 __global__ void rel_keys_kernel(const int2 *__restrict__ csr_edge, int32_t nnz, unsigned long long *__restrict__ keys,
@@ -98,8 +116,8 @@ __global__ void rel_keys_kernel(const int2 *__restrict__ csr_edge, int32_t nnz, 
 template <typename T, int MODE>
 __global__ void permute_kernel(const int32_t *__restrict__ perm, int32_t nnz, const int2 *__restrict__ csr_edge,
                                const T *__restrict__ csr_w, const int32_t *__restrict__ row_of,
-                               int2 *__restrict__ edge, T *__restrict__ w, int32_t *__restrict__ eid,
-                               int32_t *__restrict__ seg_of) {
+                               const int32_t *__restrict__ csr_eid, int2 *__restrict__ edge, T *__restrict__ w,
+                               int32_t *__restrict__ eid, int32_t *__restrict__ seg_of) {
     const int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nnz) return;
     const int32_t m = perm[p];
@@ -108,7 +126,7 @@ __global__ void permute_kernel(const int32_t *__restrict__ perm, int32_t nnz, co
     edge[p] = MODE == 0 ? make_int2(r, e.y) : make_int2(r, e.x);
     seg_of[p] = MODE == 0 ? e.x : e.y;
     w[p] = csr_w[m];
-    eid[p] = m;
+    eid[p] = csr_eid[m];
 }
 
 // both ids of an edge in one word, and a 0/1 flag per edge for "weight differs from 1" (n + 1 entries, last = 0)
@@ -271,7 +289,7 @@ IndexLayout index_layout(int64_t nnz_raw, const int32_t n_seg[3], size_t elem, i
         q.ptr = at; at = align_up(at + sizeof(int32_t) * ((size_t)n_seg[o] + 1));
         q.edge = at; at = align_up(at + sizeof(int2) * e);
         q.w = at; at = align_up(at + elem * e);
-        q.eid = at; at = align_up(at + (o == 0 ? 0 : sizeof(int32_t) * e));
+        q.eid = at; at = align_up(at + sizeof(int32_t) * e);
         q.packed = at; at = align_up(at + sizeof(uint32_t) * e);
         q.task = at; at = align_up(at + sizeof(int4) * task_upper(nnz_raw, n_seg[o], chunk));
         q.split = at; at = align_up(at + sizeof(int4) * split_upper(nnz_raw, chunk));
@@ -362,6 +380,21 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
         nnz = host_counters[CNT_NNZ];
     }
 
+    // ---- canonical numbering of the coalesced edges (arg-index contract: position in coalesce() order) ---------
+    int32_t *csr_eid = (int32_t *)(ibuf + L.order[0].eid);
+    if (nnz > 0) {
+        canonical_keys_kernel<<<blocks_for(nnz), kBuildThreads, 0, stream>>>(csr_edge, row_of, nnz, n_in, n_rel, keys_a, vals_a);
+        note_launch();
+        const unsigned long long span = (unsigned long long)n_out * (unsigned long long)n_in * (unsigned long long)n_rel;
+        const int bits = bit_length(span > 0 ? span - 1 : 0);
+        need = S.cub_bytes;
+        ULTRA_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, need, keys_a, keys_b, vals_a, vals_b, nnz, 0,
+                                                      bits > 0 ? bits : 1, stream));
+        note_launch();
+        rank_scatter_kernel<<<blocks_for(nnz), kBuildThreads, 0, stream>>>(vals_b, nnz, csr_eid);
+        note_launch();
+    }
+
     // ---- the two other orders -------------------------------------------------------------------
     int pack_shift[3] = {0, 0, 0};
     const bool any_nonunit = host_counters[CNT_NONUNIT] != 0;
@@ -387,9 +420,9 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
                                                           bits > 0 ? bits : 1, stream));
             note_launch();
             if (o == 1)
-                permute_kernel<T, 0><<<blocks_for(nnz), kBuildThreads, 0, stream>>>(vals_b, nnz, csr_edge, csr_w, row_of, edge, w, eid, seg_of);
+                permute_kernel<T, 0><<<blocks_for(nnz), kBuildThreads, 0, stream>>>(vals_b, nnz, csr_edge, csr_w, row_of, csr_eid, edge, w, eid, seg_of);
             else
-                permute_kernel<T, 1><<<blocks_for(nnz), kBuildThreads, 0, stream>>>(vals_b, nnz, csr_edge, csr_w, row_of, edge, w, eid, seg_of);
+                permute_kernel<T, 1><<<blocks_for(nnz), kBuildThreads, 0, stream>>>(vals_b, nnz, csr_edge, csr_w, row_of, csr_eid, edge, w, eid, seg_of);
             note_launch();
             segments = seg_of;
         }
@@ -445,7 +478,7 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
         out.ptr = (const int32_t *)(ibuf + L.order[o].ptr);
         out.edge = (const int32_t *)(ibuf + L.order[o].edge);
         out.w = ibuf + L.order[o].w;
-        out.eid = o == 0 ? nullptr : (const int32_t *)(ibuf + L.order[o].eid);
+        out.eid = (const int32_t *)(ibuf + L.order[o].eid);
         out.task = (const int32_t *)(ibuf + L.order[o].task);
         out.split = (const int32_t *)(ibuf + L.order[o].split);
         if (out.n_task > task_upper(nnz_raw, n_seg[o], chunk) || out.n_split > split_upper(nnz_raw, chunk))

@@ -32,6 +32,7 @@ template <typename T> struct SegArgs {
     const int2 *edge;
     const unsigned *packed;   // edge ids packed as x | y << pack_shift (null when they do not fit 32 bits)
     int pack_shift;
+    const int32_t *eid;       // ARG only: canonical coalesce() position of each edge
     const T *w;        // null when all weights are 1
     const T *A;
     const T *B;
@@ -109,24 +110,26 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
 
     auto reduce_task = [&](auto unit_tag) {
         constexpr bool UNIT = decltype(unit_tag)::value;
+        // the edges of a segment are grouped by relation (index build), so the relation row of the previous edge
+        // is kept in registers: a batch whose edges all use it issues no table loads (half the L1 wavefronts)
+        constexpr bool CACHE = B_TABLE && MSG != MSG_COPY;
+        Vec<T, VEC> cached;
+        int cached_row = -1;
         auto accumulate = [&](const Vec<T, VEC> &va, const Vec<T, VEC> &vb, T w, int position) {
+            const int canonical = ARG ? __ldg(a.eid + position) : 0;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 const T m = UNIT ? message<T, MSG>(vb.v[v], va.v[v]) : message<T, MSG>(w, vb.v[v], va.v[v]);
-                if (ARG) {
-                    if (SUM == ULTRA_RSPMM_SUM_MAX ? (m > acc[v]) : (m < acc[v])) arg[v] = position;
+                if (ARG) {   // first edge in canonical order attaining the extremum
+                    const bool better = SUM == ULTRA_RSPMM_SUM_MAX ? (m > acc[v]) : (m < acc[v]);
+                    if (better || (m == acc[v] && canonical < arg[v])) arg[v] = canonical;
                 }
                 reduce_into<T, SUM>(acc[v], m);
             }
         };
-        auto load_pair = [&](const Ids &e, Vec<T, VEC> &va, Vec<T, VEC> &vb) {
-            gather(row_ptr<T>(A, first_id(e), row_bytes), va);
-            if (MSG != MSG_COPY) {
-                if (B_TABLE) table_load(row_ptr<T>(B, second_id(e), row_bytes), vb);
-                else gather(row_ptr<T>(B, second_id(e), row_bytes), vb);
-            } else {
-                vb = va;
-            }
+        auto load_table = [&](int row, Vec<T, VEC> &vb) {
+            if (B_TABLE) table_load(row_ptr<T>(B, row, row_bytes), vb);
+            else gather(row_ptr<T>(B, row, row_bytes), vb);
         };
         Ids ahead = Ids();
         T ahead_w = T(1);
@@ -148,18 +151,48 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
             for (; u + kUnroll <= n; u += kUnroll) {
                 Vec<T, VEC> va[kUnroll], vb[kUnroll];
                 T w[kUnroll];
+                Ids e[kUnroll];
+                bool same = CACHE;
 #pragma unroll
                 for (int q = 0; q < kUnroll; ++q) {
+                    e[q] = s_edge[warp][u + q];
                     w[q] = UNIT ? T(1) : s_w[warp][u + q];
-                    load_pair(s_edge[warp][u + q], va[q], vb[q]);
+                    same = same && second_id(e[q]) == cached_row;
+                    gather(row_ptr<T>(A, first_id(e[q]), row_bytes), va[q]);
                 }
+                if (same) {   // warp-uniform
 #pragma unroll
-                for (int q = 0; q < kUnroll; ++q) accumulate(va[q], vb[q], w[q], base + u + q);
+                    for (int q = 0; q < kUnroll; ++q) accumulate(va[q], cached, w[q], base + u + q);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < kUnroll; ++q) {
+                        if (MSG != MSG_COPY) load_table(second_id(e[q]), vb[q]);
+                        else vb[q] = va[q];
+                    }
+#pragma unroll
+                    for (int q = 0; q < kUnroll; ++q) accumulate(va[q], vb[q], w[q], base + u + q);
+                    if (CACHE) {
+                        cached = vb[kUnroll - 1];
+                        cached_row = second_id(e[kUnroll - 1]);
+                    }
+                }
             }
             for (; u < n; ++u) {
                 Vec<T, VEC> va, vb;
+                const Ids e = s_edge[warp][u];
                 const T w = UNIT ? T(1) : s_w[warp][u];
-                load_pair(s_edge[warp][u], va, vb);
+                gather(row_ptr<T>(A, first_id(e), row_bytes), va);
+                if (CACHE && second_id(e) == cached_row) {
+                    vb = cached;
+                } else if (MSG != MSG_COPY) {
+                    load_table(second_id(e), vb);
+                    if (CACHE) {
+                        cached = vb;
+                        cached_row = second_id(e);
+                    }
+                } else {
+                    vb = va;
+                }
                 accumulate(va, vb, w, base + u);
             }
         }
@@ -309,7 +342,9 @@ __global__ void combine_kernel(const int4 *__restrict__ split, int n_split, cons
         const long long at = (long long)(s.y + q) * dim + col;
         const T m = partial[at];
         if (ARG) {
-            if (SUM == ULTRA_RSPMM_SUM_MAX ? (m > acc) : (m < acc)) arg = partial_arg[at];
+            const int32_t candidate = partial_arg[at];
+            const bool better = SUM == ULTRA_RSPMM_SUM_MAX ? (m > acc) : (m < acc);
+            if (better || (m == acc && candidate >= 0 && (arg < 0 || candidate < arg))) arg = candidate;
         }
         reduce_into<T, SUM>(acc, m);
     }
@@ -393,6 +428,7 @@ int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, con
     args.edge = (const int2 *)order.edge;
     args.packed = order.pack_shift > 0 ? (const unsigned *)order.packed : nullptr;
     args.pack_shift = order.pack_shift;
+    args.eid = order.eid;
     args.w = unit_weight ? nullptr : (const T *)order.w;
     args.A = A;
     args.B = B;
