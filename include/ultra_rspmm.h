@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ULTRA_RSPMM_ABI_VERSION 2
+#define ULTRA_RSPMM_ABI_VERSION 3
 
 /* status codes (0 = ok).  For ULTRA_RSPMM_ERR_CUDA the cudaError_t is kept per thread, see
  * ultra_rspmm_last_cuda_error(). */
@@ -130,10 +130,11 @@ int ultra_rspmm_fingerprint(const int64_t *dev_indices, int64_t index_stride, co
 int ultra_rspmm_workspace_bytes(const ultra_rspmm_index_t *index, int64_t dim, int32_t dtype,
                                 size_t *forward_bytes, size_t *backward_bytes);
 /* output[i,:] = (sum)_{(i,j,k)} w * (relation[k,:] (mul) input[j,:]);  dev_argidx (n_out, dim) int32 may be
- * NULL (only meaningful for min/max). */
+ * NULL (only meaningful for min/max).  dev_addend (n_out, dim), sum_op = add only, may be NULL: it is added
+ * to the reduced rows in the kernel epilogue - the `update + boundary` of reference layer.py:156,358. */
 int ultra_rspmm_forward(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
-                        void *dev_output, int32_t *dev_argidx, int64_t dim, int32_t dtype, int32_t sum_op,
-                        int32_t mul_op, void *workspace, size_t workspace_bytes, void *stream);
+                        const void *dev_addend, void *dev_output, int32_t *dev_argidx, int64_t dim, int32_t dtype,
+                        int32_t sum_op, int32_t mul_op, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- backward: rspmm_{sum}_{mul}_backward_cuda (overload without value_grad) ------------------- */
 /* dev_output is read only for min/max (may be NULL for add).  Either gradient pointer may be NULL to

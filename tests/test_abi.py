@@ -46,12 +46,12 @@ def test_version_status_and_argument_validation():
                                            ctypes.byref(scratch_bytes)) == _lib.ERR_ARG
     assert library.ultra_rspmm_index_bytes(10, 2 ** 31 - 1, 2 ** 31 - 1, 2 ** 20, _lib.F32, ctypes.byref(index_bytes),
                                            ctypes.byref(scratch_bytes)) == _lib.ERR_RANGE
-    assert library.ultra_rspmm_forward(None, None, None, None, None, 4, _lib.F32, 0, 0, None, 0, None) == _lib.ERR_ARG
+    assert library.ultra_rspmm_forward(None, None, None, None, None, None, 4, _lib.F32, 0, 0, None, 0, None) == _lib.ERR_ARG
     index = _lib.Index()
     index.dtype = _lib.F32
-    assert library.ultra_rspmm_forward(ctypes.byref(index), None, None, None, None, 4, _lib.F64, 0, 0, None, 0,
+    assert library.ultra_rspmm_forward(ctypes.byref(index), None, None, None, None, None, 4, _lib.F64, 0, 0, None, 0,
                                        None) == _lib.ERR_DTYPE
-    assert library.ultra_rspmm_forward(ctypes.byref(index), None, None, None, None, 4, _lib.F32, 9, 0, None, 0,
+    assert library.ultra_rspmm_forward(ctypes.byref(index), None, None, None, None, None, 4, _lib.F32, 9, 0, None, 0,
                                        None) == _lib.ERR_ARG
     assert library.ultra_rspmm_set_tuning(-1, 0, 0) == _lib.ERR_ARG
     assert library.ultra_rspmm_launch_count() >= 0

@@ -299,3 +299,29 @@ def test_layer_epilogue_matches_torch(cuda, dim):
     assert not F.layer_epilogue_supported(x, 48) and not F.layer_epilogue_supported(x.cpu(), dim)
     with pytest.raises(RuntimeError):
         F.layer_norm_relu_residual(x.requires_grad_(), weight, bias)
+
+
+def test_forward_with_boundary_addend(cuda):
+    """`update + boundary` fused into the kernel epilogue (direct rows and split rows) == the separate addition."""
+    from ultra_torchdrug_b200 import _lib, functional as F
+    lib = _lib.lib()
+    lib.ultra_rspmm_set_tuning(16, 0, 0)
+    try:
+        indices, values = util.random_coo(90, 90, 6, 3000, seed=21, duplicates=30, skew=True)
+        sparse = util.to_sparse(indices, values, (90, 90, 6), cuda)
+        relation = torch.from_numpy(util.random_dense(6, 200, 1)).to(cuda)
+        input = torch.from_numpy(util.random_dense(90, 200, 2)).to(cuda)
+        boundary = torch.from_numpy(util.random_dense(90, 200, 3)).to(cuda)
+        F.clear_index_cache()
+        with torch.no_grad():
+            for mul in ("mul", "add"):
+                want = F.generalized_rspmm(sparse, relation, input, sum="add", mul=mul) + boundary
+                assert torch.equal(F.rspmm_add_boundary(sparse, relation, input, boundary, mul), want)
+        assert F.graph_index(sparse).c.csr.n_split > 0
+        with pytest.raises(RuntimeError):
+            F.graph_index(sparse).forward(relation, input, "max", "mul", addend=boundary)
+        with pytest.raises(RuntimeError):
+            F.rspmm_add_boundary(sparse, relation.requires_grad_(), input, boundary)
+    finally:
+        lib.ultra_rspmm_set_tuning(256, 0, 0)
+        F.clear_index_cache()

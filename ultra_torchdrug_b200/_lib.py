@@ -8,7 +8,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK, ERR_ARG, ERR_WORKSPACE, ERR_CUDA, ERR_INDEX, ERR_DTYPE, ERR_RANGE = range(7)
 SUM_CODE = {"add": 0, "min": 1, "max": 2}
@@ -48,7 +48,7 @@ SYMBOLS = {
     "ultra_rspmm_fingerprint": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "ultra_rspmm_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(Index), c_int64, c_int32,
                                                    ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),
-    "ultra_rspmm_forward": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+    "ultra_rspmm_forward": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                            c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "ultra_rspmm_backward": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),

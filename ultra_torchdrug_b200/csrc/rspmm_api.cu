@@ -228,7 +228,7 @@ static int ctx_run(ultra_rspmm_ctx_t *ctx, const void *host_relation, const void
         // compute
         ULTRA_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->uploaded[s], 0));
         ULTRA_CUDA_OK(cudaEventRecord(ctx->tick[2 * c], ctx->stream));
-        status = ultra_rspmm_forward(&ix, b[BUF_REL], b[BUF_IN], b[BUF_OUT], nullptr, cols, ix.dtype, sum_op, mul_op,
+        status = ultra_rspmm_forward(&ix, b[BUF_REL], b[BUF_IN], nullptr, b[BUF_OUT], nullptr, cols, ix.dtype, sum_op, mul_op,
                                      b[BUF_WS], ctx->cap[s][BUF_WS], ctx->stream);
         if (status) return status;
         if (with_backward) {

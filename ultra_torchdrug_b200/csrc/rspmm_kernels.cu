@@ -37,6 +37,7 @@ template <typename T> struct SegArgs {
     const T *A;
     const T *B;
     T *out;
+    const T *addend;        // optional (n_seg, dim): added to the reduced row (the layer's `update + boundary`)
     T *partial;
     int32_t *arg_out;       // ARG only
     int32_t *partial_arg;   // ARG only
@@ -205,6 +206,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
 #pragma unroll
     for (int v = 0; v < VEC; ++v) r.v[v] = acc[v];
     if (slot < 0) {
+        if (a.addend) {
+            Vec<T, VEC> b;
+            gather_load(a.addend + (long long)task.x * a.dim + col, b);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) r.v[v] += b.v[v];
+        }
         stream_store(a.out + (long long)task.x * a.dim + col, r);
     } else {
         T *p = a.partial + (long long)slot * a.dim + col;   // re-read soon by the combine pass: default policy
@@ -331,8 +338,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 3) seg_gated_kernel(const Ga
 // Fixed-order fold of the partial rows of split segments (deterministic second stage).
 template <typename T, int SUM, bool ARG>
 __global__ void combine_kernel(const int4 *__restrict__ split, int n_split, const T *__restrict__ partial,
-                               const int32_t *__restrict__ partial_arg, T *__restrict__ out,
-                               int32_t *__restrict__ arg_out, long long dim) {
+                               const int32_t *__restrict__ partial_arg, const T *__restrict__ addend,
+                               T *__restrict__ out, int32_t *__restrict__ arg_out, long long dim) {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= dim) return;
     const int4 s = __ldg(split + blockIdx.y);
@@ -348,6 +355,7 @@ __global__ void combine_kernel(const int4 *__restrict__ split, int n_split, cons
         }
         reduce_into<T, SUM>(acc, m);
     }
+    if (addend) acc += addend[(long long)s.x * dim + col];
     out[(long long)s.x * dim + col] = acc;
     if (ARG) arg_out[(long long)s.x * dim + col] = arg;
 }
@@ -382,7 +390,7 @@ int launch_seg(const SegArgs<T> &args, cudaStream_t stream) {
 
 template <typename T, int SUM, bool ARG>
 int launch_combine(const ultra_rspmm_order_t &order, const T *partial, const int32_t *partial_arg, T *out,
-                   int32_t *arg_out, long long dim, cudaStream_t stream) {
+                   int32_t *arg_out, long long dim, cudaStream_t stream, const T *addend = nullptr) {
     if (order.n_split == 0 || dim == 0) return ULTRA_RSPMM_OK;
     const dim3 grid((unsigned)((dim + 255) / 256), (unsigned)order.n_split);
     if (order.n_split > 65535) {
@@ -390,13 +398,13 @@ int launch_combine(const ultra_rspmm_order_t &order, const T *partial, const int
         for (int at = 0; at < order.n_split; at += 65535) {
             const int n = order.n_split - at < 65535 ? order.n_split - at : 65535;
             combine_kernel<T, SUM, ARG><<<dim3(grid.x, n), 256, 0, stream>>>((const int4 *)order.split + at, n, partial,
-                                                                              partial_arg, out, arg_out, dim);
+                                                                              partial_arg, addend, out, arg_out, dim);
             note_launch();
         }
         return ULTRA_RSPMM_OK;
     }
     combine_kernel<T, SUM, ARG><<<grid, 256, 0, stream>>>((const int4 *)order.split, order.n_split, partial, partial_arg,
-                                                          out, arg_out, dim);
+                                                          addend, out, arg_out, dim);
     note_launch();
     return ULTRA_RSPMM_OK;
 }
@@ -422,7 +430,7 @@ int pick_vec(long long dim, long long rows, std::initializer_list<const void *> 
 // one reduction pass + its combine
 template <typename T, int SUM, int MSG, bool B_TABLE, bool ARG>
 int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, const T *B, long long rows_gathered, T *out,
-             int32_t *arg_out, long long dim, void *workspace, cudaStream_t stream) {
+             int32_t *arg_out, long long dim, void *workspace, cudaStream_t stream, const T *addend = nullptr) {
     SegArgs<T> args;
     args.task = (const int4 *)order.task;
     args.edge = (const int2 *)order.edge;
@@ -433,12 +441,13 @@ int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, con
     args.A = A;
     args.B = B;
     args.out = out;
+    args.addend = addend;
     args.partial = (T *)workspace;
     args.arg_out = arg_out;
     args.partial_arg = ARG ? (int32_t *)((char *)workspace + align_up((size_t)order.n_slot * dim * sizeof(T))) : nullptr;
     args.dim = dim;
     args.n_task = order.n_task;
-    const int vec = pick_vec<T>(dim, rows_gathered, {A, B, out, workspace});
+    const int vec = pick_vec<T>(dim, rows_gathered, {A, B, out, workspace, addend});
     args.n_slab = (int)((dim + 32 * vec - 1) / (32 * vec));
     args.keep = g_variant == 2 || (g_variant == 0 && rows_gathered * 32 * vec * (long long)sizeof(T) > (24ll << 20));
     int status;
@@ -446,7 +455,7 @@ int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, con
     else if (vec == 2) status = launch_seg<T, 2, SUM, MSG, B_TABLE, ARG>(args, stream);
     else status = launch_seg<T, 1, SUM, MSG, B_TABLE, ARG>(args, stream);
     if (status) return status;
-    return launch_combine<T, SUM, ARG>(order, args.partial, args.partial_arg, out, arg_out, dim, stream);
+    return launch_combine<T, SUM, ARG>(order, args.partial, args.partial_arg, out, arg_out, dim, stream, addend);
 }
 
 template <typename T, int VEC, int MSG, bool P_TABLE>
@@ -485,7 +494,7 @@ int run_gated(const ultra_rspmm_order_t &order, bool unit_weight, const T *G, co
 
 template <typename T, int SUM>
 int forward_sum(const ultra_rspmm_index_t &ix, const T *relation, const T *input, T *output, int32_t *argidx,
-                long long dim, int mul_op, void *ws, cudaStream_t stream) {
+                long long dim, int mul_op, void *ws, cudaStream_t stream, const T *addend = nullptr) {
     const bool unit = ix.unit_weight != 0;
     if (SUM != ULTRA_RSPMM_SUM_ADD && argidx) {
         if (mul_op == ULTRA_RSPMM_MUL_MUL)
@@ -493,17 +502,18 @@ int forward_sum(const ultra_rspmm_index_t &ix, const T *relation, const T *input
         return run_pass<T, SUM, MSG_ADD, true, true>(ix.csr, unit, input, relation, ix.n_in, output, argidx, dim, ws, stream);
     }
     if (mul_op == ULTRA_RSPMM_MUL_MUL)
-        return run_pass<T, SUM, MSG_MUL, true, false>(ix.csr, unit, input, relation, ix.n_in, output, nullptr, dim, ws, stream);
-    return run_pass<T, SUM, MSG_ADD, true, false>(ix.csr, unit, input, relation, ix.n_in, output, nullptr, dim, ws, stream);
+        return run_pass<T, SUM, MSG_MUL, true, false>(ix.csr, unit, input, relation, ix.n_in, output, nullptr, dim, ws, stream, addend);
+    return run_pass<T, SUM, MSG_ADD, true, false>(ix.csr, unit, input, relation, ix.n_in, output, nullptr, dim, ws, stream, addend);
 }
 
 template <typename T>
-int forward_typed(const ultra_rspmm_index_t &ix, const void *relation, const void *input, void *output, int32_t *argidx,
-                  long long dim, int sum_op, int mul_op, void *ws, cudaStream_t stream) {
+int forward_typed(const ultra_rspmm_index_t &ix, const void *relation, const void *input, const void *addend, void *output,
+                  int32_t *argidx, long long dim, int sum_op, int mul_op, void *ws, cudaStream_t stream) {
     const T *r = (const T *)relation, *x = (const T *)input;
     T *o = (T *)output;
     switch (sum_op) {
-        case ULTRA_RSPMM_SUM_ADD: return forward_sum<T, ULTRA_RSPMM_SUM_ADD>(ix, r, x, o, nullptr, dim, mul_op, ws, stream);
+        case ULTRA_RSPMM_SUM_ADD:
+            return forward_sum<T, ULTRA_RSPMM_SUM_ADD>(ix, r, x, o, nullptr, dim, mul_op, ws, stream, (const T *)addend);
         case ULTRA_RSPMM_SUM_MIN: return forward_sum<T, ULTRA_RSPMM_SUM_MIN>(ix, r, x, o, argidx, dim, mul_op, ws, stream);
         default: return forward_sum<T, ULTRA_RSPMM_SUM_MAX>(ix, r, x, o, argidx, dim, mul_op, ws, stream);
     }
@@ -577,10 +587,12 @@ extern "C" int ultra_rspmm_workspace_bytes(const ultra_rspmm_index_t *index, int
 }
 
 extern "C" int ultra_rspmm_forward(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
-                                   void *dev_output, int32_t *dev_argidx, int64_t dim, int32_t dtype, int32_t sum_op,
-                                   int32_t mul_op, void *workspace, size_t workspace_bytes, void *stream) {
+                                   const void *dev_addend, void *dev_output, int32_t *dev_argidx, int64_t dim,
+                                   int32_t dtype, int32_t sum_op, int32_t mul_op, void *workspace, size_t workspace_bytes,
+                                   void *stream) {
     int status = check_call(index, dim, dtype, sum_op, mul_op);
     if (status) return status;
+    if (dev_addend && sum_op != ULTRA_RSPMM_SUM_ADD) return ULTRA_RSPMM_ERR_ARG;
     if (index->n_out == 0 || dim == 0) return ULTRA_RSPMM_OK;
     if (!dev_output || ((index->n_rel > 0 && !dev_relation) || (index->n_in > 0 && !dev_input)))
         return ULTRA_RSPMM_ERR_ARG;
@@ -589,8 +601,8 @@ extern "C" int ultra_rspmm_forward(const ultra_rspmm_index_t *index, const void 
     if (index->csr.n_slot > 0 && (!workspace || workspace_bytes < need)) return ULTRA_RSPMM_ERR_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
     status = dtype == ULTRA_RSPMM_F32
-                 ? forward_typed<float>(*index, dev_relation, dev_input, dev_output, dev_argidx, dim, sum_op, mul_op, workspace, s)
-                 : forward_typed<double>(*index, dev_relation, dev_input, dev_output, dev_argidx, dim, sum_op, mul_op, workspace, s);
+                 ? forward_typed<float>(*index, dev_relation, dev_input, dev_addend, dev_output, dev_argidx, dim, sum_op, mul_op, workspace, s)
+                 : forward_typed<double>(*index, dev_relation, dev_input, dev_addend, dev_output, dev_argidx, dim, sum_op, mul_op, workspace, s);
     if (status) return status;
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;

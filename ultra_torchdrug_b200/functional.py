@@ -19,7 +19,7 @@ import torch
 from . import _lib
 
 __all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
-           "layer_norm_relu_residual", "layer_epilogue_supported"]
+           "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary"]
 
 _SUM_OPS = ("add", "min", "max")
 _MUL_OPS = ("mul", "add")
@@ -92,8 +92,10 @@ class GraphIndex(object):
         return self._workspace_bytes[dim]
 
     # -- raw operator calls (device tensors in, device tensors out) ---------------------------------
-    def forward(self, relation, input, sum="add", mul="mul", return_argidx=False):
+    def forward(self, relation, input, sum="add", mul="mul", return_argidx=False, addend=None):
         dim = input.shape[1]
+        if addend is not None and (sum != "add" or addend.shape != (self.shape[0], dim) or addend.dtype != input.dtype):
+            raise RuntimeError("`addend` needs sum='add' and the shape / dtype of the output")
         output = torch.empty((self.shape[0], dim), dtype=input.dtype, device=input.device)
         argidx = None
         if return_argidx and sum != "add":
@@ -102,7 +104,7 @@ class GraphIndex(object):
         with torch.cuda.device(input.device):
             workspace = torch.empty(need, dtype=torch.uint8, device=input.device) if need else None
             _lib.check(_lib.lib().ultra_rspmm_forward(
-                ctypes.byref(self.c), _ptr(relation), _ptr(input), _ptr(output), _ptr(argidx), dim,
+                ctypes.byref(self.c), _ptr(relation), _ptr(input), _ptr(addend), _ptr(output), _ptr(argidx), dim,
                 _DTYPE_CODE[self.dtype], _lib.SUM_CODE[sum], _lib.MUL_CODE[mul], _ptr(workspace), need,
                 _stream_handle()), "ultra_rspmm_forward")
         return (output, argidx) if return_argidx else output
@@ -208,6 +210,18 @@ def graph_index(sparse):
     except Exception:
         pass
     return index
+
+
+def rspmm_add_boundary(sparse, relation, input, boundary, mul="mul"):
+    """`generalized_rspmm(sparse, relation, input, sum="add", mul=mul) + boundary` with the addition done in the
+    kernel epilogue (reference layer.py:155-156, 357-358).  Inference only (no autograd graph is recorded)."""
+    _check_operands(sparse, relation, input)
+    if mul not in _MUL_OPS:
+        raise ValueError("Unknown multiplication `%s`" % mul)
+    if torch.is_grad_enabled() and (relation.requires_grad or input.requires_grad or boundary.requires_grad):
+        raise RuntimeError("rspmm_add_boundary is an inference-only entry point")
+    index = graph_index(sparse)
+    return index.forward(relation.contiguous(), input.contiguous(), "add", mul, addend=boundary.contiguous())
 
 
 def _check_operands(sparse, relation, input):

@@ -38,6 +38,9 @@ def _aggregate(adjacency, relation_input, input, boundary, degree_out, aggregate
     bounded = not aggregate_func.endswith("_nobound")
     name = aggregate_func[:-len("_nobound")] if not bounded else aggregate_func
     if name == "sum":
+        tensors = (relation_input, input, boundary)
+        if bounded and input.is_cuda and not (torch.is_grad_enabled() and any(t.requires_grad for t in tensors)):
+            return rspmm.rspmm_add_boundary(adjacency, relation_input, input, boundary, mul)   # one pass
         update = op("add")
         return update + boundary if bounded else update
     if name == "mean":
@@ -241,7 +244,13 @@ class TransferNBFNet(nn.Module):
         # tensors that is two host synchronisations per pass, so the mirror only checks host tensors
         if not h_index.is_cuda:
             assert (h_index[:, [0]] == h_index).all() and (r_index[:, [0]] == r_index).all()
-        feature = self.bellmanford(graph, h_index[:, 0], r_index[:, 0]).transpose(0, 1)
+        feature = self.bellmanford(graph, h_index[:, 0], r_index[:, 0])           # (N, B, 2d)
+        if 2 * t_index.shape[1] >= graph.num_node:
+            # ranking against (almost) all entities: score every node once, then pick - the MLP is row-wise, so this
+            # equals the reference's gather-then-score (model.py:177-193) without copying the (B, N, 2d) feature tensor
+            score = self.mlp(feature).squeeze(-1).transpose(0, 1)                 # (B, N)
+            return score.gather(1, t_index).view(shape)
+        feature = feature.transpose(0, 1)
         feature = feature.gather(1, t_index.unsqueeze(-1).expand(-1, -1, feature.shape[-1]))
         return self.mlp(feature).squeeze(-1).view(shape)
 
