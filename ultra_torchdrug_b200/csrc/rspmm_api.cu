@@ -180,7 +180,9 @@ static int ctx_run(ultra_rspmm_ctx_t *ctx, const void *host_relation, const void
     ULTRA_CUDA_OK(cudaSetDevice(ctx->device));
     const ultra_rspmm_index_t &ix = ctx->index;
     const size_t elem = ix.dtype == ULTRA_RSPMM_F32 ? 4 : 8;
-    const int64_t chunk_cols = dim < kChunkCols ? dim : kChunkCols;
+    int64_t chunk_target = kChunkCols;
+    if (const char *env = getenv("ULTRA_RSPMM_CHUNK_COLS")) chunk_target = atoll(env) > 0 ? atoll(env) : kChunkCols;
+    const int64_t chunk_cols = dim < chunk_target ? dim : chunk_target;
     const int n_chunk = dim == 0 ? 0 : (int)((dim + chunk_cols - 1) / chunk_cols);
     ctx->last_ms = 0.f;
     if (n_chunk == 0) return ULTRA_RSPMM_OK;

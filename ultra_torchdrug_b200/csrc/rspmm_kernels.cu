@@ -25,7 +25,8 @@ namespace ultra {
 
 namespace {
 
-constexpr int kUnroll = 4;   // 4 edges in flight per warp at 4 CTAs/SM beat 2x5, 6x3, 8x3, 8x2 (profiles/README.md)
+constexpr int kUnroll = 4;
+static_assert(kUnroll == 4, "the tail switch in seg_reduce_kernel enumerates 1..3 leftover edges");   // 4 edges in flight per warp at 4 CTAs/SM beat 2x5, 6x3, 8x3, 8x2 (profiles/README.md)
 
 template <typename T> struct SegArgs {
     const int4 *task;
@@ -148,14 +149,16 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
                 ahead = load_ids(ids + base + 32 + lane);
                 if (!UNIT) ahead_w = __ldg(a.w + base + 32 + lane);
             }
-            int u = 0;
-            for (; u + kUnroll <= n; u += kUnroll) {
-                Vec<T, VEC> va[kUnroll], vb[kUnroll];
-                T w[kUnroll];
-                Ids e[kUnroll];
+            // COUNT edges at once: all loads are issued before the first use; the ragged tail of a task (1..3 edges)
+            // runs as one specialised batch instead of one memory round trip per edge
+            auto run_batch = [&](auto count_tag, int u) {
+                constexpr int COUNT = decltype(count_tag)::value;
+                Vec<T, VEC> va[COUNT], vb[COUNT];
+                T w[COUNT];
+                Ids e[COUNT];
                 bool same = CACHE;
 #pragma unroll
-                for (int q = 0; q < kUnroll; ++q) {
+                for (int q = 0; q < COUNT; ++q) {
                     e[q] = s_edge[warp][u + q];
                     w[q] = UNIT ? T(1) : s_w[warp][u + q];
                     same = same && second_id(e[q]) == cached_row;
@@ -163,38 +166,28 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
                 }
                 if (same) {   // warp-uniform
 #pragma unroll
-                    for (int q = 0; q < kUnroll; ++q) accumulate(va[q], cached, w[q], base + u + q);
+                    for (int q = 0; q < COUNT; ++q) accumulate(va[q], cached, w[q], base + u + q);
                 } else {
 #pragma unroll
-                    for (int q = 0; q < kUnroll; ++q) {
+                    for (int q = 0; q < COUNT; ++q) {
                         if (MSG != MSG_COPY) load_table(second_id(e[q]), vb[q]);
                         else vb[q] = va[q];
                     }
 #pragma unroll
-                    for (int q = 0; q < kUnroll; ++q) accumulate(va[q], vb[q], w[q], base + u + q);
+                    for (int q = 0; q < COUNT; ++q) accumulate(va[q], vb[q], w[q], base + u + q);
                     if (CACHE) {
-                        cached = vb[kUnroll - 1];
-                        cached_row = second_id(e[kUnroll - 1]);
+                        cached = vb[COUNT - 1];
+                        cached_row = second_id(e[COUNT - 1]);
                     }
                 }
-            }
-            for (; u < n; ++u) {
-                Vec<T, VEC> va, vb;
-                const Ids e = s_edge[warp][u];
-                const T w = UNIT ? T(1) : s_w[warp][u];
-                gather(row_ptr<T>(A, first_id(e), row_bytes), va);
-                if (CACHE && second_id(e) == cached_row) {
-                    vb = cached;
-                } else if (MSG != MSG_COPY) {
-                    load_table(second_id(e), vb);
-                    if (CACHE) {
-                        cached = vb;
-                        cached_row = second_id(e);
-                    }
-                } else {
-                    vb = va;
-                }
-                accumulate(va, vb, w, base + u);
+            };
+            int u = 0;
+            for (; u + kUnroll <= n; u += kUnroll) run_batch(std::integral_constant<int, kUnroll>(), u);
+            switch (n - u) {
+                case 1: run_batch(std::integral_constant<int, 1>(), u); break;
+                case 2: run_batch(std::integral_constant<int, 2>(), u); break;
+                case 3: run_batch(std::integral_constant<int, 3>(), u); break;
+                default: break;
             }
         }
     };
