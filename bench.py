@@ -297,6 +297,14 @@ def run_gpu_arm(args):
                          "peak_source": peak_source, "algorithmic_bytes_per_launch": bytes_fwd,
                          "launch_ms": forward_ms,
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         # companion figures SURVEY.md 8d asks for beside the edge-model fraction
+                         "compulsory_bytes_per_launch": 4 * d * (2 * n + r) + 12 * e + 4 * (n + 1),
+                         "compulsory_frac": (4 * d * (2 * n + r) + 12 * e + 4 * (n + 1)) / (forward_ms * 1e-3) / 1e9 / peak,
+                         "ncu": {k: traffic[k] for k in ("l2_hit_rate_pct", "l1_hit_rate_pct", "l2_bytes_read_by_sm",
+                                                         "l1tex_throughput_pct", "lts_throughput_pct", "source")
+                                 if k in traffic} if traffic else None,
+                         "binding_unit": "L1 data pipe (128 B/clk/SM: gathered row + relation row = 8 wavefronts per "
+                                         "edge and 128-feature slab); L2->SM bandwidth for the relation-gradient pass",
                          "note": "edge-model bytes count one D-wide row gather per edge; slab-major scheduling "
                                  "serves those gathers from L2, so frac > 1 is expected and DRAM traffic is near the "
                                  "compulsory 2*N*D*4 bytes (see profiles/)"},

@@ -95,5 +95,41 @@ def main():
           len([k for k in record if k.startswith("grad/")]))
 
 
+def c1_case():
+    """BASELINE.json configs[0] shape (FB15k237Inductive-v1: 1,594 entities, 180 relations, 4,245 triples) with the
+    shipped architecture (6 + 6 layers x 64-d, reference config/transductive/inference.yaml), seeded random weights
+    (the td_ultra_4g.pth blob is missing from the reference tree), evaluation branch, 8 test triples = 16 queries."""
+    torch.manual_seed(1024)
+    num_node, num_relation, num_triple = synthetic.SHAPES["fb15k237_ind_v1"]
+    triples = synthetic.triples(num_node, num_relation, num_triple, seed=1024)
+    graph = data.Graph(triples, num_node=num_node, num_relation=num_relation)
+    model = ref_model.TransferNBFNet(input_dim=64, hidden_dims=[64] * 6, num_relation=num_relation,
+                                     message_func="distmult", aggregate_func="sum", short_cut=True, layer_norm=True,
+                                     project=True, mod=True)
+    rel_model = ref_rel_model.RelNBFNet(input_dim=64, hidden=64, num_layers=6, input_type="ones")
+    rel_graph = rel_model.construct_relation_graph(graph)
+    batch = triples[torch.randperm(num_triple)[:8]]
+    pos_h, pos_t, pos_r = batch.t()
+    model.eval()
+    rel_model.eval()
+    with torch.no_grad():
+        rel_input = rel_model(rel_graph, None, pos_r)["node_feature"]
+        candidates = torch.arange(num_node)
+        r_index = pos_r.unsqueeze(-1).expand(-1, num_node)
+        h_index, t_index = torch.meshgrid(pos_h, candidates, indexing="ij")
+        t_pred = model(graph, [rel_input], h_index, t_index, r_index)
+        t_index, h_index = torch.meshgrid(pos_t, candidates, indexing="ij")
+        h_pred = model(graph, [rel_input], h_index, t_index, r_index)
+    record = {"batch": batch.numpy(), "shape": np.array([num_node, num_relation, 64, 6]),
+              "num_rel_graph_edge": np.array(rel_graph.num_edge), "pred": torch.stack([t_pred, h_pred], dim=1).numpy().copy()}
+    for prefix, module in (("model/", model), ("rel_model/", rel_model)):
+        for name, tensor in module.state_dict().items():
+            record[prefix + name] = tensor.numpy().copy()
+    path = os.path.join(HERE, "model_ultra_c1.npz")
+    np.savez_compressed(path, **record)
+    print("wrote", path, "pred", record["pred"].shape, "relation graph edges", rel_graph.num_edge)
+
+
 if __name__ == "__main__":
     main()
+    c1_case()

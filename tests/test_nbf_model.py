@@ -85,3 +85,38 @@ def test_mirror_on_cuda_matches_reference_modules(cuda):
     before = F.launch_count()
     _check(g, model, rel_model, graph, cuda, rtol=2e-4, atol=2e-5)
     assert F.launch_count() > before
+
+
+# ---- BASELINE.json configs[0]: FB15k237Inductive-v1 shape, shipped architecture (6 + 6 layers x 64-d) ------------------
+GOLDEN_C1 = os.path.join(os.path.dirname(__file__), "golden", "model_ultra_c1.npz")
+
+
+def _check_c1(device, rtol, atol):
+    from ultra_torchdrug_b200 import synthetic
+    g = np.load(GOLDEN_C1)
+    num_node, num_relation, hidden, num_layers = (int(x) for x in g["shape"])
+    model, rel_model = nbf.ultra_models(num_relation, hidden=hidden, num_layers=num_layers)
+    for prefix, module in (("model/", model), ("rel_model/", rel_model)):
+        module.load_state_dict({k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}, strict=True)
+    assert sum(p.numel() for p in model.parameters()) + sum(p.numel() for p in rel_model.parameters()) == 117505 + 76608
+    triples = synthetic.triples(num_node, num_relation, synthetic.SHAPES["fb15k237_ind_v1"][2], seed=1024)
+    graph = data.Graph(triples, num_node=num_node, num_relation=num_relation).to(device)
+    ranker = nbf.UltraRanker(model.to(device).eval(), rel_model.to(device).eval(), graph)
+    assert ranker.rel_graph.num_edge == int(g["num_rel_graph_edge"])
+    batch = torch.from_numpy(g["batch"]).to(device)
+    with torch.no_grad():
+        pred = ranker.predict(batch)
+    want = torch.from_numpy(g["pred"]).to(device)
+    torch.testing.assert_close(pred, want, rtol=rtol, atol=atol)
+    target = torch.stack([batch[:, 1], batch[:, 0]], dim=1)
+    mask = ranker.filter_mask(batch)
+    got, ref = nbf.metrics(ranker.rank(pred, target, mask)), nbf.metrics(ranker.rank(want, target, mask))
+    for name in ("mrr", "hits@10", "hits@1", "mr"):      # north_star: MRR / Hits@10 equal to 4 decimals
+        assert round(got[name], 4) == round(ref[name], 4), (name, got, ref)
+
+
+@pytest.mark.gpu
+def test_c1_zero_shot_scores_and_mrr_on_cuda(cuda):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    _check_c1(cuda, rtol=1e-3, atol=1e-4)
