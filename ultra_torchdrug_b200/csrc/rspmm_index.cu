@@ -257,6 +257,26 @@ __global__ void fingerprint_kernel(const int64_t *__restrict__ indices, int64_t 
     }
 }
 
+// Stable radix sort of (key, value) pairs from the `in` buffers into the `out` buffers.  Uses CUB's DoubleBuffer
+// form (the plain form allocates a second copy of both arrays inside its temporary storage: 12 bytes per edge);
+// the result is copied over when the last pass happened to land in the `in` buffers.
+template <typename K, typename V>
+int sort_pairs(void *tmp, size_t tmp_bytes, K *keys_in, K *keys_out, V *vals_in, V *vals_out, int n, int bits,
+               cudaStream_t stream) {
+    cub::DoubleBuffer<K> keys(keys_in, keys_out);
+    cub::DoubleBuffer<V> vals(vals_in, vals_out);
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, n, 0, bits > 0 ? bits : 1, stream);
+    if (need > tmp_bytes) return ULTRA_RSPMM_ERR_WORKSPACE;
+    ULTRA_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp, need, keys, vals, n, 0, bits > 0 ? bits : 1, stream));
+    note_launch();
+    if (keys.Current() != keys_out)
+        ULTRA_CUDA_OK(cudaMemcpyAsync(keys_out, keys.Current(), sizeof(K) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+    if (vals.Current() != vals_out)
+        ULTRA_CUDA_OK(cudaMemcpyAsync(vals_out, vals.Current(), sizeof(V) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+    return ULTRA_RSPMM_OK;
+}
+
 int bit_length(unsigned long long v) {
     int bits = 0;
     while (v) { ++bits; v >>= 1; }
@@ -321,7 +341,7 @@ ScratchLayout scratch_layout(int64_t nnz_raw, int32_t n_seg_max, int chunk) {
     S.counters = at; at = align_up(at + 4 * CNT_SIZE);
     S.cub = at;
     // CUB temporary storage: radix sort / scan need O(tiles) words; provision generously and verify at build time
-    S.cub_bytes = align_up((size_t)(16u << 20) + 8 * e + 8 * nt);
+    S.cub_bytes = align_up((size_t)(16u << 20) + e + nt);   // radix-sort histograms / scan tile states: O(items / tile)
     at += S.cub_bytes;
     S.total = at;
     return S;
@@ -356,13 +376,8 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
         note_launch();
         const unsigned long long span = (unsigned long long)n_out * (unsigned long long)n_in * (unsigned long long)n_rel;
         const int bits = bit_length(span > 0 ? span - 1 : 0);
-        need = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, need, keys_a, keys_b, vals_a, vals_b, (int)nnz_raw, 0, bits > 0 ? bits : 1, stream);
-        if (need > S.cub_bytes) return ULTRA_RSPMM_ERR_WORKSPACE;
-        need = S.cub_bytes;
-        ULTRA_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, need, keys_a, keys_b, vals_a, vals_b, (int)nnz_raw, 0,
-                                                      bits > 0 ? bits : 1, stream));
-        note_launch();
+        if (int status = sort_pairs(cub_tmp, S.cub_bytes, keys_a, keys_b, vals_a, vals_b, (int)nnz_raw, bits, stream))
+            return status;
         head_flags_kernel<<<blocks_for(nnz_raw + 1), kBuildThreads, 0, stream>>>(keys_b, nnz_raw, vals_a);
         note_launch();
         need = 0;
@@ -387,10 +402,7 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
         note_launch();
         const unsigned long long span = (unsigned long long)n_out * (unsigned long long)n_in * (unsigned long long)n_rel;
         const int bits = bit_length(span > 0 ? span - 1 : 0);
-        need = S.cub_bytes;
-        ULTRA_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, need, keys_a, keys_b, vals_a, vals_b, nnz, 0,
-                                                      bits > 0 ? bits : 1, stream));
-        note_launch();
+        if (int status = sort_pairs(cub_tmp, S.cub_bytes, keys_a, keys_b, vals_a, vals_b, nnz, bits, stream)) return status;
         rank_scatter_kernel<<<blocks_for(nnz), kBuildThreads, 0, stream>>>(vals_b, nnz, csr_eid);
         note_launch();
     }
@@ -415,10 +427,7 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
                 bits = bit_length(n_rel > 0 ? (unsigned long long)n_rel - 1 : 0);
             }
             note_launch();
-            need = S.cub_bytes;
-            ULTRA_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, need, keys_a, keys_b, vals_a, vals_b, nnz, 0,
-                                                          bits > 0 ? bits : 1, stream));
-            note_launch();
+            if (int status = sort_pairs(cub_tmp, S.cub_bytes, keys_a, keys_b, vals_a, vals_b, nnz, bits, stream)) return status;
             if (o == 1)
                 permute_kernel<T, 0><<<blocks_for(nnz), kBuildThreads, 0, stream>>>(vals_b, nnz, csr_edge, csr_w, row_of, csr_eid, edge, w, eid, seg_of);
             else
@@ -492,10 +501,9 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
             any_nonunit ? (const int32_t *)(sbuf + S.nonunit) + (size_t)o * ((size_t)(nnz_raw > 0 ? nnz_raw : 1) + 1) : nullptr,
             task_tmp, tkey_a, tval_a, (int4 *)(ibuf + L.order[o].split));
         note_launch();
-        need = S.cub_bytes;
-        ULTRA_CUDA_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, need, tkey_a, tkey_b, tval_a, tval_b, out.n_task, 0,
-                                                      bit_length((unsigned long long)chunk), stream));
-        note_launch();
+        if (int status = sort_pairs(cub_tmp, S.cub_bytes, tkey_a, tkey_b, tval_a, tval_b, out.n_task,
+                                    bit_length((unsigned long long)chunk), stream))
+            return status;
         task_gather_kernel<<<blocks_for(out.n_task), kBuildThreads, 0, stream>>>(task_tmp, tval_b, out.n_task,
                                                                                (int4 *)(ibuf + L.order[o].task));
         note_launch();
