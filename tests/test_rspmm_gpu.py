@@ -325,3 +325,25 @@ def test_forward_with_boundary_addend(cuda):
     finally:
         lib.ultra_rspmm_set_tuning(256, 0, 0)
         F.clear_index_cache()
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_parity_randomized(cuda, seed):
+    """Seeded random shapes: rectangular operands, self-loops, isolated rows, Zipf destinations, odd feature widths,
+    tiny / huge chunk sizes, unit and merged weights, fp32 and fp64 (SURVEY.md section 8c test (4))."""
+    from ultra_torchdrug_b200 import _lib
+    rng = np.random.default_rng(1000 + seed)
+    n_out, n_in = int(rng.integers(1, 120)), int(rng.integers(1, 120))
+    n_rel = int(rng.choice([1, 2, 4, 9, 40]))
+    nnz = int(rng.integers(0, 6 * max(n_out, n_in)))
+    dim = int(rng.choice([1, 2, 5, 8, 31, 64, 96, 129, 256, 300]))
+    sum, mul = util.OPS[seed % len(util.OPS)]
+    chunk = int(rng.choice([4, 32, 256]))
+    dtype = np.float64 if seed % 5 == 4 else np.float32
+    lib = _lib.lib()
+    lib.ultra_rspmm_set_tuning(chunk, int(rng.integers(0, 3)), 0)
+    try:
+        _run_case(cuda, n_out, n_in, n_rel, nnz, dim, sum, mul, seed=seed, duplicates=int(rng.integers(0, 20)) if nnz else 0,
+                  weights="random" if seed % 3 == 0 else "unit", skew=bool(seed % 2), ties=bool(seed % 4 == 1), dtype=dtype)
+    finally:
+        lib.ultra_rspmm_set_tuning(256, 0, 0)

@@ -225,6 +225,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
 template <typename T> struct GatedArgs {
     const int4 *task;
     const int2 *edge;
+    const unsigned *packed;
+    int pack_shift;
+    int keep;
     const T *w;
     const T *G;   // grad_output, gathered by edge.x
     const T *O;   // output, gathered by edge.x
@@ -237,10 +240,11 @@ template <typename T> struct GatedArgs {
     int n_slab;
 };
 
-template <typename T, int VEC, int MSG, bool P_TABLE, bool UNIT>
+template <typename T, int VEC, int MSG, bool P_TABLE, bool PACKED, bool KEEP>
 __global__ void __launch_bounds__(kThreadsPerBlock, 3) seg_gated_kernel(const GatedArgs<T> a) {
-    __shared__ int2 s_edge[kWarpsPerBlock][32];
-    __shared__ T s_w[UNIT ? 1 : kWarpsPerBlock][32];
+    using Ids = typename std::conditional<PACKED, unsigned, int2>::type;
+    __shared__ __align__(16) Ids s_edge[kWarpsPerBlock][32];
+    __shared__ __align__(16) T s_w[kWarpsPerBlock][32];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long gw = (long long)blockIdx.x * kWarpsPerBlock + warp;
@@ -255,6 +259,17 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 3) seg_gated_kernel(const Ga
     const char *G = reinterpret_cast<const char *>(a.G + safe_col);
     const char *O = reinterpret_cast<const char *>(a.O + safe_col);
     const char *P = reinterpret_cast<const char *>(a.P + safe_col);
+    const Ids *ids = reinterpret_cast<const Ids *>(PACKED ? (const void *)a.packed : (const void *)a.edge);
+    const int shift = a.pack_shift;
+    const unsigned low = PACKED ? (shift >= 32 ? 0xffffffffu : ((1u << shift) - 1u)) : 0u;
+    const unsigned long long keep_policy = KEEP ? policy_evict_last() : 0, once_policy = KEEP ? policy_evict_first() : 0;
+    auto gather = [&](const T *p, Vec<T, VEC> &v) {
+        if (KEEP) gather_load_keep(p, v, keep_policy);
+        else gather_load(p, v);
+    };
+    auto load_ids = [&](const Ids *p) { return KEEP ? edge_load_once(p, once_policy) : __ldg(p); };
+    auto first_id = [&](const Ids &e) { return PACKED ? (int)(id_bits(e) & low) : id_x(e); };
+    auto second_id = [&](const Ids &e) { return PACKED ? (int)(id_bits(e) >> shift) : id_y(e); };
 
     Vec<T, VEC> own;
     T acc[VEC];
@@ -262,60 +277,61 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 3) seg_gated_kernel(const Ga
     for (int v = 0; v < VEC; ++v) { acc[v] = T(0); own.v[v] = T(0); }
     if (task.z > task.y) gather_load(a.S + (long long)task.x * a.dim + safe_col, own);
 
-    auto accumulate = [&](const Vec<T, VEC> &vg, const Vec<T, VEC> &vo, const Vec<T, VEC> &vp, T w) {
+    auto reduce_task = [&](auto unit_tag) {
+        constexpr bool UNIT = decltype(unit_tag)::value;
+        Ids ahead = Ids();
+        T ahead_w = T(1);
+        if (task.y + lane < task.z) {
+            ahead = load_ids(ids + task.y + lane);
+            if (!UNIT) ahead_w = __ldg(a.w + task.y + lane);
+        }
+        for (int base = task.y; base < task.z; base += 32) {
+            const int n = min(32, task.z - base);
+            __syncwarp();
+            s_edge[warp][lane] = ahead;
+            if (!UNIT) s_w[warp][lane] = ahead_w;
+            __syncwarp();
+            if (base + 32 + lane < task.z) {
+                ahead = load_ids(ids + base + 32 + lane);
+                if (!UNIT) ahead_w = __ldg(a.w + base + 32 + lane);
+            }
+            auto run_batch = [&](auto count_tag, int u) {
+                constexpr int COUNT = decltype(count_tag)::value;
+                Vec<T, VEC> vg[COUNT], vo[COUNT], vp[COUNT];
+                T w[COUNT];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const T y = UNIT ? message<T, MSG>(vp.v[v], own.v[v]) : message<T, MSG>(w, vp.v[v], own.v[v]);
-            const T up = UNIT ? vg.v[v] : vg.v[v] * w;
-            const T term = MSG == MSG_MUL ? up * vp.v[v] : up;
-            if (vo.v[v] == y) acc[v] += term;
+                for (int q = 0; q < COUNT; ++q) {
+                    const Ids e = s_edge[warp][u + q];
+                    w[q] = UNIT ? T(1) : s_w[warp][u + q];
+                    gather(row_ptr<T>(G, first_id(e), row_bytes), vg[q]);
+                    gather(row_ptr<T>(O, first_id(e), row_bytes), vo[q]);
+                    if (P_TABLE) table_load(row_ptr<T>(P, second_id(e), row_bytes), vp[q]);
+                    else gather(row_ptr<T>(P, second_id(e), row_bytes), vp[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < COUNT; ++q) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const T y = UNIT ? message<T, MSG>(vp[q].v[v], own.v[v]) : message<T, MSG>(w[q], vp[q].v[v], own.v[v]);
+                        const T up = UNIT ? vg[q].v[v] : vg[q].v[v] * w[q];
+                        const T term = MSG == MSG_MUL ? up * vp[q].v[v] : up;
+                        if (vo[q].v[v] == y) acc[v] += term;
+                    }
+                }
+            };
+            int u = 0;
+            for (; u + kUnroll <= n; u += kUnroll) run_batch(std::integral_constant<int, kUnroll>(), u);
+            switch (n - u) {
+                case 1: run_batch(std::integral_constant<int, 1>(), u); break;
+                case 2: run_batch(std::integral_constant<int, 2>(), u); break;
+                case 3: run_batch(std::integral_constant<int, 3>(), u); break;
+                default: break;
+            }
         }
     };
+    if (a.w == nullptr || !(task.w & kNonUnitTask)) reduce_task(std::true_type());
+    else reduce_task(std::false_type());
 
-    int2 ahead = make_int2(0, 0);
-    T ahead_w = T(1);
-    if (task.y + lane < task.z) {
-        ahead = __ldg(a.edge + task.y + lane);
-        if (!UNIT) ahead_w = __ldg(a.w + task.y + lane);
-    }
-    constexpr int kGatedUnroll = 2;
-    for (int base = task.y; base < task.z; base += 32) {
-        const int n = min(32, task.z - base);
-        __syncwarp();
-        s_edge[warp][lane] = ahead;
-        if (!UNIT) s_w[warp][lane] = ahead_w;
-        __syncwarp();
-        if (base + 32 + lane < task.z) {
-            ahead = __ldg(a.edge + base + 32 + lane);
-            if (!UNIT) ahead_w = __ldg(a.w + base + 32 + lane);
-        }
-        int u = 0;
-        for (; u + kGatedUnroll <= n; u += kGatedUnroll) {
-            Vec<T, VEC> vg[kGatedUnroll], vo[kGatedUnroll], vp[kGatedUnroll];
-            T w[kGatedUnroll];
-#pragma unroll
-            for (int q = 0; q < kGatedUnroll; ++q) {
-                const int2 e = s_edge[warp][u + q];
-                w[q] = UNIT ? T(1) : s_w[warp][u + q];
-                gather_load(row_ptr<T>(G, e.x, row_bytes), vg[q]);
-                gather_load(row_ptr<T>(O, e.x, row_bytes), vo[q]);
-                if (P_TABLE) table_load(row_ptr<T>(P, e.y, row_bytes), vp[q]);
-                else gather_load(row_ptr<T>(P, e.y, row_bytes), vp[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < kGatedUnroll; ++q) accumulate(vg[q], vo[q], vp[q], w[q]);
-        }
-        for (; u < n; ++u) {
-            Vec<T, VEC> vg, vo, vp;
-            const int2 e = s_edge[warp][u];
-            const T w = UNIT ? T(1) : s_w[warp][u];
-            gather_load(row_ptr<T>(G, e.x, row_bytes), vg);
-            gather_load(row_ptr<T>(O, e.x, row_bytes), vo);
-            if (P_TABLE) table_load(row_ptr<T>(P, e.y, row_bytes), vp);
-            else gather_load(row_ptr<T>(P, e.y, row_bytes), vp);
-            accumulate(vg, vo, vp, w);
-        }
-    }
     if (!active) return;
     T *p = slot < 0 ? a.out + (long long)task.x * a.dim + col : a.partial + (long long)slot * a.dim + col;
     Vec<T, VEC> r;
@@ -457,8 +473,13 @@ int launch_gated(const GatedArgs<T> &args, cudaStream_t stream) {
     if (warps == 0) return ULTRA_RSPMM_OK;
     const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > 0x7fffffffLL || args.dim * (long long)sizeof(T) > 0xffffffffLL) return ULTRA_RSPMM_ERR_RANGE;
-    if (args.w) seg_gated_kernel<T, VEC, MSG, P_TABLE, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
-    else seg_gated_kernel<T, VEC, MSG, P_TABLE, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    if (args.keep) {
+        if (args.packed) seg_gated_kernel<T, VEC, MSG, P_TABLE, true, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        else seg_gated_kernel<T, VEC, MSG, P_TABLE, false, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    } else {
+        if (args.packed) seg_gated_kernel<T, VEC, MSG, P_TABLE, true, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        else seg_gated_kernel<T, VEC, MSG, P_TABLE, false, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    }
     note_launch();
     return ULTRA_RSPMM_OK;
 }
@@ -469,6 +490,8 @@ int run_gated(const ultra_rspmm_order_t &order, bool unit_weight, const T *G, co
     GatedArgs<T> args;
     args.task = (const int4 *)order.task;
     args.edge = (const int2 *)order.edge;
+    args.packed = order.pack_shift > 0 ? (const unsigned *)order.packed : nullptr;
+    args.pack_shift = order.pack_shift;
     args.w = unit_weight ? nullptr : (const T *)order.w;
     args.G = G; args.O = O; args.P = P; args.S = S;
     args.out = out;
@@ -477,6 +500,7 @@ int run_gated(const ultra_rspmm_order_t &order, bool unit_weight, const T *G, co
     args.n_task = order.n_task;
     const int vec = pick_vec<T>(dim, 2 * rows_gathered, {G, O, P, S, out, workspace});   // two gathered operands share L2
     args.n_slab = (int)((dim + 32 * vec - 1) / (32 * vec));
+    args.keep = g_variant == 2 || (g_variant == 0 && 2 * rows_gathered * 32 * vec * (long long)sizeof(T) > (24ll << 20));
     int status;
     if (vec == 4) status = launch_gated<T, sizeof(T) == 4 ? 4 : 2, MSG, P_TABLE>(args, stream);
     else if (vec == 2) status = launch_gated<T, 2, MSG, P_TABLE>(args, stream);
