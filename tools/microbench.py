@@ -17,8 +17,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ultra_torchdrug_b200 import functional as F, synthetic  # noqa: E402
 
 
-def edge_model_bytes(n, r, e, d, passes="fwd", elem=4):
+def edge_model_bytes(n, r, e, d, passes="fwd", elem=4, gated=False):
     idx = 12 * e + 4 * (n + 1)
+    if gated and passes == "bwd":                     # min/max backward (all-ties rule): gathers out[i] and g[i]
+        return elem * d * (2 * e + 2 * n + 2 * r) + idx
+    if gated and passes in ("bwd_input", "bwd_relation"):
+        return elem * d * (2 * e + (n if passes == "bwd_input" else 0) + r + n) + idx
     if passes == "fwd":
         return elem * d * (e + r + n) + idx
     if passes == "bwd_input":
@@ -102,11 +106,11 @@ def main():
     results["bwd"] = timed(lambda i: index.backward(relation, inputs[i % copies], out, grads[i % copies], args.sum,
                                                     args.mul), args.iters)
     for name, ms in results.items():
-        gb = edge_model_bytes(n, r, e, d, name) / 1e9
+        gb = edge_model_bytes(n, r, e, d, name, gated=args.sum != "add") / 1e9
         print("%-13s %8.3f ms   %8.1f GB/s edge-model  (%.1f%% of measured HBM %.0f GB/s)   %.2f G edge-msg/s"
               % (name, ms, gb / ms * 1e3, 100 * gb / ms * 1e3 / peak, peak, e * d / ms / 1e6))
     total = results["fwd"] + results["bwd"]
-    gb = (edge_model_bytes(n, r, e, d, "fwd") + edge_model_bytes(n, r, e, d, "bwd")) / 1e9
+    gb = (edge_model_bytes(n, r, e, d, "fwd") + edge_model_bytes(n, r, e, d, "bwd", gated=args.sum != "add")) / 1e9
     print("fwd+bwd       %8.3f ms   %8.1f GB/s edge-model  (%.1f%% of measured HBM)" % (total, gb / total * 1e3, 100 * gb / total * 1e3 / peak))
 
 
