@@ -173,10 +173,20 @@ int ultra_rspmm_host_free(void *ptr);
 /* out = relu(layer_norm(x + linear_bias; eps) * gamma + beta) + residual over `rows` rows of `dim` fp32
  * features (dim in {4, 8, ..., 128}); linear_bias, gamma/beta (both or neither) and residual may be NULL;
  * relu = 0 skips the activation.  x is the output of the layer's Linear without its bias (a cuBLAS GEMM
- * that stays in PyTorch).  Inference only. */
+ * that stays in PyTorch). */
 int ultra_layer_norm_relu_residual(const float *dev_x, const float *dev_linear_bias, const float *dev_gamma, const float *dev_beta,
                                    const float *dev_residual, float *dev_out, int64_t rows, int32_t dim, float eps,
                                    int32_t relu, void *stream);
+
+/* Backward of the fused epilogue (fine-tuning): given d(out) it writes d(x) and the column sums d(linear_bias),
+ * d(gamma), d(beta) (any of the three may be NULL); d(residual) = d(out).  Row statistics are recomputed from x.
+ * workspace: ultra_layer_norm_relu_residual_backward_bytes(dim).  Deterministic (no atomics). */
+int ultra_layer_norm_relu_residual_backward_bytes(int32_t dim, size_t *workspace_bytes);
+int ultra_layer_norm_relu_residual_backward(const float *dev_x, const float *dev_linear_bias, const float *dev_gamma,
+                                            const float *dev_beta, const float *dev_grad_out, float *dev_grad_x,
+                                            float *dev_grad_linear_bias, float *dev_grad_gamma, float *dev_grad_beta,
+                                            int64_t rows, int32_t dim, float eps, int32_t relu, void *workspace,
+                                            size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -297,8 +297,18 @@ def test_layer_epilogue_matches_torch(cuda, dim):
     want = torch.nn.functional.layer_norm(x, (dim,), None, None, 1e-5)
     torch.testing.assert_close(F.layer_norm_relu_residual(x, None, None, None, 1e-5, relu=False), want, rtol=1e-5, atol=2e-6)
     assert not F.layer_epilogue_supported(x, 48) and not F.layer_epilogue_supported(x.cpu(), dim)
-    with pytest.raises(RuntimeError):
-        F.layer_norm_relu_residual(x.requires_grad_(), weight, bias)
+    # fused backward vs autograd through the separate PyTorch ops
+    leaves = [t.clone().requires_grad_() for t in (x, shift, weight, bias, residual)]
+    ours = [t.clone().requires_grad_() for t in (x, shift, weight, bias, residual)]
+    upstream = torch.randn_like(x)
+    (torch.relu(torch.nn.functional.layer_norm(leaves[0] + leaves[1], (dim,), leaves[2], leaves[3], 1e-5)) + leaves[4]).backward(upstream)
+    F.layer_norm_relu_residual(ours[0], ours[2], ours[3], ours[4], 1e-5, relu=True, linear_bias=ours[1]).backward(upstream)
+    for name, a, b in zip(("x", "linear_bias", "weight", "bias", "residual"), ours, leaves):
+        scale = float(b.grad.abs().max()) + 1e-6
+        torch.testing.assert_close(a.grad, b.grad, rtol=1e-4, atol=1e-5 * scale, msg=lambda m: "%s: %s" % (name, m))
+    again = [t.clone().requires_grad_() for t in (x, shift, weight, bias, residual)]
+    F.layer_norm_relu_residual(again[0], again[2], again[3], again[4], 1e-5, relu=True, linear_bias=again[1]).backward(upstream)
+    assert all(torch.equal(a.grad, b.grad) for a, b in zip(ours, again)), "fused backward is not deterministic"
 
 
 def test_forward_with_boundary_addend(cuda):

@@ -64,6 +64,10 @@ SYMBOLS = {
     "ultra_rspmm_host_free": (ctypes.c_int, [c_void_p]),
     "ultra_layer_norm_relu_residual": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                                       ctypes.c_float, c_int32, c_void_p]),
+    "ultra_layer_norm_relu_residual_backward_bytes": (ctypes.c_int, [c_int32, ctypes.POINTER(c_size_t)]),
+    "ultra_layer_norm_relu_residual_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                               c_void_p, c_void_p, c_void_p, c_int64, c_int32, ctypes.c_float,
+                                                               c_int32, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -19,7 +19,7 @@ import torch
 from . import _lib
 
 __all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
-           "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary"]
+           "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "LayerEpilogueFunction"]
 
 _SUM_OPS = ("add", "min", "max")
 _MUL_OPS = ("mul", "add")
@@ -138,30 +138,68 @@ def launch_count(reset=False):
 
 
 def layer_epilogue_supported(x, normalized_dim):
-    """The fused epilogue covers fp32 CUDA tensors with 4..128 (power of two) features per row, outside autograd."""
+    """The fused epilogue covers fp32 CUDA tensors with 4..128 (power of two) features per row."""
     return (x.is_cuda and x.dtype == torch.float32 and normalized_dim % 4 == 0 and normalized_dim <= 128
-            and normalized_dim & (normalized_dim - 1) == 0 and not (torch.is_grad_enabled() and x.requires_grad))
+            and normalized_dim & (normalized_dim - 1) == 0)
+
+
+def _epilogue_forward(x, linear_bias, weight, bias, residual, eps, relu):
+    dim = x.shape[-1]
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().ultra_layer_norm_relu_residual(
+            _ptr(x), _ptr(linear_bias), _ptr(weight), _ptr(bias), _ptr(residual), _ptr(out), x.numel() // max(dim, 1), dim,
+            float(eps), int(bool(relu)), _stream_handle()), "ultra_layer_norm_relu_residual")
+    return out
+
+
+class LayerEpilogueFunction(torch.autograd.Function):
+    """relu(layer_norm(x + linear_bias) * weight + bias) + residual with a fused, deterministic backward."""
+
+    @staticmethod
+    def forward(ctx, x, linear_bias, weight, bias, residual, eps, relu):
+        x = x.contiguous()
+        tensors = [None if t is None else t.detach().contiguous() for t in (linear_bias, weight, bias, residual)]
+        out = _epilogue_forward(x.detach(), tensors[0], tensors[1], tensors[2], tensors[3], eps, relu)
+        ctx.save_for_backward(x.detach(), *[t if t is not None else x.new_empty(0) for t in tensors[:3]])
+        ctx.present = [t is not None for t in tensors[:3]]
+        ctx.has_residual = residual is not None
+        ctx.eps, ctx.relu = eps, relu
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, linear_bias, weight, bias = ctx.saved_tensors
+        linear_bias, weight, bias = (t if present else None for t, present in zip((linear_bias, weight, bias), ctx.present))
+        grad_out = grad_out.contiguous()
+        dim = x.shape[-1]
+        lib = _lib.lib()
+        need = ctypes.c_size_t()
+        _lib.check(lib.ultra_layer_norm_relu_residual_backward_bytes(dim, ctypes.byref(need)), "backward_bytes")
+        grad_x = torch.empty_like(x)
+        sums = torch.empty(3, dim, dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            workspace = torch.empty(need.value, dtype=torch.uint8, device=x.device)
+            _lib.check(lib.ultra_layer_norm_relu_residual_backward(
+                _ptr(x), _ptr(linear_bias), _ptr(weight), _ptr(bias), _ptr(grad_out), _ptr(grad_x), _ptr(sums[0]),
+                _ptr(sums[1]), _ptr(sums[2]), x.numel() // max(dim, 1), dim, float(ctx.eps), int(bool(ctx.relu)),
+                _ptr(workspace), need.value, _stream_handle()), "ultra_layer_norm_relu_residual_backward")
+        return (grad_x, sums[0] if linear_bias is not None else None, sums[1] if weight is not None else None,
+                sums[2] if bias is not None else None, grad_out if ctx.has_residual else None, None, None)
 
 
 def layer_norm_relu_residual(x, weight=None, bias=None, residual=None, eps=1e-5, relu=True, linear_bias=None):
     """relu(layer_norm(x + linear_bias) * weight + bias) + residual in one pass (reference layer.py:386-392 +
-    model.py:126-127).  Inference only: raises if `x` requires grad."""
-    if torch.is_grad_enabled() and x.requires_grad:
-        raise RuntimeError("layer_norm_relu_residual is an inference-only kernel (no backward)")
-    dim = x.shape[-1]
-    x = x.contiguous()
-    if residual is not None:
-        if residual.shape != x.shape:
-            raise RuntimeError("residual shape %s != input shape %s" % (tuple(residual.shape), tuple(x.shape)))
-        residual = residual.contiguous()
-    out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().ultra_layer_norm_relu_residual(
-            _ptr(x), _ptr(linear_bias.contiguous() if linear_bias is not None else None),
-            _ptr(weight.contiguous() if weight is not None else None),
-            _ptr(bias.contiguous() if bias is not None else None), _ptr(residual), _ptr(out), x.numel() // max(dim, 1), dim,
-            float(eps), int(bool(relu)), _stream_handle()), "ultra_layer_norm_relu_residual")
-    return out
+    model.py:126-127), differentiable (fused backward) when any operand requires grad."""
+    if not layer_epilogue_supported(x, x.shape[-1]):
+        raise RuntimeError("layer_norm_relu_residual needs a float32 CUDA tensor with 4..128 (power of two) features per row")
+    if residual is not None and residual.shape != x.shape:
+        raise RuntimeError("residual shape %s != input shape %s" % (tuple(residual.shape), tuple(x.shape)))
+    operands = [t for t in (x, linear_bias, weight, bias, residual) if t is not None]
+    if torch.is_grad_enabled() and any(t.requires_grad for t in operands):
+        return LayerEpilogueFunction.apply(x, linear_bias, weight, bias, residual, eps, relu)
+    contiguous = [None if t is None else t.contiguous() for t in (linear_bias, weight, bias, residual)]
+    return _epilogue_forward(x.contiguous(), contiguous[0], contiguous[1], contiguous[2], contiguous[3], eps, relu)
 
 
 def _fingerprint(indices, values):

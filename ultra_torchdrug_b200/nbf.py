@@ -99,13 +99,11 @@ class _RelationalConvBase(nn.Module):
 
     def combine(self, input, update, residual=None):
         """relu(layer_norm(linear(cat[input, update]))) (+ residual: the caller's short-cut, model.py:126-127).
-        Outside autograd the normalisation, activation and short-cut run as one fused pass (SURVEY 8 row f1);
-        under autograd they are the reference's separate PyTorch ops."""
+        On CUDA the Linear's bias, the normalisation, the activation and the short-cut run as one fused pass with a
+        fused backward; elsewhere they are the reference's separate PyTorch ops."""
         joined = torch.cat([input, update], dim=-1)
         fusable = self.layer_norm is not None and self.activation in (F.relu, None)
-        needs_grad = torch.is_grad_enabled() and (joined.requires_grad or self.linear.weight.requires_grad or
-                                                  self.layer_norm is not None and self.layer_norm.weight.requires_grad)
-        if fusable and not needs_grad and rspmm.layer_epilogue_supported(joined, self.output_dim):
+        if fusable and rspmm.layer_epilogue_supported(joined, self.output_dim):
             output = F.linear(joined, self.linear.weight)      # bias, normalisation, activation, short-cut: one pass
             return rspmm.layer_norm_relu_residual(output, self.layer_norm.weight, self.layer_norm.bias, residual,
                                                   self.layer_norm.eps, relu=self.activation is not None,
