@@ -54,6 +54,7 @@ def main():
     parser.add_argument("--sum", default="add")
     parser.add_argument("--mul", default="mul")
     parser.add_argument("--skew", type=float, default=None)
+    parser.add_argument("--relskew", type=float, default=None)
     parser.add_argument("--iters", type=int, default=10)
     parser.add_argument("--chunk", type=int, default=0)
     parser.add_argument("--l2mb", type=int, default=0, help="L2 budget (MiB) used to pick the slab width")
@@ -69,7 +70,7 @@ def main():
     if args.chunk or args.l2mb or args.variant:
         from ultra_torchdrug_b200 import _lib
         _lib.lib().ultra_rspmm_set_tuning(args.chunk, args.variant, args.l2mb << 20)
-    edge_list, n, r = synthetic.named_graph(args.graph, skew=args.skew)
+    edge_list, n, r = synthetic.named_graph(args.graph, skew=args.skew, relation_skew=args.relskew)
     if args.relgraph:
         nodes = r
         grid = torch.cartesian_prod(torch.arange(nodes), torch.arange(nodes), torch.arange(4))

@@ -16,8 +16,9 @@ SHAPES = {
 }
 
 
-def triples(num_node, num_relation, num_triple, seed=1024, skew=None):
-    """(num_triple, 3) int64 [h, t, r].  `skew`: Zipf exponent for the tail distribution (hub nodes)."""
+def triples(num_node, num_relation, num_triple, seed=1024, skew=None, relation_skew=None):
+    """(num_triple, 3) int64 [h, t, r].  `skew`: Zipf exponent for the tail distribution (hub nodes);
+    `relation_skew`: Zipf exponent for the relation distribution (a few frequent relation types, as in real KGs)."""
     generator = torch.Generator().manual_seed(seed)
     h = torch.randint(num_node, (num_triple,), generator=generator)
     if skew:
@@ -25,7 +26,11 @@ def triples(num_node, num_relation, num_triple, seed=1024, skew=None):
         t = torch.multinomial(rank.pow(-float(skew)), num_triple, replacement=True, generator=generator)
     else:
         t = torch.randint(num_node, (num_triple,), generator=generator)
-    r = torch.randint(num_relation, (num_triple,), generator=generator)
+    if relation_skew:
+        rank = torch.arange(1, num_relation + 1, dtype=torch.float64)
+        r = torch.multinomial(rank.pow(-float(relation_skew)), num_triple, replacement=True, generator=generator)
+    else:
+        r = torch.randint(num_relation, (num_triple,), generator=generator)
     return torch.stack([h, t, r], dim=-1)
 
 
@@ -47,8 +52,8 @@ def operator_operand(edge_list, num_node, num_relation, device=None, dtype=torch
     return torch.sparse_coo_tensor(indices, values, (num_node, num_node, num_relation), check_invariants=False)
 
 
-def named_graph(name, seed=1024, skew=None):
+def named_graph(name, seed=1024, skew=None, relation_skew=None):
     """(edge_list (E, 3), num_node, num_relation incl. inverses) of a BASELINE.json shape."""
     num_node, num_relation, num_triple = SHAPES[name]
-    edge_list = undirected_edge_list(triples(num_node, num_relation, num_triple, seed, skew), num_relation)
+    edge_list = undirected_edge_list(triples(num_node, num_relation, num_triple, seed, skew, relation_skew), num_relation)
     return edge_list, num_node, 2 * num_relation
