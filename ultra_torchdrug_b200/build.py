@@ -61,7 +61,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or jobs or _stale(LIB_PATH, objects):
-        subprocess.check_call([nvcc, "-shared", "-o", LIB_PATH] + objects + ["-lcudart"])
+        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objects + ["-lcudart"])
     return LIB_PATH
 
 

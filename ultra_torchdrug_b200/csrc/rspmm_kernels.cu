@@ -374,8 +374,6 @@ __global__ void combine_kernel(const int4 *__restrict__ split, int n_split, cons
 // ------------------------------------------------------------------------------------------------
 template <typename T> constexpr int wide_vec() { return 16 / sizeof(T); }
 
-inline bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
-
 template <typename T, int VEC, int SUM, int MSG, bool B_TABLE, bool ARG>
 int launch_seg(const SegArgs<T> &args, cudaStream_t stream) {
     const long long warps = (long long)args.n_task * args.n_slab;
