@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("filterwarnings", "ignore:Sparse invariant checks are implicitly disabled:UserWarning")
+    config.addinivalue_line("filterwarnings", "ignore:Sparse CSR tensor support is in beta state:UserWarning")
 
 
 @pytest.fixture(scope="session")
