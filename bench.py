@@ -290,6 +290,8 @@ def run_gpu_arm(args):
             "ultra_queries": {"value": world * queries["queries_per_batch"] / (queries["ms_per_batch"] * 1e-3),
                               "unit": "queries/s", "ms_per_batch": queries["ms_per_batch"],
                               "batch_per_gpu": BATCH, "relation_graph_edges": queries["relation_graph_edges"],
+                              "rspmm_edge_model_GBps": world * queries["rspmm_edge_model_bytes_per_batch"] / (queries["ms_per_batch"] * 1e-3) / 1e9,
+                              "pct_of_hbm_peak": 100.0 * queries["rspmm_edge_model_bytes_per_batch"] / (queries["ms_per_batch"] * 1e-3) / 1e9 / peak,
                               "what": "ULTRA zero-shot tail+head ranking, 6+6 layers x 64-d, all entities as candidates, "
                                       "fresh batch per step, random-init weights, fp32 (TF32 off)"},
             "roofline": {"bound": "hbm", "kernel": "seg_reduce_kernel<float,4,add,mul> (forward)",
@@ -345,8 +347,15 @@ def ultra_queries(device, rank, steps, warmup=2):
         stop.record()
         torch.cuda.synchronize()
     ms = start.elapsed_time(stop) / steps
+    # edge-model bytes of the 18 operator calls of one batch: 6 relation-graph layers + 2 x 6 entity-graph layers
+    from ultra_torchdrug_b200 import functional as F
+    d = BATCH * HIDDEN
+    entity_index = F.graph_index(graph.undirected(add_inverse=True).adjacency.transpose(0, 1))
+    relation_index = F.graph_index(ranker.rel_graph.adjacency.transpose(0, 1))
+    model_bytes = 12 * edge_model_bytes(num_node, 2 * num_relation, entity_index.nnz, d, "fwd") + \
+        6 * edge_model_bytes(2 * num_relation, 4, relation_index.nnz, d, "fwd")
     return {"ms_per_batch": ms, "queries_per_batch": 2 * BATCH, "relation_graph_edges": int(ranker.rel_graph.num_edge),
-            "score_checksum": float(pred.float().mean())}
+            "rspmm_edge_model_bytes_per_batch": model_bytes, "score_checksum": float(pred.float().mean())}
 
 
 def e2e_host_buffers(lib, edge_list, n, r, d, device_index, steps, rank):

@@ -94,9 +94,11 @@ def lib():
         path = _build.LIB_PATH
         try:
             path = _build.build()
-        except Exception:
+        except Exception as error:
             if not os.path.exists(path):
                 raise
+            import warnings
+            warnings.warn("could not (re)build libultra_rspmm.so (%s); loading the existing %s" % (error, path))
     handle = ctypes.CDLL(path)
     for name, (restype, argtypes) in SYMBOLS.items():
         function = getattr(handle, name)  # AttributeError when the library does not export a declared symbol
