@@ -136,6 +136,13 @@ int ultra_rspmm_forward(const ultra_rspmm_index_t *index, const void *dev_relati
                         const void *dev_addend, void *dev_output, int32_t *dev_argidx, int64_t dim, int32_t dtype,
                         int32_t sum_op, int32_t mul_op, void *workspace, size_t workspace_bytes, void *stream);
 
+/* PNA aggregation in one pass: the four operator calls of reference layer.py:141-144 / 164-167 / 343-346 / 366-369
+ * (add, add of the squared operands, max, min) over one gather per edge.  Outputs (n_out, dim) each.
+ * workspace: 4 x the forward partial-row bytes (4 * csr.n_slot * dim * sizeof(element)); forward only. */
+int ultra_rspmm_forward_pna(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
+                            void *dev_sum, void *dev_square_sum, void *dev_max, void *dev_min, int64_t dim,
+                            int32_t dtype, int32_t mul_op, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- backward: rspmm_{sum}_{mul}_backward_cuda (overload without value_grad) ------------------- */
 /* dev_output is read only for min/max (may be NULL for add).  Either gradient pointer may be NULL to
  * skip that pass.  Results are written (not accumulated). */

@@ -357,3 +357,35 @@ def test_parity_randomized(cuda, seed):
                   weights="random" if seed % 3 == 0 else "unit", skew=bool(seed % 2), ties=bool(seed % 4 == 1), dtype=dtype)
     finally:
         lib.ultra_rspmm_set_tuning(256, 0, 0)
+
+
+@pytest.mark.parametrize("mul", ["mul", "add"])
+@pytest.mark.parametrize("weights", ["unit", "random"])
+def test_fused_pna_equals_four_calls(cuda, mul, weights):
+    """One-pass PNA aggregates == the reference's four operator calls: max / min bit for bit, the two sums to fp32
+    rounding (the one-pass kernel rounds each message before adding it, the add kernel fuses multiply and add)."""
+    from ultra_torchdrug_b200 import _lib, functional as F
+    lib = _lib.lib()
+    lib.ultra_rspmm_set_tuning(32, 0, 0)      # some split rows
+    try:
+        indices, values = util.random_coo(70, 60, 5, 2500, seed=31, duplicates=40, weights=weights, skew=True)
+        sparse = util.to_sparse(indices, values, (70, 60, 5), cuda)
+        relation = torch.from_numpy(util.random_dense(5, 264, 1)).to(cuda)
+        input = torch.from_numpy(util.random_dense(60, 264, 2)).to(cuda)
+        F.clear_index_cache()
+        with torch.no_grad():
+            got = F.rspmm_pna(sparse, relation, input, mul)
+            want = (F.generalized_rspmm(sparse, relation, input, sum="add", mul=mul),
+                    F.generalized_rspmm(sparse, relation ** 2, input ** 2, sum="add", mul=mul),
+                    F.generalized_rspmm(sparse, relation, input, sum="max", mul=mul),
+                    F.generalized_rspmm(sparse, relation, input, sum="min", mul=mul))
+        for name, a, b in zip(("sum", "square sum", "max", "min"), got, want):
+            if name in ("max", "min"):
+                assert torch.equal(a, b), name
+            else:
+                torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-4, msg=lambda m: "%s: %s" % (name, m))
+        with pytest.raises(RuntimeError):
+            F.rspmm_pna(sparse, relation.requires_grad_(), input, mul)
+    finally:
+        lib.ultra_rspmm_set_tuning(256, 0, 0)
+        F.clear_index_cache()

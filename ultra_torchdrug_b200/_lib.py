@@ -50,6 +50,8 @@ SYMBOLS = {
                                                    ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),
     "ultra_rspmm_forward": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                            c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
+    "ultra_rspmm_forward_pna": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p, c_int64, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "ultra_rspmm_backward": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "ultra_rspmm_ctx_create": (ctypes.c_int, [ctypes.POINTER(c_void_p), c_int32]),

@@ -344,6 +344,146 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 3) seg_gated_kernel(const Ga
     }
 }
 
+// PNA aggregation in one pass (reference layer.py:141-144, 164-167, 343-346, 366-369 issue four operator calls over the
+// same edges: add, add of squared operands, max, min).  One gather per edge feeds four accumulators:
+//     sum += w (r (x) x)    sq += w (r^2 (x) x^2)    max / min of w (r (x) x)
+// with the reference's rounding (the squares are formed first, as `relation ** 2` / `input ** 2` are in the reference).
+// Outputs and partial rows are stacked [4][rows][dim] in the order sum, squares, max, min.
+template <typename T> struct PnaArgs {
+    const int4 *task;
+    const int2 *edge;
+    const unsigned *packed;
+    int pack_shift;
+    int keep;
+    const T *w;
+    const T *A;
+    const T *B;
+    T *out[4];
+    T *partial;          // [4][n_slot][dim]
+    long long dim;
+    long long slot_stride;   // n_slot * dim
+    int n_task;
+    int n_slab;
+};
+
+template <typename T, int VEC, int MSG, bool PACKED, bool KEEP>
+__global__ void __launch_bounds__(kThreadsPerBlock, 2) seg_pna_kernel(const PnaArgs<T> a) {
+    using Ids = typename std::conditional<PACKED, unsigned, int2>::type;
+    __shared__ __align__(16) Ids s_edge[kWarpsPerBlock][32];
+    __shared__ __align__(16) T s_w[kWarpsPerBlock][32];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    if (gw >= (long long)a.n_task * a.n_slab) return;
+    const int slab = (int)(gw / a.n_task);
+    const int4 task = __ldg(a.task + (gw - (long long)slab * a.n_task));
+    const int slot = task_slot(task.w);
+    const long long col = (long long)slab * (32 * VEC) + lane * VEC;
+    const bool active = col < a.dim;
+    const long long safe_col = active ? col : 0;
+    const unsigned row_bytes = (unsigned)(a.dim * sizeof(T));
+    const char *A = reinterpret_cast<const char *>(a.A + safe_col);
+    const char *B = reinterpret_cast<const char *>(a.B + safe_col);
+    const Ids *ids = reinterpret_cast<const Ids *>(PACKED ? (const void *)a.packed : (const void *)a.edge);
+    const int shift = a.pack_shift;
+    const unsigned low = PACKED ? (shift >= 32 ? 0xffffffffu : ((1u << shift) - 1u)) : 0u;
+    const unsigned long long keep_policy = KEEP ? policy_evict_last() : 0, once_policy = KEEP ? policy_evict_first() : 0;
+    auto gather = [&](const T *p, Vec<T, VEC> &v) {
+        if (KEEP) gather_load_keep(p, v, keep_policy);
+        else gather_load(p, v);
+    };
+    auto load_ids = [&](const Ids *p) { return KEEP ? edge_load_once(p, once_policy) : __ldg(p); };
+    auto first_id = [&](const Ids &e) { return PACKED ? (int)(id_bits(e) & low) : id_x(e); };
+    auto second_id = [&](const Ids &e) { return PACKED ? (int)(id_bits(e) >> shift) : id_y(e); };
+
+    T acc_sum[VEC], acc_sq[VEC], acc_max[VEC], acc_min[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        acc_sum[v] = acc_sq[v] = T(0);
+        acc_max[v] = Limits<T>::lowest();
+        acc_min[v] = Limits<T>::highest();
+    }
+    const bool weighted = a.w != nullptr && (task.w & kNonUnitTask);
+    Vec<T, VEC> cached;
+    int cached_row = -1;
+    Ids ahead = Ids();
+    T ahead_w = T(1);
+    if (task.y + lane < task.z) {
+        ahead = load_ids(ids + task.y + lane);
+        if (weighted) ahead_w = __ldg(a.w + task.y + lane);
+    }
+    for (int base = task.y; base < task.z; base += 32) {
+        const int n = min(32, task.z - base);
+        __syncwarp();
+        s_edge[warp][lane] = ahead;
+        s_w[warp][lane] = ahead_w;
+        __syncwarp();
+        if (base + 32 + lane < task.z) {
+            ahead = load_ids(ids + base + 32 + lane);
+            if (weighted) ahead_w = __ldg(a.w + base + 32 + lane);
+        }
+        auto run_batch = [&](auto count_tag, int u) {
+            constexpr int COUNT = decltype(count_tag)::value;
+            Vec<T, VEC> va[COUNT], vb[COUNT];
+            T w[COUNT];
+            Ids e[COUNT];
+            bool same = true;
+#pragma unroll
+            for (int q = 0; q < COUNT; ++q) {
+                e[q] = s_edge[warp][u + q];
+                w[q] = s_w[warp][u + q];
+                same = same && second_id(e[q]) == cached_row;
+                gather(row_ptr<T>(A, first_id(e[q]), row_bytes), va[q]);
+            }
+            if (!same) {
+#pragma unroll
+                for (int q = 0; q < COUNT; ++q) table_load(row_ptr<T>(B, second_id(e[q]), row_bytes), vb[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < COUNT; ++q) {
+                const Vec<T, VEC> &rel = same ? cached : vb[q];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const T r = rel.v[v], x = va[q].v[v];
+                    const T m = message<T, MSG>(w[q], r, x);                 // weight 1 multiplies exactly
+                    const T msq = message<T, MSG>(w[q], r * r, x * x);
+                    acc_sum[v] += m;
+                    acc_sq[v] += msq;
+                    acc_max[v] = acc_max[v] > m ? acc_max[v] : m;
+                    acc_min[v] = acc_min[v] < m ? acc_min[v] : m;
+                }
+            }
+            if (!same) {
+                cached = vb[COUNT - 1];
+                cached_row = second_id(e[COUNT - 1]);
+            }
+        };
+        int u = 0;
+        for (; u + kUnroll <= n; u += kUnroll) run_batch(std::integral_constant<int, kUnroll>(), u);
+        switch (n - u) {
+            case 1: run_batch(std::integral_constant<int, 1>(), u); break;
+            case 2: run_batch(std::integral_constant<int, 2>(), u); break;
+            case 3: run_batch(std::integral_constant<int, 3>(), u); break;
+            default: break;
+        }
+    }
+    if (!active) return;
+    const T *results[4] = {acc_sum, acc_sq, acc_max, acc_min};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        Vec<T, VEC> r;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r.v[v] = results[k][v];
+        if (slot < 0) {
+            stream_store(a.out[k] + (long long)task.x * a.dim + col, r);
+        } else {
+            T *p = a.partial + k * a.slot_stride + (long long)slot * a.dim + col;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) p[v] = r.v[v];
+        }
+    }
+}
+
 // Fixed-order fold of the partial rows of split segments (deterministic second stage).
 template <typename T, int SUM, bool ARG>
 __global__ void combine_kernel(const int4 *__restrict__ split, int n_split, const T *__restrict__ partial,
@@ -569,6 +709,57 @@ int backward_typed(const ultra_rspmm_index_t &ix, const void *relation, const vo
     return status;
 }
 
+
+template <typename T, int VEC, int MSG>
+int launch_pna(const PnaArgs<T> &args, cudaStream_t stream) {
+    const long long warps = (long long)args.n_task * args.n_slab;
+    if (warps == 0) return ULTRA_RSPMM_OK;
+    const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks > 0x7fffffffLL || args.dim * (long long)sizeof(T) > 0xffffffffLL) return ULTRA_RSPMM_ERR_RANGE;
+    if (args.keep) {
+        if (args.packed) seg_pna_kernel<T, VEC, MSG, true, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        else seg_pna_kernel<T, VEC, MSG, false, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    } else {
+        if (args.packed) seg_pna_kernel<T, VEC, MSG, true, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        else seg_pna_kernel<T, VEC, MSG, false, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    }
+    note_launch();
+    return ULTRA_RSPMM_OK;
+}
+
+template <typename T, int MSG>
+int forward_pna_typed(const ultra_rspmm_index_t &ix, const T *relation, const T *input, T *const out[4], long long dim,
+                      void *workspace, cudaStream_t stream) {
+    const ultra_rspmm_order_t &order = ix.csr;
+    PnaArgs<T> args;
+    args.task = (const int4 *)order.task;
+    args.edge = (const int2 *)order.edge;
+    args.packed = order.pack_shift > 0 ? (const unsigned *)order.packed : nullptr;
+    args.pack_shift = order.pack_shift;
+    args.w = ix.unit_weight ? nullptr : (const T *)order.w;
+    args.A = input;
+    args.B = relation;
+    for (int k = 0; k < 4; ++k) args.out[k] = out[k];
+    args.partial = (T *)workspace;
+    args.dim = dim;
+    args.slot_stride = (long long)order.n_slot * dim;
+    args.n_task = order.n_task;
+    const int vec = pick_vec<T>(dim, ix.n_in, {input, relation, out[0], out[1], out[2], out[3], workspace});
+    args.n_slab = (int)((dim + 32 * vec - 1) / (32 * vec));
+    args.keep = g_variant == 2 || (g_variant == 0 && (long long)ix.n_in * 32 * vec * (long long)sizeof(T) > (24ll << 20));
+    int status;
+    if (vec == 4) status = launch_pna<T, sizeof(T) == 4 ? 4 : 2, MSG>(args, stream);
+    else if (vec == 2) status = launch_pna<T, 2, MSG>(args, stream);
+    else status = launch_pna<T, 1, MSG>(args, stream);
+    if (status) return status;
+    const T *partial = (const T *)workspace;
+    const long long stride = args.slot_stride;
+    if ((status = launch_combine<T, ULTRA_RSPMM_SUM_ADD, false>(order, partial, nullptr, out[0], nullptr, dim, stream))) return status;
+    if ((status = launch_combine<T, ULTRA_RSPMM_SUM_ADD, false>(order, partial + stride, nullptr, out[1], nullptr, dim, stream))) return status;
+    if ((status = launch_combine<T, ULTRA_RSPMM_SUM_MAX, false>(order, partial + 2 * stride, nullptr, out[2], nullptr, dim, stream))) return status;
+    return launch_combine<T, ULTRA_RSPMM_SUM_MIN, false>(order, partial + 3 * stride, nullptr, out[3], nullptr, dim, stream);
+}
+
 int check_call(const ultra_rspmm_index_t *index, int64_t dim, int32_t dtype, int32_t sum_op, int32_t mul_op) {
     if (!index || dim < 0) return ULTRA_RSPMM_ERR_ARG;
     if (dtype != ULTRA_RSPMM_F32 && dtype != ULTRA_RSPMM_F64) return ULTRA_RSPMM_ERR_ARG;
@@ -648,6 +839,34 @@ extern "C" int ultra_rspmm_backward(const ultra_rspmm_index_t *index, const void
                                          dev_grad_input, dim, sum_op, mul_op, workspace, s)
                  : backward_typed<double>(*index, dev_relation, dev_input, dev_output, dev_grad_output, dev_grad_relation,
                                           dev_grad_input, dim, sum_op, mul_op, workspace, s);
+    if (status) return status;
+    ULTRA_CUDA_OK(cudaGetLastError());
+    return ULTRA_RSPMM_OK;
+}
+
+extern "C" int ultra_rspmm_forward_pna(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
+                                       void *dev_sum, void *dev_square_sum, void *dev_max, void *dev_min, int64_t dim,
+                                       int32_t dtype, int32_t mul_op, void *workspace, size_t workspace_bytes, void *stream) {
+    int status = check_call(index, dim, dtype, ULTRA_RSPMM_SUM_ADD, mul_op);
+    if (status) return status;
+    if (index->n_out == 0 || dim == 0) return ULTRA_RSPMM_OK;
+    if (!dev_sum || !dev_square_sum || !dev_max || !dev_min) return ULTRA_RSPMM_ERR_ARG;
+    if ((index->n_rel > 0 && !dev_relation) || (index->n_in > 0 && !dev_input)) return ULTRA_RSPMM_ERR_ARG;
+    const size_t elem = dtype == ULTRA_RSPMM_F32 ? 4 : 8;
+    const size_t need = 4 * (size_t)index->csr.n_slot * dim * elem;
+    if (index->csr.n_slot > 0 && (!workspace || workspace_bytes < need)) return ULTRA_RSPMM_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == ULTRA_RSPMM_F32) {
+        float *const out[4] = {(float *)dev_sum, (float *)dev_square_sum, (float *)dev_max, (float *)dev_min};
+        status = mul_op == ULTRA_RSPMM_MUL_MUL
+                     ? forward_pna_typed<float, MSG_MUL>(*index, (const float *)dev_relation, (const float *)dev_input, out, dim, workspace, s)
+                     : forward_pna_typed<float, MSG_ADD>(*index, (const float *)dev_relation, (const float *)dev_input, out, dim, workspace, s);
+    } else {
+        double *const out[4] = {(double *)dev_sum, (double *)dev_square_sum, (double *)dev_max, (double *)dev_min};
+        status = mul_op == ULTRA_RSPMM_MUL_MUL
+                     ? forward_pna_typed<double, MSG_MUL>(*index, (const double *)dev_relation, (const double *)dev_input, out, dim, workspace, s)
+                     : forward_pna_typed<double, MSG_ADD>(*index, (const double *)dev_relation, (const double *)dev_input, out, dim, workspace, s);
+    }
     if (status) return status;
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;

@@ -19,7 +19,7 @@ import torch
 from . import _lib
 
 __all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
-           "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "LayerEpilogueFunction"]
+           "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "rspmm_pna", "LayerEpilogueFunction"]
 
 _SUM_OPS = ("add", "min", "max")
 _MUL_OPS = ("mul", "add")
@@ -108,6 +108,20 @@ class GraphIndex(object):
                 _DTYPE_CODE[self.dtype], _lib.SUM_CODE[sum], _lib.MUL_CODE[mul], _ptr(workspace), need,
                 _stream_handle()), "ultra_rspmm_forward")
         return (output, argidx) if return_argidx else output
+
+    def forward_pna(self, relation, input, mul="mul"):
+        """(sum, sum of squared operands, max, min) of the messages in one pass - the four operator calls of the
+        reference's `pna` aggregation (layer.py:141-144, 343-346) over a single gather per edge.  Forward only."""
+        dim = input.shape[1]
+        outputs = [torch.empty((self.shape[0], dim), dtype=input.dtype, device=input.device) for _ in range(4)]
+        need = 4 * self.workspace_bytes(dim)[0]
+        with torch.cuda.device(input.device):
+            workspace = torch.empty(need, dtype=torch.uint8, device=input.device) if need else None
+            _lib.check(_lib.lib().ultra_rspmm_forward_pna(
+                ctypes.byref(self.c), _ptr(relation), _ptr(input), _ptr(outputs[0]), _ptr(outputs[1]), _ptr(outputs[2]),
+                _ptr(outputs[3]), dim, _DTYPE_CODE[self.dtype], _lib.MUL_CODE[mul], _ptr(workspace), need,
+                _stream_handle()), "ultra_rspmm_forward_pna")
+        return tuple(outputs)
 
     def backward(self, relation, input, output, grad_output, sum="add", mul="mul", need_relation=True,
                  need_input=True):
@@ -260,6 +274,18 @@ def rspmm_add_boundary(sparse, relation, input, boundary, mul="mul"):
         raise RuntimeError("rspmm_add_boundary is an inference-only entry point")
     index = graph_index(sparse)
     return index.forward(relation.contiguous(), input.contiguous(), "add", mul, addend=boundary.contiguous())
+
+
+def rspmm_pna(sparse, relation, input, mul="mul"):
+    """The four aggregates of the `pna` layer - generalized_rspmm(sum="add"), generalized_rspmm(relation ** 2,
+    input ** 2, sum="add"), sum="max", sum="min" (reference layer.py:141-144, 343-346) - in one kernel pass.
+    Inference only; under autograd call generalized_rspmm four times."""
+    _check_operands(sparse, relation, input)
+    if mul not in _MUL_OPS:
+        raise ValueError("Unknown multiplication `%s`" % mul)
+    if torch.is_grad_enabled() and (relation.requires_grad or input.requires_grad):
+        raise RuntimeError("rspmm_pna is an inference-only entry point")
+    return graph_index(sparse).forward_pna(relation.contiguous(), input.contiguous(), mul)
 
 
 def _check_operands(sparse, relation, input):

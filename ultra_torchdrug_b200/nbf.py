@@ -50,8 +50,11 @@ def _aggregate(adjacency, relation_input, input, boundary, degree_out, aggregate
         update = op("max")
         return torch.max(update, boundary) if bounded else update
     if name == "pna":
-        total, sq_total = op("add"), op("add", relation_input ** 2, input ** 2)
-        maximum, minimum = op("max"), op("min")
+        if input.is_cuda and not (torch.is_grad_enabled() and (relation_input.requires_grad or input.requires_grad)):
+            total, sq_total, maximum, minimum = rspmm.rspmm_pna(adjacency, relation_input, input, mul)   # one pass
+        else:
+            total, sq_total = op("add"), op("add", relation_input ** 2, input ** 2)
+            maximum, minimum = op("max"), op("min")
         if bounded:
             total, sq_total = total + boundary, sq_total + boundary ** 2
             maximum, minimum = torch.max(maximum, boundary), torch.min(minimum, boundary)
