@@ -13,6 +13,7 @@ SHAPES = {
     "fb15k237": (14541, 237, 272115),          # configs[1]                 (C2)
     "codex_l": (77951, 69, 551193),            # configs[2]                 (C3)
     "yago310": (123182, 37, 1079040),          # configs[3]                 (C4)
+    "wn18rr": (40943, 11, 86835),              # low-degree shape (average in-degree 4.2), not a BASELINE config
 }
 
 
