@@ -65,6 +65,8 @@ typedef struct ultra_rspmm_order {
     int32_t n_split;      /* number of split segments                                                   */
     int32_t max_seg_nnz;  /* longest segment                                                            */
     int32_t pack_shift;   /* > 0: `packed` holds edge.x | edge.y << pack_shift; 0: ids do not fit 32 bits      */
+    int32_t n_gtask;      /* tasks of the grouped list (0: no grouped list was built for this order)            */
+    int32_t group_edges;  /* rows of at most this many edges are grouped (0: grouping off)                      */
     const int32_t *ptr;   /* n_seg + 1: edges of segment s are [ptr[s], ptr[s+1])                        */
     const int32_t *edge;  /* M x int2: the two row ids each edge gathers from (see ultra_rspmm_index_t)  */
     const void *w;        /* M merged values, element type = index dtype                                */
@@ -74,6 +76,10 @@ typedef struct ultra_rspmm_order {
                              slot = -1: the task writes the result row itself.  Sorted by descending edge
                              count (longest first).                                                     */
     const int32_t *split; /* n_split x int4 {seg, first_slot, n_slots, 0}                                */
+    const int32_t *gtask; /* n_gtask x int4: the same work with short rows grouped - a group task
+                             {first seg, begin, end, 0x20000000 | (rows - 1) << 24 | non-unit flag} covers up to 16
+                             consecutive segments of <= group_edges edges each (one warp walks them back to back,
+                             so a short row does not pay its own task start-up); longer segments appear as in `task` */
 } ultra_rspmm_order_t;
 
 /* Graph index: int32 device arrays describing the coalesced operand in the three edge orders the
@@ -100,7 +106,7 @@ const char *ultra_rspmm_status_string(int status);
 int64_t ultra_rspmm_launch_count(void);
 void ultra_rspmm_launch_count_reset(void);
 /* tuning knobs (process-wide; 0 keeps the current value).  chunk: edges per task for indexes built
- * afterwards (default 256).  variant: L2 eviction-priority hints of the gather kernels - 0 = automatic
+ * afterwards (default 256; rows of up to chunk / 4 edges are grouped, see `gtask`).  variant: L2 eviction-priority hints of the gather kernels - 0 = automatic
  * (on when the gathered slab exceeds 24 MiB), 1 = never, 2 = always.
  * l2_budget_bytes: L2 bytes the gathered operand's slab (rows x slab width) may occupy; the slab width
  * (512 / 256 / 128 bytes per row) is the widest that fits (default: unlimited, i.e. always 512). */

@@ -26,8 +26,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    # ultra_rspmm_order_t: 6 x int32 + 7 pointers; ultra_rspmm_index_t: 2 x int64 + 6 x int32 + 3 orders
-    assert ctypes.sizeof(_lib.Order) == 6 * 4 + 7 * 8
+    # ultra_rspmm_order_t: 8 x int32 + 8 pointers; ultra_rspmm_index_t: 2 x int64 + 6 x int32 + 3 orders
+    assert ctypes.sizeof(_lib.Order) == 8 * 4 + 8 * 8
     assert ctypes.sizeof(_lib.Index) == 2 * 8 + 6 * 4 + 3 * ctypes.sizeof(_lib.Order)
 
 

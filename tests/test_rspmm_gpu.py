@@ -389,3 +389,51 @@ def test_fused_pna_equals_four_calls(cuda, mul, weights):
     finally:
         lib.ultra_rspmm_set_tuning(256, 0, 0)
         F.clear_index_cache()
+
+
+def test_grouped_task_list_covers_every_segment_once(cuda):
+    """Low-degree operand: the grouped task list (short rows share a task) covers every segment and every edge exactly
+    once, group tasks hold at most 16 consecutive short segments, and results equal the plain path bit for bit."""
+    from ultra_torchdrug_b200 import _lib, functional as F
+    rng = np.random.default_rng(5)
+    n, r, nnz = 600, 7, 2400                                   # average degree 4, some empty rows, one hub
+    indices = np.stack([rng.integers(0, n, nnz), rng.integers(0, n, nnz), rng.integers(0, r, nnz)]).astype(np.int64)
+    indices[0, :300] = 17                                      # a long row (300 edges > chunk / 4)
+    values = np.ones(nnz, dtype=np.float32)
+    index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), (n, n, r))
+    base = index.buffer.data_ptr()
+
+    def view(ptr, count, dtype):
+        offset = ptr - base
+        return index.buffer[offset:offset + count * 4].view(dtype).cpu().numpy()
+
+    for order in (index.c.csr, index.c.csc):
+        assert order.n_gtask > 0 and order.n_gtask < order.n_task and order.group_edges == 64
+        ptr = view(order.ptr, n + 1, torch.int32)
+        task = view(order.gtask, 4 * order.n_gtask, torch.int32).reshape(-1, 4)
+        seg_hits, edge_hits = np.zeros(n, dtype=int), np.zeros(index.nnz, dtype=int)
+        for seg, begin, end, encoded in task:
+            rows = ((encoded >> 24) & 15) + 1 if encoded & 0x20000000 else 1
+            if encoded & 0x20000000:
+                assert begin == ptr[seg] and end == ptr[seg + rows] and rows <= 16
+                assert (np.diff(ptr[seg:seg + rows + 1]) <= 64).all()
+                seg_hits[seg:seg + rows] += 1
+            else:
+                assert ptr[seg] <= begin <= end <= ptr[seg + 1]
+                seg_hits[seg] += (begin == ptr[seg])
+            edge_hits[begin:end] += 1
+        assert (seg_hits == 1).all() and (edge_hits == 1).all()
+    relation, input = util.random_dense(r, 256, 1), util.random_dense(n, 256, 2)
+    grad = util.random_dense(n, 256, 3)
+    d = [torch.from_numpy(x).to(cuda) for x in (relation, input, grad)]
+    out = index.forward(d[0], d[1], "add", "mul", addend=d[2])
+    g_rel, g_in = index.backward(d[0], d[1], out, d[2], "add", "mul")
+    exp, _ = util.oracle_forward(indices, values, (n, n, r), relation, input, "add", "mul", dtype=np.float64)
+    np.testing.assert_allclose(out.cpu().numpy(), exp + grad, rtol=1e-5, atol=1e-5)
+    e_rel, e_in = util.oracle_backward(indices, values, (n, n, r), relation, input, None, grad, "add", "mul", dtype=np.float64)
+    np.testing.assert_allclose(g_in.cpu().numpy(), e_in, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(g_rel.cpu().numpy(), e_rel, rtol=1e-5, atol=2e-3)
+    mx, arg = index.forward(d[0], d[1], "max", "mul", return_argidx=True)       # arg-index path keeps the plain list
+    exp_max, exp_arg = util.oracle_forward(indices, values, (n, n, r), relation, input, "max", "mul")
+    assert np.array_equal(mx.cpu().numpy(), exp_max) and np.array_equal(arg.cpu().numpy().astype(np.int64), exp_arg)
+    assert np.array_equal(index.forward(d[0], d[1], "max", "mul").cpu().numpy(), exp_max)   # grouped, no arg-index

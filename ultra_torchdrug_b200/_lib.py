@@ -21,9 +21,9 @@ c_void_p, c_int32, c_int64, c_size_t = ctypes.c_void_p, ctypes.c_int32, ctypes.c
 class Order(ctypes.Structure):
     """`ultra_rspmm_order_t`"""
     _fields_ = [("n_seg", c_int32), ("n_task", c_int32), ("n_slot", c_int32), ("n_split", c_int32),
-                ("max_seg_nnz", c_int32), ("pack_shift", c_int32),
+                ("max_seg_nnz", c_int32), ("pack_shift", c_int32), ("n_gtask", c_int32), ("group_edges", c_int32),
                 ("ptr", c_void_p), ("edge", c_void_p), ("w", c_void_p), ("eid", c_void_p), ("packed", c_void_p),
-                ("task", c_void_p), ("split", c_void_p)]
+                ("task", c_void_p), ("split", c_void_p), ("gtask", c_void_p)]
 
 
 class Index(ctypes.Structure):

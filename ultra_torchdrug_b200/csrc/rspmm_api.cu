@@ -13,6 +13,7 @@ static std::atomic<long long> g_launches{0};
 static thread_local int t_last_cuda_error = 0;
 int g_chunk = 256;
 int g_variant = 0;
+int g_group_edges = getenv("ULTRA_RSPMM_GROUP") ? atoi(getenv("ULTRA_RSPMM_GROUP")) : -1;
 long long g_l2_budget = 1ll << 40;   // slab narrowing off by default: it lost on every measured shape (profiles/)
 
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }

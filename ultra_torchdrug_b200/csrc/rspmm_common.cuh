@@ -168,7 +168,15 @@ template <typename T, int MSG> __device__ __forceinline__ T message(T r, T x) {
 // task.w = (slot + 1) | kNonUnitTask: slot of the partial row the task writes (-1 = the result row itself) and
 // whether any of its edges has a merged weight different from 1
 constexpr int kNonUnitTask = 0x40000000;
-__host__ __device__ __forceinline__ int task_slot(int encoded) { return (encoded & (kNonUnitTask - 1)) - 1; }
+// group tasks (grouped task list): task.w = kGroupTask | (rows - 1) << 24 | kNonUnitTask?; they never write partial rows
+constexpr int kGroupTask = 0x20000000;
+constexpr int kGroupRows = 16;   // most segments per group task (4 bits at bit 24)
+__host__ __device__ __forceinline__ int task_slot(int encoded) {
+    return (encoded & kGroupTask) ? -1 : (encoded & (kGroupTask - 1)) - 1;
+}
+__host__ __device__ __forceinline__ int task_rows(int encoded) {
+    return (encoded & kGroupTask) ? ((encoded >> 24) & (kGroupRows - 1)) + 1 : 1;
+}
 
 // launch bookkeeping (claimed in bench.py as `gpu_launches`)
 void note_launch();
@@ -176,6 +184,7 @@ void note_launch();
 int fail_cuda(cudaError_t error);
 extern int g_chunk;    // edges per task for new indexes
 extern int g_variant;  // 0 auto, 1 generic, 2 staged
+extern int g_group_edges;  // rows of up to this many edges are grouped in the grouped task list (-1: chunk / 4, 0: off)
 extern long long g_l2_budget;  // bytes of L2 the gathered operand's slab may occupy (slab width is chosen to fit)
 
 #define ULTRA_CUDA_OK(expr)                                      \

@@ -31,6 +31,7 @@ enum Counter {
     CNT_NNZ = 2,      // merged edge count
     CNT_MAXSEG = 3,   // +order: longest segment
     CNT_TOTALS = 8,   // +3*order: n_task, n_slot, n_split
+    CNT_GTASKS = 20,  // +order: n_gtask
     CNT_SIZE = 32
 };
 
@@ -218,6 +219,71 @@ __global__ void task_emit_kernel(const int32_t *__restrict__ ptr, int32_t n_seg,
     split[off_split[s]] = make_int4(s, slot0, c, 0);
 }
 
+// ---- grouped task list: consecutive short segments share one task -------------------------------------------------
+// A segment of at most `group` edges is "short".  Consecutive short segments whose first edges fall into the same
+// window of `group` edges (and the same block of kGroupRows segments) form one group task; every other segment
+// gets the tasks it has in the plain list.
+__device__ __forceinline__ bool group_head(const int32_t *__restrict__ ptr, int32_t s, int32_t group) {
+    if (s == 0) return true;
+    if (ptr[s] - ptr[s - 1] > group) return true;                 // the previous segment is not short
+    return ptr[s] / group != ptr[s - 1] / group || s / kGroupRows != (s - 1) / kGroupRows;
+}
+
+__global__ void group_count_kernel(const int32_t *__restrict__ ptr, int32_t n_seg, int32_t chunk, int32_t group,
+                                   int32_t *__restrict__ cnt_gtask) {
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_seg) return;
+    if (s == n_seg) {
+        cnt_gtask[s] = 0;
+        return;
+    }
+    const int32_t deg = ptr[s + 1] - ptr[s];
+    if (deg > group) cnt_gtask[s] = deg <= chunk ? 1 : (deg + chunk - 1) / chunk;
+    else cnt_gtask[s] = group_head(ptr, s, group) ? 1 : 0;
+}
+
+__global__ void group_emit_kernel(const int32_t *__restrict__ ptr, int32_t n_seg, int32_t chunk, int32_t group,
+                                  const int32_t *__restrict__ off_gtask, const int32_t *__restrict__ off_slot,
+                                  const int32_t *__restrict__ nonunit_before, int4 *__restrict__ task,
+                                  uint32_t *__restrict__ task_key, int32_t *__restrict__ task_val) {
+    const int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const int32_t begin = ptr[s], deg = ptr[s + 1] - begin;
+    const int32_t t0 = off_gtask[s];
+    auto nonunit = [&](int32_t from, int32_t to) {
+        return nonunit_before && nonunit_before[to] != nonunit_before[from] ? kNonUnitTask : 0;
+    };
+    if (deg <= group) {
+        if (!group_head(ptr, s, group)) return;
+        int32_t rows = 1;
+        while (rows < kGroupRows && s + rows < n_seg && ptr[s + rows + 1] - ptr[s + rows] <= group &&
+               !group_head(ptr, s + rows, group))
+            ++rows;
+        const int32_t end = ptr[s + rows];
+        task[t0] = make_int4(s, begin, end, kGroupTask | ((rows - 1) << 24) | nonunit(begin, end));
+        task_key[t0] = (uint32_t)(chunk - (end - begin));
+        task_val[t0] = t0;
+        return;
+    }
+    const int32_t end = begin + deg;
+    if (deg <= chunk) {
+        task[t0] = make_int4(s, begin, end, 0 | nonunit(begin, end));
+        task_key[t0] = (uint32_t)(chunk - deg);
+        task_val[t0] = t0;
+        return;
+    }
+    const int32_t c = (deg + chunk - 1) / chunk, slot0 = off_slot[s];
+    const int32_t base = deg / c, extra = deg % c;
+    int32_t at = begin;
+    for (int32_t q = 0; q < c; ++q) {
+        const int32_t len = base + (q < extra ? 1 : 0);
+        task[t0 + q] = make_int4(s, at, at + len, (slot0 + q + 1) | nonunit(at, at + len));
+        task_key[t0 + q] = (uint32_t)(chunk - len);
+        task_val[t0 + q] = t0 + q;
+        at += len;
+    }
+}
+
 __global__ void task_gather_kernel(const int4 *__restrict__ task_in, const int32_t *__restrict__ order, int32_t n_task,
                                    int4 *__restrict__ task_out) {
     const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,7 +350,7 @@ int bit_length(unsigned long long v) {
 }
 
 struct OrderLayout {
-    size_t ptr, edge, w, eid, packed, task, split;
+    size_t ptr, edge, w, eid, packed, task, split, gtask;
 };
 
 struct IndexLayout {
@@ -313,6 +379,7 @@ IndexLayout index_layout(int64_t nnz_raw, const int32_t n_seg[3], size_t elem, i
         q.packed = at; at = align_up(at + sizeof(uint32_t) * e);
         q.task = at; at = align_up(at + sizeof(int4) * task_upper(nnz_raw, n_seg[o], chunk));
         q.split = at; at = align_up(at + sizeof(int4) * split_upper(nnz_raw, chunk));
+        q.gtask = at; at = align_up(at + (o == 2 ? 0 : sizeof(int4) * task_upper(nnz_raw, n_seg[o], chunk)));
     }
     L.total = at;
     return L;
@@ -330,8 +397,8 @@ ScratchLayout scratch_layout(int64_t nnz_raw, int32_t n_seg_max, int chunk) {
     S.pos = at; at = align_up(at + 4 * (e + 1));
     S.row_of = at; at = align_up(at + 4 * e);
     S.seg_of = at; at = align_up(at + 4 * e);
-    S.cnt = at; at = align_up(at + 3 * 4 * ((size_t)n_seg_max + 1));
-    S.off = at; at = align_up(at + 9 * 4 * ((size_t)n_seg_max + 1));
+    S.cnt = at; at = align_up(at + 4 * 4 * ((size_t)n_seg_max + 1));
+    S.off = at; at = align_up(at + 12 * 4 * ((size_t)n_seg_max + 1));
     S.task_tmp = at; at = align_up(at + 16 * nt);
     S.tkey_a = at; at = align_up(at + 4 * nt);
     S.tkey_b = at; at = align_up(at + 4 * nt);
@@ -351,6 +418,7 @@ template <typename T>
 int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values, int64_t nnz_raw, int32_t n_out,
                 int32_t n_in, int32_t n_rel, char *ibuf, char *sbuf, ultra_rspmm_index_t *index, cudaStream_t stream) {
     const int chunk = g_chunk;
+    const int group = g_group_edges < 0 ? chunk / 4 : (g_group_edges > chunk / 2 ? chunk / 2 : g_group_edges);
     const int32_t n_seg[3] = {n_out, n_in, n_rel};
     const int32_t n_seg_max = n_out > n_in ? (n_out > n_rel ? n_out : n_rel) : (n_in > n_rel ? n_in : n_rel);
     const IndexLayout L = index_layout(nnz_raw, n_seg, sizeof(T), chunk);
@@ -455,7 +523,7 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
             }
         }
         int32_t *cnt = (int32_t *)(sbuf + S.cnt);
-        int32_t *off = (int32_t *)(sbuf + S.off) + (size_t)o * 3 * ((size_t)n_seg_max + 1);
+        int32_t *off = (int32_t *)(sbuf + S.off) + (size_t)o * 4 * ((size_t)n_seg_max + 1);
         const size_t span = (size_t)n_seg_max + 1;
         task_count_kernel<<<blocks_for((int64_t)n_seg[o] + 1), kBuildThreads, 0, stream>>>(
             ptr, n_seg[o], chunk, cnt, cnt + span, cnt + 2 * span, counters + CNT_MAXSEG + o);
@@ -467,6 +535,16 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
         }
         gather_totals_kernel<<<1, 1, 0, stream>>>(off, off + span, off + 2 * span, n_seg[o], counters + CNT_TOTALS + 3 * o);
         note_launch();
+        if (o < 2 && group > 0 && (long long)nnz < 30ll * n_seg[o]) {   // grouped task list: worth it for short segments only
+            group_count_kernel<<<blocks_for((int64_t)n_seg[o] + 1), kBuildThreads, 0, stream>>>(ptr, n_seg[o], chunk, group,
+                                                                                              cnt + 3 * span);
+            note_launch();
+            need = S.cub_bytes;
+            ULTRA_CUDA_OK(cub::DeviceScan::ExclusiveSum(cub_tmp, need, cnt + 3 * span, off + 3 * span, n_seg[o] + 1, stream));
+            note_launch();
+            ULTRA_CUDA_OK(cudaMemcpyAsync(counters + CNT_GTASKS + o, off + 3 * span + n_seg[o], sizeof(int32_t),
+                                          cudaMemcpyDeviceToDevice, stream));
+        }
     }
     ULTRA_CUDA_OK(cudaMemcpyAsync(host_counters, counters, 4 * CNT_SIZE, cudaMemcpyDeviceToHost, stream));
     ULTRA_CUDA_OK(cudaStreamSynchronize(stream));
@@ -476,7 +554,7 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
     for (int o = 0; o < 3; ++o) {
         ultra_rspmm_order_t &out = *orders[o];
         const size_t span = (size_t)n_seg_max + 1;
-        const int32_t *off = (int32_t *)(sbuf + S.off) + (size_t)o * 3 * span;
+        const int32_t *off = (int32_t *)(sbuf + S.off) + (size_t)o * 4 * span;
         out.n_seg = n_seg[o];
         out.n_task = host_counters[CNT_TOTALS + 3 * o];
         out.n_slot = host_counters[CNT_TOTALS + 3 * o + 1];
@@ -507,6 +585,23 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
         task_gather_kernel<<<blocks_for(out.n_task), kBuildThreads, 0, stream>>>(task_tmp, tval_b, out.n_task,
                                                                                (int4 *)(ibuf + L.order[o].task));
         note_launch();
+        out.n_gtask = o < 2 && group > 0 && (long long)nnz < 30ll * n_seg[o] ? host_counters[CNT_GTASKS + o] : 0;
+        out.group_edges = out.n_gtask > 0 ? group : 0;
+        out.gtask = out.n_gtask > 0 ? (const int32_t *)(ibuf + L.order[o].gtask) : nullptr;
+        if (out.n_gtask > 0) {
+            if (out.n_gtask > task_upper(nnz_raw, n_seg[o], chunk)) return ULTRA_RSPMM_ERR_WORKSPACE;
+            group_emit_kernel<<<blocks_for(n_seg[o]), kBuildThreads, 0, stream>>>(
+                out.ptr, n_seg[o], chunk, group, off + 3 * span, off + span,
+                any_nonunit ? (const int32_t *)(sbuf + S.nonunit) + (size_t)o * ((size_t)(nnz_raw > 0 ? nnz_raw : 1) + 1) : nullptr,
+                task_tmp, tkey_a, tval_a);
+            note_launch();
+            if (int status = sort_pairs(cub_tmp, S.cub_bytes, tkey_a, tkey_b, tval_a, tval_b, out.n_gtask,
+                                        bit_length((unsigned long long)chunk), stream))
+                return status;
+            task_gather_kernel<<<blocks_for(out.n_gtask), kBuildThreads, 0, stream>>>(task_tmp, tval_b, out.n_gtask,
+                                                                                    (int4 *)(ibuf + L.order[o].gtask));
+            note_launch();
+        }
     }
     ULTRA_CUDA_OK(cudaGetLastError());
     ULTRA_CUDA_OK(cudaStreamSynchronize(stream));  // scratch may be released by the caller on return

@@ -29,6 +29,7 @@ constexpr int kUnroll = 4;
 static_assert(kUnroll == 4, "the tail switch in seg_reduce_kernel enumerates 1..3 leftover edges");   // 4 edges in flight per warp at 4 CTAs/SM beat 2x5, 6x3, 8x3, 8x2 (profiles/README.md)
 
 template <typename T> struct SegArgs {
+    const int32_t *ptr;       // segment pointers of the order (group tasks read their rows' boundaries here)
     const int4 *task;
     const int2 *edge;
     const unsigned *packed;   // edge ids packed as x | y << pack_shift (null when they do not fit 32 bits)
@@ -46,6 +47,7 @@ template <typename T> struct SegArgs {
     int n_task;
     int n_slab;
     int keep;   // 1: mark the gathered slab evict_last in L2 and the edge-id stream evict_first
+    int grouped;   // 1: `task` is the grouped list (short rows share a task)
 };
 
 template <typename T, int SUM> __device__ __forceinline__ void reduce_into(T &acc, T m) {
@@ -71,7 +73,7 @@ template <typename T> __device__ __forceinline__ const T *row_ptr(const char *ba
 // ids (staged by the whole warp; one LDS.128 serves 4 edges when the two ids pack into 32 bits), 2 IMAD.WIDE
 // (row addresses), 2 LDG.128, VEC FFMA - no shuffles, no predicates; the ragged tail of a task runs in a separate
 // single-edge loop.  Tasks whose edges all have weight 1 (flag in task.w) skip the weight stream and multiply.
-template <typename T, int VEC, int SUM, int MSG, bool B_TABLE, bool ARG, bool PACKED, bool KEEP>
+template <typename T, int VEC, int SUM, int MSG, bool B_TABLE, bool ARG, bool PACKED, bool KEEP, bool GROUPED>
 __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const SegArgs<T> a) {
     using Ids = typename std::conditional<PACKED, unsigned, int2>::type;
     __shared__ __align__(16) Ids s_edge[kWarpsPerBlock][32];
@@ -83,6 +85,13 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
     const int slab = (int)(gw / a.n_task);
     const int4 task = __ldg(a.task + (gw - (long long)slab * a.n_task));
     const int slot = task_slot(task.w);
+    // a group task walks `rows` consecutive short segments back to back: lane l keeps the start of row l (lane `rows`
+    // the end of the last one); a plain task is the case rows == 1
+    const int rows = GROUPED ? task_rows(task.w) : 1;
+    int boundary_of_lane = task.z;
+    if (GROUPED && rows > 1 && lane <= rows) boundary_of_lane = __ldg(a.ptr + task.x + lane);
+    int row_local = 0;
+    int next_boundary = GROUPED && rows > 1 ? __shfl_sync(kFullMask, boundary_of_lane, 1) : task.z;
     const long long col = (long long)slab * (32 * VEC) + lane * VEC;
     const bool active = col < a.dim;
     const long long safe_col = active ? col : 0;   // idle lanes (dim % (32 * VEC) != 0) read column 0, store nothing
@@ -109,6 +118,43 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
         acc[v] = reduce_identity<T, SUM>();
         arg[v] = -1;
     }
+    // write the finished row (or partial row) and start the next one; warp-uniform
+    auto flush = [&]() {
+        if (active) {
+            Vec<T, VEC> r;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) r.v[v] = acc[v];
+            const long long row = task.x + row_local;
+            if (slot < 0) {
+                if (a.addend) {
+                    Vec<T, VEC> b;
+                    gather_load(a.addend + row * a.dim + col, b);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) r.v[v] += b.v[v];
+                }
+                stream_store(a.out + row * a.dim + col, r);
+            } else {
+                T *p = a.partial + (long long)slot * a.dim + col;   // re-read soon by the combine pass: default policy
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) p[v] = r.v[v];
+            }
+            if (ARG) {
+                int32_t *p = slot < 0 ? a.arg_out + row * a.dim + col : a.partial_arg + (long long)slot * a.dim + col;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) p[v] = arg[v];
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            acc[v] = reduce_identity<T, SUM>();
+            arg[v] = -1;
+        }
+        ++row_local;
+        if (GROUPED) {
+            const int upcoming = __shfl_sync(kFullMask, boundary_of_lane, (row_local + 1) & 31);
+            next_boundary = row_local < rows ? upcoming : 0x7fffffff;
+        }
+    };
 
     auto reduce_task = [&](auto unit_tag) {
         constexpr bool UNIT = decltype(unit_tag)::value;
@@ -182,39 +228,28 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
                 }
             };
             int u = 0;
-            for (; u + kUnroll <= n; u += kUnroll) run_batch(std::integral_constant<int, kUnroll>(), u);
-            switch (n - u) {
-                case 1: run_batch(std::integral_constant<int, 1>(), u); break;
-                case 2: run_batch(std::integral_constant<int, 2>(), u); break;
-                case 3: run_batch(std::integral_constant<int, 3>(), u); break;
-                default: break;
+            while (u < n) {
+                if (GROUPED) {
+                    while (base + u == next_boundary) flush();   // a group task: the next row(s) start here
+                }
+                const int stop = GROUPED ? min(n, next_boundary - base) : n;   // the current row's edges inside this batch
+                for (; u + kUnroll <= stop; u += kUnroll) run_batch(std::integral_constant<int, kUnroll>(), u);
+                switch (stop - u) {
+                    case 1: run_batch(std::integral_constant<int, 1>(), u); break;
+                    case 2: run_batch(std::integral_constant<int, 2>(), u); break;
+                    case 3: run_batch(std::integral_constant<int, 3>(), u); break;
+                    default: break;
+                }
+                u = stop;
             }
         }
     };
     if (a.w == nullptr || !(task.w & kNonUnitTask)) reduce_task(std::true_type());
     else reduce_task(std::false_type());
-
-    if (!active) return;
-    Vec<T, VEC> r;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) r.v[v] = acc[v];
-    if (slot < 0) {
-        if (a.addend) {
-            Vec<T, VEC> b;
-            gather_load(a.addend + (long long)task.x * a.dim + col, b);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) r.v[v] += b.v[v];
-        }
-        stream_store(a.out + (long long)task.x * a.dim + col, r);
+    if (GROUPED) {
+        while (row_local < rows) flush();   // the last row, and empty rows that close a group
     } else {
-        T *p = a.partial + (long long)slot * a.dim + col;   // re-read soon by the combine pass: default policy
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) p[v] = r.v[v];
-    }
-    if (ARG) {
-        int32_t *p = slot < 0 ? a.arg_out + (long long)task.x * a.dim + col : a.partial_arg + (long long)slot * a.dim + col;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) p[v] = arg[v];
+        flush();
     }
 }
 
@@ -514,23 +549,27 @@ __global__ void combine_kernel(const int4 *__restrict__ split, int n_split, cons
 // ------------------------------------------------------------------------------------------------
 template <typename T> constexpr int wide_vec() { return 16 / sizeof(T); }
 
+// Instantiation budget: the L2-hint (KEEP) and grouped-task variants exist only where they matter - float operands at the
+// full slab width; group tasks never carry an arg-index.  args.keep / args.grouped are set accordingly by run_pass.
 template <typename T, int VEC, int SUM, int MSG, bool B_TABLE, bool ARG>
 int launch_seg(const SegArgs<T> &args, cudaStream_t stream) {
     const long long warps = (long long)args.n_task * args.n_slab;
     if (warps == 0) return ULTRA_RSPMM_OK;
     const long long blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > 0x7fffffffLL || args.dim * (long long)sizeof(T) > 0xffffffffLL) return ULTRA_RSPMM_ERR_RANGE;
-    if (args.keep) {
-        if (args.packed)
-            seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, true, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
-        else
-            seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, false, true><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+    constexpr bool TUNED = sizeof(T) == 4 && VEC == 4;
+    const unsigned grid = (unsigned)blocks;
+#define ULTRA_SEG(PACKED, KEEP, GROUPED) \
+    seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, PACKED, KEEP, GROUPED><<<grid, kThreadsPerBlock, 0, stream>>>(args)
+    if (TUNED && args.grouped && !ARG) {
+        if (args.keep) { if (args.packed) ULTRA_SEG(true, TUNED, (TUNED && !ARG)); else ULTRA_SEG(false, TUNED, (TUNED && !ARG)); }
+        else { if (args.packed) ULTRA_SEG(true, false, (TUNED && !ARG)); else ULTRA_SEG(false, false, (TUNED && !ARG)); }
+    } else if (TUNED && args.keep) {
+        if (args.packed) ULTRA_SEG(true, TUNED, false); else ULTRA_SEG(false, TUNED, false);
     } else {
-        if (args.packed)
-            seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, true, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
-        else
-            seg_reduce_kernel<T, VEC, SUM, MSG, B_TABLE, ARG, false, false><<<(unsigned)blocks, kThreadsPerBlock, 0, stream>>>(args);
+        if (args.packed) ULTRA_SEG(true, false, false); else ULTRA_SEG(false, false, false);
     }
+#undef ULTRA_SEG
     note_launch();
     return ULTRA_RSPMM_OK;
 }
@@ -579,6 +618,7 @@ template <typename T, int SUM, int MSG, bool B_TABLE, bool ARG>
 int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, const T *B, long long rows_gathered, T *out,
              int32_t *arg_out, long long dim, void *workspace, cudaStream_t stream, const T *addend = nullptr) {
     SegArgs<T> args;
+    args.ptr = order.ptr;
     args.task = (const int4 *)order.task;
     args.edge = (const int2 *)order.edge;
     args.packed = order.pack_shift > 0 ? (const unsigned *)order.packed : nullptr;
@@ -596,7 +636,15 @@ int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, con
     args.n_task = order.n_task;
     const int vec = pick_vec<T>(dim, rows_gathered, {A, B, out, workspace, addend});
     args.n_slab = (int)((dim + 32 * vec - 1) / (32 * vec));
-    args.keep = g_variant == 2 || (g_variant == 0 && rows_gathered * 32 * vec * (long long)sizeof(T) > (24ll << 20));
+    const bool tuned = sizeof(T) == 4 && vec == 4;
+    args.keep = tuned && (g_variant == 2 || (g_variant == 0 && rows_gathered * 32 * vec * (long long)sizeof(T) > (24ll << 20)));
+    // short rows are walked several per warp: the grouped task list (built only for orders whose segments average
+    // fewer than ~30 edges, see rspmm_index.cu)
+    args.grouped = tuned && !ARG && order.n_gtask > 0;
+    if (args.grouped) {
+        args.task = (const int4 *)order.gtask;
+        args.n_task = order.n_gtask;
+    }
     int status;
     if (vec == 4) status = launch_seg<T, sizeof(T) == 4 ? 4 : 2, SUM, MSG, B_TABLE, ARG>(args, stream);
     else if (vec == 2) status = launch_seg<T, 2, SUM, MSG, B_TABLE, ARG>(args, stream);
