@@ -184,6 +184,25 @@ def workload_config():
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(gpu_index):
+    """Multi-GPU runs: keep this rank (and the pinned host buffers it allocates for the e2e leg) on the CPU cores
+    that are NUMA-local to its GPU, so that 8 ranks do not push their PCIe traffic across the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -194,7 +213,9 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the rspmm path has no CPU fallback (use --impl reference "
                          "for the CPU baseline)")
+    numa_cores = None
     if world > 1:
+        numa_cores = bind_to_gpu_numa_node(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
@@ -284,7 +305,7 @@ def run_gpu_arm(args):
             "edge_messages_per_s": world * 2.0 * e * d / (ms_per_step * 1e-3),
             "clocks": clocks,
             "e2e": {"value": world * bytes_step / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "numa_local_cores_per_rank": numa_cores,
                     "api": "ultra_rspmm_ctx_forward_backward (C ABI, pinned host buffers)"},
             "gpu_launches": launches,
             "ultra_queries": {"value": world * queries["queries_per_batch"] / (queries["ms_per_batch"] * 1e-3),
