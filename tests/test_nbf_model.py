@@ -120,3 +120,26 @@ def test_c1_zero_shot_scores_and_mrr_on_cuda(cuda):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     _check_c1(cuda, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_predict_equals_eager(cuda):
+    """`UltraRanker.capture`: one CUDA graph per batch size, replayed on fresh batches, reproduces eager `predict`."""
+    from ultra_torchdrug_b200 import functional as F, synthetic
+    torch.manual_seed(5)
+    num_node, num_relation = 300, 6
+    triples = synthetic.triples(num_node, num_relation, 1500, seed=5)
+    graph = data.Graph(triples, num_node=num_node, num_relation=num_relation).to(cuda)
+    model, rel_model = nbf.ultra_models(num_relation, hidden=32, num_layers=3)
+    ranker = nbf.UltraRanker(model.to(cuda).eval(), rel_model.to(cuda).eval(), graph)
+    run = ranker.capture(batch_size=8)
+    launches = F.launch_count()
+    for seed in range(3):
+        batch = triples[torch.randperm(len(triples), generator=torch.Generator().manual_seed(seed))[:8]].to(cuda)
+        with torch.no_grad():
+            eager = ranker.predict(batch)
+        replayed = run(batch).clone()
+        assert torch.equal(replayed, eager), "graph replay differs from eager execution"
+    with pytest.raises(ValueError):
+        run(batch[:4])
+    assert F.launch_count() > launches

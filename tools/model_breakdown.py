@@ -46,6 +46,9 @@ with torch.no_grad():
     print("entity model pass     %8.3f ms device  %8.3f ms wall" % (ms, wall))
     ms, wall, _ = timed(lambda: ranker.predict(batch))
     print("predict (1 rel + 2 entity passes) %8.3f ms device  -> %.0f queries/s" % (ms, 2 * batch_size / ms * 1e3))
+    run = ranker.capture(batch_size)
+    ms, wall, _ = timed(lambda: run(batch))
+    print("predict, CUDA graph replay        %8.3f ms device  %8.3f ms wall -> %.0f queries/s" % (ms, wall, 2 * batch_size / ms * 1e3))
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         ranker.predict(batch)
