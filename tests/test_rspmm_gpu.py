@@ -6,6 +6,7 @@ rtol 1e-5 / atol 1e-6 of the oracle.  Sums are compared against the oracle evalu
 absolute tolerance is scaled by the row's sum of |terms| as usual for floating-point sums.
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -337,7 +338,7 @@ def test_forward_with_boundary_addend(cuda):
         F.clear_index_cache()
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("ULTRA_TEST_SEEDS", "24"))))
 def test_parity_randomized(cuda, seed):
     """Seeded random shapes: rectangular operands, self-loops, isolated rows, Zipf destinations, odd feature widths,
     tiny / huge chunk sizes, unit and merged weights, fp32 and fp64 (SURVEY.md section 8c test (4))."""
@@ -437,3 +438,10 @@ def test_grouped_task_list_covers_every_segment_once(cuda):
     exp_max, exp_arg = util.oracle_forward(indices, values, (n, n, r), relation, input, "max", "mul")
     assert np.array_equal(mx.cpu().numpy(), exp_max) and np.array_equal(arg.cpu().numpy().astype(np.int64), exp_arg)
     assert np.array_equal(index.forward(d[0], d[1], "max", "mul").cpu().numpy(), exp_max)   # grouped, no arg-index
+
+
+@pytest.mark.parametrize("sum,mul", [("add", "mul"), ("max", "mul"), ("add", "add")])
+def test_parity_moderate_power_law(cuda, sum, mul):
+    """4,000 nodes, 45,000 edges, Zipf destinations: hub rows split into partial rows, thousands of short rows walked in
+    group tasks, empty rows - all in one index; against the oracle."""
+    _run_case(cuda, 4000, 4000, 12, 45000, 260, sum, mul, seed=41, duplicates=500, weights="random", skew=True)
