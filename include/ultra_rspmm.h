@@ -142,6 +142,17 @@ int ultra_rspmm_forward(const ultra_rspmm_index_t *index, const void *dev_relati
                         const void *dev_addend, void *dev_output, int32_t *dev_argidx, int64_t dim, int32_t dtype,
                         int32_t sum_op, int32_t mul_op, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Forward (sum = add, fp32) on operands that live inside a wider buffer: a row of `input` / `output` is dim / block
+ * blocks of `block` features, consecutive blocks `*_block_stride` elements apart, the output shifted by
+ * `output_block_offset` inside its stride.  With block = 64, strides = 128, offset = 64 the operator reads the layer
+ * input from the left halves and writes `update + boundary` into the right halves of the (N, B, 128) buffer that the
+ * layer's Linear consumes - the `torch.cat([input, update], dim=-1)` of reference layer.py:387 disappears.
+ * relation (n_rel, dim) and addend (n_out, dim, may be NULL) are plain matrices.  All strides / offsets % 4 == 0. */
+int ultra_rspmm_forward_blocked(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
+                                const void *dev_addend, void *dev_output, int64_t dim, int32_t dtype, int32_t mul_op,
+                                int64_t block, int64_t input_block_stride, int64_t output_block_stride,
+                                int64_t output_block_offset, void *workspace, size_t workspace_bytes, void *stream);
+
 /* PNA aggregation in one pass: the four operator calls of reference layer.py:141-144 / 164-167 / 343-346 / 366-369
  * (add, add of the squared operands, max, min) over one gather per edge.  Outputs (n_out, dim) each.
  * workspace: 4 x the forward partial-row bytes (4 * csr.n_slot * dim * sizeof(element)); forward only. */
@@ -194,6 +205,13 @@ int ultra_layer_norm_relu_residual(const float *dev_x, const float *dev_linear_b
 /* Backward of the fused epilogue (fine-tuning): given d(out) it writes d(x) and the column sums d(linear_bias),
  * d(gamma), d(beta) (any of the three may be NULL); d(residual) = d(out).  Row statistics are recomputed from x.
  * workspace: ultra_layer_norm_relu_residual_backward_bytes(dim).  Deterministic (no atomics). */
+/* Strided form of the epilogue: row r of out / residual starts at r * out_stride / r * residual_stride elements
+ * (strides % 4 == 0, >= dim), x stays a plain (rows, dim) matrix - lets the epilogue read its short-cut from, and write
+ * its result into, the left halves of the (N, B, 128) layer buffers (see ultra_rspmm_forward_blocked). */
+int ultra_layer_norm_relu_residual_strided(const float *dev_x, const float *dev_linear_bias, const float *dev_gamma,
+                                           const float *dev_beta, const float *dev_residual, float *dev_out,
+                                           int64_t rows, int32_t dim, int64_t residual_stride, int64_t out_stride,
+                                           float eps, int32_t relu, void *stream);
 int ultra_layer_norm_relu_residual_backward_bytes(int32_t dim, size_t *workspace_bytes);
 int ultra_layer_norm_relu_residual_backward(const float *dev_x, const float *dev_linear_bias, const float *dev_gamma,
                                             const float *dev_beta, const float *dev_grad_out, float *dev_grad_x,

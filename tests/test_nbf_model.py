@@ -143,3 +143,32 @@ def test_cuda_graph_predict_equals_eager(cuda):
     with pytest.raises(ValueError):
         run(batch[:4])
     assert F.launch_count() > launches
+
+
+@pytest.mark.gpu
+def test_buffered_layer_loop_equals_generic_loop(cuda, monkeypatch):
+    """The cat-free inference loop (`_run_layers_buffered`) gives the scores of the generic loop (cat + Linear +
+    epilogue): same kernels, same GEMM operands — only where the bytes live differs."""
+    from ultra_torchdrug_b200 import synthetic
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(11)
+    num_node, num_relation = 400, 7
+    triples = synthetic.triples(num_node, num_relation, 2500, seed=11)
+    graph = data.Graph(triples, num_node=num_node, num_relation=num_relation).to(cuda)
+    model, rel_model = nbf.ultra_models(num_relation, hidden=64, num_layers=3)
+    ranker = nbf.UltraRanker(model.to(cuda).eval(), rel_model.to(cuda).eval(), graph)
+    batch = triples[:6].to(cuda)
+    taken = []
+    original = nbf._run_layers_buffered
+    monkeypatch.setattr(nbf, "_run_layers_buffered", lambda *a: taken.append(1) or original(*a))
+    with torch.no_grad():
+        buffered = ranker.predict(batch)
+    assert len(taken) == 3, "the buffered loop must serve the relation pass and both entity passes"
+    monkeypatch.setattr(nbf, "_buffered_layers_supported", lambda layers, boundary: False)
+    with torch.no_grad():
+        generic = ranker.predict(batch)
+    assert len(taken) == 3
+    torch.testing.assert_close(buffered, generic, rtol=1e-5, atol=1e-6)
+    with torch.enable_grad():                        # training keeps the autograd path
+        ranker.predict(batch).sum().backward()
+    assert len(taken) == 3

@@ -338,6 +338,61 @@ def test_forward_with_boundary_addend(cuda):
         F.clear_index_cache()
 
 
+@pytest.mark.parametrize("mul", ["mul", "add"])
+@pytest.mark.parametrize("block,batch,chunk,nnz", [(64, 3, 256, 4000), (16, 5, 16, 3000), (4, 7, 256, 150), (128, 2, 16, 2500)])
+def test_forward_blocked_equals_plain_forward(cuda, mul, block, batch, chunk, nnz):
+    """The cat-free layout (operands embedded in (rows, B, stride) buffers, reference layer.py:387) is bit-identical to
+    the plain operator + addend on direct rows, split rows (chunk 16) and grouped short rows (nnz 150)."""
+    from ultra_torchdrug_b200 import _lib, functional as F
+    lib = _lib.lib()
+    lib.ultra_rspmm_set_tuning(chunk, 0, 0)
+    try:
+        n, n_rel, dim = 120, 5, block * batch
+        indices, values = util.random_coo(n, n, n_rel, nnz, seed=block + batch, duplicates=10, skew=True)
+        index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), (n, n, n_rel))
+        relation = torch.from_numpy(util.random_dense(n_rel, dim, 1)).to(cuda)
+        input = torch.from_numpy(util.random_dense(n, dim, 2)).to(cuda)
+        boundary = torch.from_numpy(util.random_dense(n, dim, 3)).to(cuda)
+        want = index.forward(relation, input, "add", mul, addend=boundary)
+        # one buffer: input in the left halves, result into the right halves
+        buffer = torch.full((n, batch, 2 * block), float("nan"), device=cuda)
+        buffer[..., :block] = input.view(n, batch, block)
+        index.forward_blocked(relation, buffer, buffer, block, 0, block, mul, addend=boundary)
+        assert torch.equal(buffer[..., block:], want.view(n, batch, block)), "blocked result differs"
+        assert torch.equal(buffer[..., :block], input.view(n, batch, block)), "input halves were modified"
+        # separate buffers, input at an offset, no addend, wider output stride
+        source = torch.full((n, batch, block + 8), float("nan"), device=cuda)
+        source[..., 8:] = input.view(n, batch, block)
+        target = torch.full((n, batch, 3 * block), -7.0, device=cuda)
+        index.forward_blocked(relation, source, target, block, 8, 2 * block, mul)
+        assert torch.equal(target[..., 2 * block:], index.forward(relation, input, "add", mul).view(n, batch, block))
+        assert bool((target[..., :2 * block] == -7.0).all()), "bytes outside the output blocks were written"
+        with pytest.raises(RuntimeError):
+            index.forward_blocked(relation, buffer[:, :, :-1], buffer, block, 0, block, mul)
+    finally:
+        lib.ultra_rspmm_set_tuning(256, 0, 0)
+
+
+def test_layer_epilogue_strided_equals_contiguous(cuda):
+    """The strided epilogue (residual read from / result written into halves of wider buffers) == the contiguous one."""
+    from ultra_torchdrug_b200 import functional as F
+    torch.manual_seed(5)
+    dim = 64
+    x = torch.randn(700, 3, dim, device=cuda) * 2
+    weight, bias, shift = (torch.randn(dim, device=cuda) for _ in range(3))
+    current = torch.randn(700, 3, 2 * dim, device=cuda)
+    following = torch.full((700, 3, 2 * dim), 9.0, device=cuda)
+    want = F.layer_norm_relu_residual(x, weight, bias, current[..., :dim].contiguous(), 1e-5, relu=True, linear_bias=shift)
+    F.layer_norm_relu_residual_into(x, following[..., :dim], weight, bias, current[..., :dim], 1e-5, True, shift)
+    assert torch.equal(following[..., :dim], want)
+    assert bool((following[..., dim:] == 9.0).all())
+    want = F.layer_norm_relu_residual(x, None, None, None, 1e-5, relu=False)
+    F.layer_norm_relu_residual_into(x, following[..., dim:], relu=False)
+    assert torch.equal(following[..., dim:], want)
+    with pytest.raises(RuntimeError):
+        F.layer_norm_relu_residual_into(x, following[..., ::2])
+
+
 @pytest.mark.parametrize("seed", range(int(os.environ.get("ULTRA_TEST_SEEDS", "24"))))
 def test_parity_randomized(cuda, seed):
     """Seeded random shapes: rectangular operands, self-loops, isolated rows, Zipf destinations, odd feature widths,

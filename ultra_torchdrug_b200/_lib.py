@@ -50,6 +50,9 @@ SYMBOLS = {
                                                    ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),
     "ultra_rspmm_forward": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                            c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
+    "ultra_rspmm_forward_blocked": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                                   c_int32, c_int32, c_int64, c_int64, c_int64, c_int64, c_void_p, c_size_t,
+                                                   c_void_p]),
     "ultra_rspmm_forward_pna": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                c_void_p, c_int64, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "ultra_rspmm_backward": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -66,6 +69,9 @@ SYMBOLS = {
     "ultra_rspmm_host_free": (ctypes.c_int, [c_void_p]),
     "ultra_layer_norm_relu_residual": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                                       ctypes.c_float, c_int32, c_void_p]),
+    "ultra_layer_norm_relu_residual_strided": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                              c_int64, c_int32, c_int64, c_int64, ctypes.c_float, c_int32,
+                                                              c_void_p]),
     "ultra_layer_norm_relu_residual_backward_bytes": (ctypes.c_int, [c_int32, ctypes.POINTER(c_size_t)]),
     "ultra_layer_norm_relu_residual_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                                c_void_p, c_void_p, c_void_p, c_int64, c_int32, ctypes.c_float,

@@ -21,12 +21,15 @@ __global__ void __launch_bounds__(256) norm_relu_residual_kernel(const float4 *_
                                                                   const float4 *__restrict__ beta,
                                                                   const float4 *__restrict__ residual,
                                                                   float4 *__restrict__ out, long long rows, float eps,
-                                                                  int relu) {
+                                                                  int relu, long long residual_stride4,
+                                                                  long long out_stride4) {
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES;
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const bool live = row < rows;
     const long long at = (live ? row : 0) * LANES + sub;
+    const long long residual_at = (live ? row : 0) * residual_stride4 + sub;   // strides in float4 units
+    const long long out_at = (live ? row : 0) * out_stride4 + sub;
     float4 v = live ? __ldcs(x + at) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (linear_bias) {
         const float4 b = __ldg(linear_bias + sub);
@@ -50,10 +53,10 @@ __global__ void __launch_bounds__(256) norm_relu_residual_kernel(const float4 *_
     }
     if (relu) r = make_float4(fmaxf(r.x, 0.f), fmaxf(r.y, 0.f), fmaxf(r.z, 0.f), fmaxf(r.w, 0.f));
     if (residual) {
-        const float4 s = __ldcs(residual + at);
+        const float4 s = __ldcs(residual + residual_at);
         r = make_float4(r.x + s.x, r.y + s.y, r.z + s.z, r.w + s.w);
     }
-    out[at] = r;
+    out[out_at] = r;
 }
 
 // Backward of the fused epilogue.  Per row (recomputing mean / rstd / xhat from x):
@@ -159,12 +162,14 @@ __global__ void column_sums_kernel(const float *__restrict__ partial, int blocks
 
 using namespace ultra;
 
-extern "C" int ultra_layer_norm_relu_residual(const float *dev_x, const float *dev_linear_bias, const float *dev_gamma, const float *dev_beta,
-                                              const float *dev_residual, float *dev_out, int64_t rows, int32_t dim,
-                                              float eps, int32_t relu, void *stream) {
+static int epilogue_forward(const float *dev_x, const float *dev_linear_bias, const float *dev_gamma, const float *dev_beta,
+                            const float *dev_residual, float *dev_out, int64_t rows, int32_t dim, int64_t residual_stride,
+                            int64_t out_stride, float eps, int32_t relu, void *stream) {
     if (rows < 0 || dim <= 0 || (rows > 0 && (!dev_x || !dev_out))) return ULTRA_RSPMM_ERR_ARG;
     if ((dev_gamma == nullptr) != (dev_beta == nullptr)) return ULTRA_RSPMM_ERR_ARG;
     if (dim % 4 || dim > 128 || (dim & (dim - 1))) return ULTRA_RSPMM_ERR_RANGE;   // 4, 8, ..., 128 features per row
+    if (residual_stride % 4 || out_stride % 4 || out_stride < dim || (dev_residual && residual_stride < dim))
+        return ULTRA_RSPMM_ERR_ARG;
     if (((uintptr_t)dev_x | (uintptr_t)dev_out | (uintptr_t)dev_gamma | (uintptr_t)dev_beta | (uintptr_t)dev_residual |
          (uintptr_t)dev_linear_bias) & 15)
         return ULTRA_RSPMM_ERR_ARG;
@@ -175,9 +180,10 @@ extern "C" int ultra_layer_norm_relu_residual(const float *dev_x, const float *d
     if (blocks > 0x7fffffffLL) return ULTRA_RSPMM_ERR_RANGE;
     cudaStream_t s = (cudaStream_t)stream;
 #define ULTRA_LAUNCH(L)                                                                                              \
-    norm_relu_residual_kernel<L><<<(unsigned)blocks, 256, 0, s>>>((const float4 *)dev_x, (const float4 *)dev_linear_bias, (const float4 *)dev_gamma, \
-                                                                    (const float4 *)dev_beta, (const float4 *)dev_residual, \
-                                                                    (float4 *)dev_out, rows, eps, relu)
+    norm_relu_residual_kernel<L><<<(unsigned)blocks, 256, 0, s>>>((const float4 *)dev_x, (const float4 *)dev_linear_bias, \
+                                                                    (const float4 *)dev_gamma, (const float4 *)dev_beta, \
+                                                                    (const float4 *)dev_residual, (float4 *)dev_out, rows, \
+                                                                    eps, relu, residual_stride / 4, out_stride / 4)
     switch (lanes) {
         case 1: ULTRA_LAUNCH(1); break;
         case 2: ULTRA_LAUNCH(2); break;
@@ -190,6 +196,22 @@ extern "C" int ultra_layer_norm_relu_residual(const float *dev_x, const float *d
     note_launch();
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;
+}
+
+extern "C" int ultra_layer_norm_relu_residual(const float *dev_x, const float *dev_linear_bias, const float *dev_gamma, const float *dev_beta,
+                                              const float *dev_residual, float *dev_out, int64_t rows, int32_t dim,
+                                              float eps, int32_t relu, void *stream) {
+    return epilogue_forward(dev_x, dev_linear_bias, dev_gamma, dev_beta, dev_residual, dev_out, rows, dim, dim, dim, eps, relu,
+                            stream);
+}
+
+extern "C" int ultra_layer_norm_relu_residual_strided(const float *dev_x, const float *dev_linear_bias,
+                                                      const float *dev_gamma, const float *dev_beta,
+                                                      const float *dev_residual, float *dev_out, int64_t rows,
+                                                      int32_t dim, int64_t residual_stride, int64_t out_stride, float eps,
+                                                      int32_t relu, void *stream) {
+    return epilogue_forward(dev_x, dev_linear_bias, dev_gamma, dev_beta, dev_residual, dev_out, rows, dim, residual_stride,
+                            out_stride, eps, relu, stream);
 }
 
 extern "C" int ultra_layer_norm_relu_residual_backward_bytes(int32_t dim, size_t *workspace_bytes) {

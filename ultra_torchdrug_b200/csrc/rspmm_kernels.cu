@@ -48,6 +48,10 @@ template <typename T> struct SegArgs {
     int n_slab;
     int keep;   // 1: mark the gathered slab evict_last in L2 and the edge-id stream evict_first
     int grouped;   // 1: `task` is the grouped list (short rows share a task)
+    // blocked layout (block == 0: A and out are plain (rows, dim) matrices).  Otherwise a row of A / out is dim / block
+    // blocks of `block` features, consecutive blocks a_stride / o_stride elements apart, out shifted by o_offset:
+    // the (N, B, 2d) buffer whose halves are the layer input and the layer update (reference layer.py:387 `cat`)
+    long long block, a_stride, o_stride, o_offset;
 };
 
 template <typename T, int SUM> __device__ __forceinline__ void reduce_into(T &acc, T m) {
@@ -96,7 +100,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
     const bool active = col < a.dim;
     const long long safe_col = active ? col : 0;   // idle lanes (dim % (32 * VEC) != 0) read column 0, store nothing
     const unsigned row_bytes = (unsigned)(a.dim * sizeof(T));
-    const char *A = reinterpret_cast<const char *>(a.A + safe_col);
+    // blocked operands: column c of the logical (rows, dim) matrix lives at (c / block) * stride + c % block
+    const long long a_col = a.block ? (safe_col / a.block) * a.a_stride + safe_col % a.block : safe_col;
+    const unsigned a_row_bytes = a.block ? (unsigned)((a.dim / a.block) * a.a_stride * sizeof(T)) : row_bytes;
+    const char *A = reinterpret_cast<const char *>(a.A + a_col);
     const char *B = reinterpret_cast<const char *>(a.B + safe_col);
     const Ids *ids = reinterpret_cast<const Ids *>(PACKED ? (const void *)a.packed : (const void *)a.edge);
     const int shift = a.pack_shift;
@@ -132,7 +139,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) r.v[v] += b.v[v];
                 }
-                stream_store(a.out + row * a.dim + col, r);
+                // (the blocked output position is recomputed here rather than kept live across the edge loop)
+                const long long o_col = a.block ? (col / a.block) * a.o_stride + a.o_offset + col % a.block : col;
+                const long long o_row = a.block ? (a.dim / a.block) * a.o_stride : a.dim;
+                stream_store(a.out + row * o_row + o_col, r);
             } else {
                 T *p = a.partial + (long long)slot * a.dim + col;   // re-read soon by the combine pass: default policy
 #pragma unroll
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
                     e[q] = s_edge[warp][u + q];
                     w[q] = UNIT ? T(1) : s_w[warp][u + q];
                     same = same && second_id(e[q]) == cached_row;
-                    gather(row_ptr<T>(A, first_id(e[q]), row_bytes), va[q]);
+                    gather(row_ptr<T>(A, first_id(e[q]), a_row_bytes), va[q]);
                 }
                 if (same) {   // warp-uniform
 #pragma unroll
@@ -523,7 +533,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 2) seg_pna_kernel(const PnaA
 template <typename T, int SUM, bool ARG>
 __global__ void combine_kernel(const int4 *__restrict__ split, int n_split, const T *__restrict__ partial,
                                const int32_t *__restrict__ partial_arg, const T *__restrict__ addend,
-                               T *__restrict__ out, int32_t *__restrict__ arg_out, long long dim) {
+                               T *__restrict__ out, int32_t *__restrict__ arg_out, long long dim, long long block,
+                               long long o_stride, long long o_offset) {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= dim) return;
     const int4 s = __ldg(split + blockIdx.y);
@@ -540,7 +551,8 @@ __global__ void combine_kernel(const int4 *__restrict__ split, int n_split, cons
         reduce_into<T, SUM>(acc, m);
     }
     if (addend) acc += addend[(long long)s.x * dim + col];
-    out[(long long)s.x * dim + col] = acc;
+    if (block) out[(long long)s.x * (dim / block) * o_stride + (col / block) * o_stride + o_offset + col % block] = acc;
+    else out[(long long)s.x * dim + col] = acc;
     if (ARG) arg_out[(long long)s.x * dim + col] = arg;
 }
 
@@ -576,7 +588,8 @@ int launch_seg(const SegArgs<T> &args, cudaStream_t stream) {
 
 template <typename T, int SUM, bool ARG>
 int launch_combine(const ultra_rspmm_order_t &order, const T *partial, const int32_t *partial_arg, T *out,
-                   int32_t *arg_out, long long dim, cudaStream_t stream, const T *addend = nullptr) {
+                   int32_t *arg_out, long long dim, cudaStream_t stream, const T *addend = nullptr, long long block = 0,
+                   long long o_stride = 0, long long o_offset = 0) {
     if (order.n_split == 0 || dim == 0) return ULTRA_RSPMM_OK;
     const dim3 grid((unsigned)((dim + 255) / 256), (unsigned)order.n_split);
     if (order.n_split > 65535) {
@@ -584,13 +597,14 @@ int launch_combine(const ultra_rspmm_order_t &order, const T *partial, const int
         for (int at = 0; at < order.n_split; at += 65535) {
             const int n = order.n_split - at < 65535 ? order.n_split - at : 65535;
             combine_kernel<T, SUM, ARG><<<dim3(grid.x, n), 256, 0, stream>>>((const int4 *)order.split + at, n, partial,
-                                                                              partial_arg, addend, out, arg_out, dim);
+                                                                              partial_arg, addend, out, arg_out, dim, block,
+                                                                              o_stride, o_offset);
             note_launch();
         }
         return ULTRA_RSPMM_OK;
     }
     combine_kernel<T, SUM, ARG><<<grid, 256, 0, stream>>>((const int4 *)order.split, order.n_split, partial, partial_arg,
-                                                          addend, out, arg_out, dim);
+                                                          addend, out, arg_out, dim, block, o_stride, o_offset);
     note_launch();
     return ULTRA_RSPMM_OK;
 }
@@ -613,10 +627,15 @@ int pick_vec(long long dim, long long rows, std::initializer_list<const void *> 
     return vec;
 }
 
+struct BlockedLayout {
+    long long block = 0, a_stride = 0, o_stride = 0, o_offset = 0;
+};
+
 // one reduction pass + its combine
 template <typename T, int SUM, int MSG, bool B_TABLE, bool ARG>
 int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, const T *B, long long rows_gathered, T *out,
-             int32_t *arg_out, long long dim, void *workspace, cudaStream_t stream, const T *addend = nullptr) {
+             int32_t *arg_out, long long dim, void *workspace, cudaStream_t stream, const T *addend = nullptr,
+             const BlockedLayout layout = BlockedLayout()) {
     SegArgs<T> args;
     args.ptr = order.ptr;
     args.task = (const int4 *)order.task;
@@ -634,6 +653,10 @@ int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, con
     args.partial_arg = ARG ? (int32_t *)((char *)workspace + align_up((size_t)order.n_slot * dim * sizeof(T))) : nullptr;
     args.dim = dim;
     args.n_task = order.n_task;
+    args.block = layout.block;
+    args.a_stride = layout.a_stride;
+    args.o_stride = layout.o_stride;
+    args.o_offset = layout.o_offset;
     const int vec = pick_vec<T>(dim, rows_gathered, {A, B, out, workspace, addend});
     args.n_slab = (int)((dim + 32 * vec - 1) / (32 * vec));
     const bool tuned = sizeof(T) == 4 && vec == 4;
@@ -650,7 +673,8 @@ int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, con
     else if (vec == 2) status = launch_seg<T, 2, SUM, MSG, B_TABLE, ARG>(args, stream);
     else status = launch_seg<T, 1, SUM, MSG, B_TABLE, ARG>(args, stream);
     if (status) return status;
-    return launch_combine<T, SUM, ARG>(order, args.partial, args.partial_arg, out, arg_out, dim, stream, addend);
+    return launch_combine<T, SUM, ARG>(order, args.partial, args.partial_arg, out, arg_out, dim, stream, addend,
+                                       layout.block, layout.o_stride, layout.o_offset);
 }
 
 template <typename T, int VEC, int MSG, bool P_TABLE>
@@ -915,6 +939,41 @@ extern "C" int ultra_rspmm_forward_pna(const ultra_rspmm_index_t *index, const v
                      ? forward_pna_typed<double, MSG_MUL>(*index, (const double *)dev_relation, (const double *)dev_input, out, dim, workspace, s)
                      : forward_pna_typed<double, MSG_ADD>(*index, (const double *)dev_relation, (const double *)dev_input, out, dim, workspace, s);
     }
+    if (status) return status;
+    ULTRA_CUDA_OK(cudaGetLastError());
+    return ULTRA_RSPMM_OK;
+}
+
+extern "C" int ultra_rspmm_forward_blocked(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
+                                           const void *dev_addend, void *dev_output, int64_t dim, int32_t dtype,
+                                           int32_t mul_op, int64_t block, int64_t input_block_stride,
+                                           int64_t output_block_stride, int64_t output_block_offset, void *workspace,
+                                           size_t workspace_bytes, void *stream) {
+    int status = check_call(index, dim, dtype, ULTRA_RSPMM_SUM_ADD, mul_op);
+    if (status) return status;
+    if (dtype != ULTRA_RSPMM_F32) return ULTRA_RSPMM_ERR_DTYPE;
+    if (block <= 0 || dim % block || block % 4 || input_block_stride < block || output_block_stride < block ||
+        input_block_stride % 4 || output_block_stride % 4 || output_block_offset % 4 || output_block_offset < 0 ||
+        output_block_offset + block > output_block_stride)
+        return ULTRA_RSPMM_ERR_ARG;
+    if (index->n_out == 0 || dim == 0) return ULTRA_RSPMM_OK;
+    if (!dev_output || !dev_relation || !dev_input) return ULTRA_RSPMM_ERR_ARG;
+    if ((dim / block) * input_block_stride * 4 > 0xffffffffLL) return ULTRA_RSPMM_ERR_RANGE;
+    const size_t need = pass_bytes(index->csr, dim, 4, false);
+    if (index->csr.n_slot > 0 && (!workspace || workspace_bytes < need)) return ULTRA_RSPMM_ERR_WORKSPACE;
+    BlockedLayout layout;
+    layout.block = block;
+    layout.a_stride = input_block_stride;
+    layout.o_stride = output_block_stride;
+    layout.o_offset = output_block_offset;
+    const bool unit = index->unit_weight != 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const float *r = (const float *)dev_relation, *x = (const float *)dev_input, *b = (const float *)dev_addend;
+    float *o = (float *)dev_output;
+    constexpr int ADD = ULTRA_RSPMM_SUM_ADD;
+    status = mul_op == ULTRA_RSPMM_MUL_MUL
+                 ? run_pass<float, ADD, MSG_MUL, true, false>(index->csr, unit, x, r, index->n_in, o, nullptr, dim, workspace, s, b, layout)
+                 : run_pass<float, ADD, MSG_ADD, true, false>(index->csr, unit, x, r, index->n_in, o, nullptr, dim, workspace, s, b, layout);
     if (status) return status;
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;

@@ -19,7 +19,8 @@ import torch
 from . import _lib
 
 __all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
-           "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "rspmm_pna", "LayerEpilogueFunction"]
+           "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "rspmm_pna", "LayerEpilogueFunction",
+           "layer_norm_relu_residual_into"]
 
 _SUM_OPS = ("add", "min", "max")
 _MUL_OPS = ("mul", "add")
@@ -108,6 +109,30 @@ class GraphIndex(object):
                 _DTYPE_CODE[self.dtype], _lib.SUM_CODE[sum], _lib.MUL_CODE[mul], _ptr(workspace), need,
                 _stream_handle()), "ultra_rspmm_forward")
         return (output, argidx) if return_argidx else output
+
+    def forward_blocked(self, relation, input_buffer, output_buffer, block, input_offset, output_offset, mul="mul",
+                        addend=None):
+        """sum-aggregation forward on operands embedded in wider (rows, B, stride) fp32 buffers: the input is
+        `input_buffer[..., input_offset:input_offset + block]`, the result (+ addend) is written into
+        `output_buffer[..., output_offset:output_offset + block]` (may be the same buffer).  Removes the
+        `torch.cat([input, update], -1)` of reference layer.py:387 when the buffer is what the layer's Linear reads."""
+        batch = input_buffer.shape[1]
+        dim = batch * block
+        for name, buffer, rows in (("input", input_buffer, self.shape[1]), ("output", output_buffer, self.shape[0])):
+            if buffer.dim() != 3 or not buffer.is_contiguous() or buffer.dtype != torch.float32 or buffer.shape[0] != rows \
+                    or buffer.shape[1] != batch:
+                raise RuntimeError("%s buffer must be a contiguous float32 (%d, %d, stride) tensor" % (name, rows, batch))
+        if addend is not None and (addend.shape != (self.shape[0], dim) or addend.dtype != torch.float32):
+            raise RuntimeError("`addend` must be a float32 (%d, %d) matrix" % (self.shape[0], dim))
+        need = self.workspace_bytes(dim)[0]
+        with torch.cuda.device(input_buffer.device):
+            workspace = torch.empty(need, dtype=torch.uint8, device=input_buffer.device) if need else None
+            _lib.check(_lib.lib().ultra_rspmm_forward_blocked(
+                ctypes.byref(self.c), _ptr(relation), ctypes.c_void_p(input_buffer.data_ptr() + 4 * input_offset),
+                _ptr(addend), _ptr(output_buffer), dim, _DTYPE_CODE[self.dtype], _lib.MUL_CODE[mul], block,
+                input_buffer.shape[2], output_buffer.shape[2], output_offset, _ptr(workspace), need, _stream_handle()),
+                "ultra_rspmm_forward_blocked")
+        return output_buffer
 
     def forward_pna(self, relation, input, mul="mul"):
         """(sum, sum of squared operands, max, min) of the messages in one pass - the four operator calls of the
@@ -214,6 +239,30 @@ def layer_norm_relu_residual(x, weight=None, bias=None, residual=None, eps=1e-5,
         return LayerEpilogueFunction.apply(x, linear_bias, weight, bias, residual, eps, relu)
     contiguous = [None if t is None else t.contiguous() for t in (linear_bias, weight, bias, residual)]
     return _epilogue_forward(x.contiguous(), contiguous[0], contiguous[1], contiguous[2], contiguous[3], eps, relu)
+
+
+def layer_norm_relu_residual_into(x, out, weight=None, bias=None, residual=None, eps=1e-5, relu=True, linear_bias=None):
+    """Strided form of `layer_norm_relu_residual` (inference): `out` and `residual` are (..., dim) views whose rows are
+    `stride(-2)` elements apart (e.g. the left halves of (N, B, 2 * dim) layer buffers); x is contiguous."""
+    dim = x.shape[-1]
+    rows = x.numel() // max(dim, 1)
+    if not layer_epilogue_supported(x, dim) or not x.is_contiguous():
+        raise RuntimeError("layer_norm_relu_residual_into needs a contiguous float32 CUDA input with 4..128 features per row")
+    for name, view in (("out", out), ("residual", residual)):
+        if view is None:
+            continue
+        uniform = view.dim() >= 2 and all(view.stride(axis) == view.stride(axis + 1) * view.shape[axis + 1]
+                                          for axis in range(view.dim() - 2))
+        if view.shape != x.shape or view.dtype != torch.float32 or view.device != x.device or view.stride(-1) != 1 \
+                or not uniform or view.stride(-2) < dim:
+            raise RuntimeError("`%s` must be a float32 view of shape %s whose rows are evenly spaced" % (name, tuple(x.shape)))
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().ultra_layer_norm_relu_residual_strided(
+            _ptr(x), _ptr(linear_bias), _ptr(weight), _ptr(bias),
+            ctypes.c_void_p(residual.data_ptr()) if residual is not None else ctypes.c_void_p(0),
+            ctypes.c_void_p(out.data_ptr()), rows, dim, residual.stride(-2) if residual is not None else dim,
+            out.stride(-2), float(eps), int(bool(relu)), _stream_handle()), "ultra_layer_norm_relu_residual_strided")
+    return out
 
 
 def _fingerprint(indices, values):

@@ -165,7 +165,45 @@ class GeneralizedRelationalConvNBFMod(_RelationalConvBase):
         return relation.transpose(1, 0).flatten(1)   # (B, R', d) -> (R', B * d)
 
 
+def _buffered_layers_supported(layers, boundary):
+    """Inference fast path of `_run_layers_buffered`: sum aggregation, LayerNorm + ReLU, equal widths, fp32 CUDA."""
+    if not boundary.is_cuda or boundary.dtype != torch.float32 or torch.is_grad_enabled():
+        return False
+    width = boundary.shape[-1]
+    for layer in layers:
+        if layer.aggregate_func != "sum" or layer.message_func not in MESSAGE_TO_MUL or layer.layer_norm is None:
+            return False
+        if layer.activation not in (F.relu, None) or layer.input_dim != width or layer.output_dim != width:
+            return False
+    return rspmm.layer_epilogue_supported(boundary, width)
+
+
+def _run_layers_buffered(layers, graph, boundary, short_cut):
+    """The layer loop without `torch.cat([input, update], -1)` (reference layer.py:387): two (N, B, 2d) buffers whose
+    left halves hold the layer input and whose right halves receive `update + boundary` straight from the operator; the
+    Linear reads a buffer as is, and the fused epilogue writes the next layer's input into the other buffer's left half.
+    Same arithmetic as `_run_layers`; returns the final buffer (left half = hidden state, right half free)."""
+    num_node, batch, width = boundary.shape
+    buffers = [torch.empty(num_node, batch, 2 * width, dtype=boundary.dtype, device=boundary.device) for _ in range(2)]
+    buffers[0][..., :width] = boundary
+    flat_boundary = boundary.flatten(1)
+    index = rspmm.graph_index(graph.adjacency.transpose(0, 1))
+    for number, layer in enumerate(layers):
+        current, following = buffers[number % 2], buffers[(number + 1) % 2]
+        relation_input = layer.relation_input(graph, batch).contiguous()
+        index.forward_blocked(relation_input, current, current, width, 0, width, MESSAGE_TO_MUL[layer.message_func],
+                              addend=flat_boundary)
+        projected = F.linear(current.view(num_node * batch, 2 * width), layer.linear.weight)
+        rspmm.layer_norm_relu_residual_into(
+            projected.view(num_node, batch, width), following[..., :width], layer.layer_norm.weight, layer.layer_norm.bias,
+            current[..., :width] if short_cut else None, layer.layer_norm.eps, relu=layer.activation is not None,
+            linear_bias=layer.linear.bias)
+    return buffers[len(layers) % 2]
+
+
 def _run_layers(layers, graph, boundary, short_cut):
+    if _buffered_layers_supported(layers, boundary):
+        return _run_layers_buffered(layers, graph, boundary, short_cut)[..., :boundary.shape[-1]]
     hidden = boundary
     for layer in layers:
         skip = hidden if short_cut and layer.output_dim == hidden.shape[-1] else None
@@ -228,6 +266,10 @@ class TransferNBFNet(nn.Module):
             graph.query = query
         with graph.node():
             graph.boundary = boundary
+        if _buffered_layers_supported(self.layers, boundary):
+            feature = _run_layers_buffered(self.layers, graph, boundary, self.short_cut)   # (N, B, 2d): hidden | free
+            feature[..., boundary.shape[-1]:] = query                                      # cat([hidden, query]) in place
+            return feature
         hidden = _run_layers(self.layers, graph, boundary, self.short_cut)
         return torch.cat([hidden, query.expand(graph.num_node, -1, -1)], dim=-1)
 
