@@ -219,6 +219,14 @@ int ultra_layer_norm_relu_residual_backward(const float *dev_x, const float *dev
                                             int64_t rows, int32_t dim, float eps, int32_t relu, void *workspace,
                                             size_t workspace_bytes, void *stream);
 
+/* ---- scoring head (reference model.py:177-193, the 2-layer MLP over [hidden | query]) ---- */
+/* score[r] = bias[0] + sum_c weight[c] * relu(z[r, c] + query_bias[r % batch, c]) over `rows` rows of `dim` fp32 features
+ * (dim in {4, 8, ..., 128}).  z = hidden @ W1[:, :d]^T (a cuBLAS GEMM that stays in PyTorch), query_bias (batch, dim) =
+ * query @ W1[:, d:]^T + b1, weight (dim) = W2[0], bias (1 element, may be NULL) = b2.  Rows are (node, query) pairs with
+ * the query index fastest. */
+int ultra_score_head(const float *dev_z, const float *dev_query_bias, const float *dev_weight, const float *dev_bias,
+                     float *dev_score, int64_t rows, int32_t batch, int32_t dim, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

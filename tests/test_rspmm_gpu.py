@@ -393,6 +393,20 @@ def test_layer_epilogue_strided_equals_contiguous(cuda):
         F.layer_norm_relu_residual_into(x, following[..., ::2])
 
 
+@pytest.mark.parametrize("dim", [4, 32, 128])
+def test_score_head_matches_torch(cuda, dim):
+    """Fused `relu(z + query_bias) . w + b` vs the separate PyTorch ops of the scoring MLP (model.py:177-193)."""
+    from ultra_torchdrug_b200 import functional as F
+    torch.manual_seed(dim)
+    z = torch.randn(333, 5, dim, device=cuda)
+    query_bias, weight, bias = torch.randn(5, dim, device=cuda), torch.randn(1, dim, device=cuda), torch.randn(1, device=cuda)
+    want = torch.nn.functional.linear(torch.relu(z + query_bias), weight, bias).squeeze(-1)
+    torch.testing.assert_close(F.score_head(z, query_bias, weight, bias), want, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(F.score_head(z, query_bias, weight), want - bias, rtol=1e-5, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        F.score_head(z, query_bias[:4], weight, bias)
+
+
 @pytest.mark.parametrize("seed", range(int(os.environ.get("ULTRA_TEST_SEEDS", "24"))))
 def test_parity_randomized(cuda, seed):
     """Seeded random shapes: rectangular operands, self-loops, isolated rows, Zipf destinations, odd feature widths,

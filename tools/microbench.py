@@ -23,6 +23,8 @@ def edge_model_bytes(n, r, e, d, passes="fwd", elem=4, gated=False):
         return elem * d * (2 * e + 2 * n + 2 * r) + idx
     if gated and passes in ("bwd_input", "bwd_relation"):
         return elem * d * (2 * e + (n if passes == "bwd_input" else 0) + r + n) + idx
+    if passes in ("fwd+addend", "fwd_blocked"):
+        return elem * d * (e + r + 2 * n) + idx
     if passes == "fwd":
         return elem * d * (e + r + n) + idx
     if passes == "bwd_input":
@@ -106,6 +108,13 @@ def main():
                                                              args.sum, args.mul, need_input=False), args.iters)
     results["bwd"] = timed(lambda i: index.backward(relation, inputs[i % copies], out, grads[i % copies], args.sum,
                                                     args.mul), args.iters)
+    if args.sum == "add":        # the two forms the layers actually call: + boundary, and the cat-free blocked layout
+        results["fwd+addend"] = timed(lambda i: index.forward(relation, inputs[i % copies], "add", args.mul,
+                                                               addend=grads[i % copies]), args.iters)
+        buffers = [torch.randn(n, args.batch, 128, device=device, generator=generator) for _ in range(copies)]
+        results["fwd_blocked"] = timed(lambda i: index.forward_blocked(relation, buffers[i % copies], buffers[i % copies],
+                                                                       64, 0, 64, args.mul, addend=grads[i % copies]),
+                                       args.iters)
     for name, ms in results.items():
         gb = edge_model_bytes(n, r, e, d, name, gated=args.sum != "add") / 1e9
         print("%-13s %8.3f ms   %8.1f GB/s edge-model  (%.1f%% of measured HBM %.0f GB/s)   %.2f G edge-msg/s"

@@ -156,6 +156,32 @@ __global__ void column_sums_kernel(const float *__restrict__ partial, int blocks
     if (target) target[c % dim] = total;
 }
 
+// Scoring head of TransferNBFNet.forward (reference ultra/model.py:177-193): score = w2 . relu(W1 [hidden | query] + b1) + b2.
+// W1 [hidden | query] = W1h hidden + W1q query, and the query part is one row per QUERY, not per (node, query): the caller
+// runs z = hidden @ W1h^T as a K = d GEMM (half the flops of the K = 2d one) and passes query_bias = query @ W1q^T + b1
+// (batch rows).  This kernel is the rest of the head in one pass over z: add the row's query bias, ReLU, dot with w2.
+// Row r of z belongs to query r % batch (rows are (node, query) pairs, query fastest).
+template <int LANES>
+__global__ void __launch_bounds__(256) score_head_kernel(const float4 *__restrict__ z, const float4 *__restrict__ query_bias,
+                                                          const float4 *__restrict__ weight, const float *__restrict__ bias,
+                                                          float *__restrict__ score, long long rows, int batch) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LANES;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const bool live = row < rows;
+    const long long safe = live ? row : 0;
+    const float4 v = live ? __ldcs(z + safe * LANES + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 q = __ldg(query_bias + (safe % batch) * LANES + sub);
+    const float4 w = __ldg(weight + sub);
+    float dot = fmaxf(v.x + q.x, 0.f) * w.x;
+    dot = fmaf(fmaxf(v.y + q.y, 0.f), w.y, dot);
+    dot = fmaf(fmaxf(v.z + q.z, 0.f), w.z, dot);
+    dot = fmaf(fmaxf(v.w + q.w, 0.f), w.w, dot);
+#pragma unroll
+    for (int off = LANES / 2; off; off >>= 1) dot += __shfl_xor_sync(kFullMask, dot, off);
+    if (live && sub == 0) score[row] = dot + (bias ? __ldg(bias) : 0.f);
+}
+
 }  // namespace
 
 }  // namespace ultra
@@ -253,6 +279,34 @@ extern "C" int ultra_layer_norm_relu_residual_backward(const float *dev_x, const
     note_launch();
     column_sums_kernel<<<(3 * dim + 127) / 128, 128, 0, s>>>((const float *)workspace, kBackwardBlocks, 3 * dim,
                                                              dev_grad_gamma, dev_grad_beta, dev_grad_linear_bias, dim);
+    note_launch();
+    ULTRA_CUDA_OK(cudaGetLastError());
+    return ULTRA_RSPMM_OK;
+}
+
+extern "C" int ultra_score_head(const float *dev_z, const float *dev_query_bias, const float *dev_weight, const float *dev_bias,
+                                float *dev_score, int64_t rows, int32_t batch, int32_t dim, void *stream) {
+    if (rows < 0 || batch <= 0 || dim <= 0 || (rows > 0 && (!dev_z || !dev_query_bias || !dev_weight || !dev_score)))
+        return ULTRA_RSPMM_ERR_ARG;
+    if (dim % 4 || dim > 128 || (dim & (dim - 1))) return ULTRA_RSPMM_ERR_RANGE;   // 4, 8, ..., 128 features per row
+    if (((uintptr_t)dev_z | (uintptr_t)dev_query_bias | (uintptr_t)dev_weight) & 15) return ULTRA_RSPMM_ERR_ARG;
+    if (rows == 0) return ULTRA_RSPMM_OK;
+    const int lanes = dim / 4;
+    const long long blocks = (rows * lanes + 255) / 256;
+    if (blocks > 0x7fffffffLL) return ULTRA_RSPMM_ERR_RANGE;
+    cudaStream_t s = (cudaStream_t)stream;
+#define ULTRA_LAUNCH(L)                                                                                                    \
+    score_head_kernel<L><<<(unsigned)blocks, 256, 0, s>>>((const float4 *)dev_z, (const float4 *)dev_query_bias,          \
+                                                           (const float4 *)dev_weight, dev_bias, dev_score, rows, batch)
+    switch (lanes) {
+        case 1: ULTRA_LAUNCH(1); break;
+        case 2: ULTRA_LAUNCH(2); break;
+        case 4: ULTRA_LAUNCH(4); break;
+        case 8: ULTRA_LAUNCH(8); break;
+        case 16: ULTRA_LAUNCH(16); break;
+        default: ULTRA_LAUNCH(32); break;
+    }
+#undef ULTRA_LAUNCH
     note_launch();
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;

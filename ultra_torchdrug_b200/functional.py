@@ -20,7 +20,7 @@ from . import _lib
 
 __all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
            "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "rspmm_pna", "LayerEpilogueFunction",
-           "layer_norm_relu_residual_into"]
+           "layer_norm_relu_residual_into", "score_head"]
 
 _SUM_OPS = ("add", "min", "max")
 _MUL_OPS = ("mul", "add")
@@ -263,6 +263,22 @@ def layer_norm_relu_residual_into(x, out, weight=None, bias=None, residual=None,
             ctypes.c_void_p(out.data_ptr()), rows, dim, residual.stride(-2) if residual is not None else dim,
             out.stride(-2), float(eps), int(bool(relu)), _stream_handle()), "ultra_layer_norm_relu_residual_strided")
     return out
+
+
+def score_head(z, query_bias, weight, bias=None):
+    """`relu(z + query_bias[query]) @ weight + bias` for z of shape (N, B, dim) -> (N, B) scores: the second half of the
+    2-layer scoring MLP of reference model.py:177-193 in one pass (inference only; see `ultra_score_head`)."""
+    num_node, batch, dim = z.shape
+    if not layer_epilogue_supported(z, dim) or not z.is_contiguous():
+        raise RuntimeError("score_head needs a contiguous float32 CUDA tensor with 4..128 features per row")
+    query_bias, weight = query_bias.contiguous(), weight.contiguous().view(-1)
+    if query_bias.shape != (batch, dim) or weight.shape != (dim,) or query_bias.dtype != z.dtype or weight.dtype != z.dtype:
+        raise RuntimeError("score_head: query_bias must be (%d, %d) and weight (%d,) float32" % (batch, dim, dim))
+    score = torch.empty(num_node, batch, dtype=z.dtype, device=z.device)
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.lib().ultra_score_head(_ptr(z), _ptr(query_bias), _ptr(weight), _ptr(bias), _ptr(score),
+                                               num_node * batch, batch, dim, _stream_handle()), "ultra_score_head")
+    return score
 
 
 def _fingerprint(indices, values):

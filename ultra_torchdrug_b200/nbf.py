@@ -258,6 +258,25 @@ class TransferNBFNet(nn.Module):
         keep[edge_index] = False
         return graph.edge_mask(keep)
 
+    def _split_head_supported(self, feature):
+        """2-layer ReLU scoring MLP over [hidden | query] on the inference fast path (see `_split_head`)."""
+        layers = self.mlp.layers
+        return (len(layers) == 2 and layers[1].out_features == 1 and self.mlp.activation is F.relu
+                and not self.mlp.short_cut and self.mlp.batch_norms is None and self.mlp.dropout is None
+                and layers[0].in_features == feature.shape[-1] and layers[0].bias is not None
+                and rspmm.layer_epilogue_supported(feature, layers[0].out_features))
+
+    def _split_head(self, feature, query):
+        """Scores of every (node, query) pair from the (N, B, 2d) layer buffer without materialising cat([hidden, query])
+        (reference model.py:141-143, 177-193): W1 [hidden | query] = W1h hidden + W1q query, the second term being one row
+        per query.  The GEMM over all pairs halves to K = d; bias, ReLU and the 1-row second Linear are one fused pass."""
+        num_node, batch, width = feature.shape
+        hidden_dim = width - query.shape[-1]
+        first, second = self.mlp.layers
+        z = F.linear(feature.view(num_node * batch, width)[:, :hidden_dim], first.weight[:, :hidden_dim])
+        query_bias = F.linear(query, first.weight[:, hidden_dim:], first.bias)
+        return rspmm.score_head(z.view(num_node, batch, -1), query_bias, second.weight, second.bias)   # (N, B)
+
     def bellmanford(self, graph, h_index, r_index):
         batch = torch.arange(h_index.shape[0], device=h_index.device)
         query = self.query[r_index] if self.query.dim() == 2 else self.query[batch, r_index]
@@ -268,6 +287,8 @@ class TransferNBFNet(nn.Module):
             graph.boundary = boundary
         if _buffered_layers_supported(self.layers, boundary):
             feature = _run_layers_buffered(self.layers, graph, boundary, self.short_cut)   # (N, B, 2d): hidden | free
+            if self._split_head_supported(feature):
+                return feature, query                                                      # head reads the halves apart
             feature[..., boundary.shape[-1]:] = query                                      # cat([hidden, query]) in place
             return feature
         hidden = _run_layers(self.layers, graph, boundary, self.short_cut)
@@ -288,6 +309,9 @@ class TransferNBFNet(nn.Module):
         if not h_index.is_cuda:
             assert (h_index[:, :1] == h_index).all() and (r_index[:, :1] == r_index).all()
         feature = self.bellmanford(graph, h_index[:, 0], r_index[:, 0])           # (N, B, 2d)
+        if isinstance(feature, tuple):
+            score = self._split_head(*feature).transpose(0, 1)                    # (B, N)
+            return score.gather(1, t_index).view(shape)
         if 2 * t_index.shape[1] >= graph.num_node:
             # ranking against (almost) all entities: score every node once, then pick - the MLP is row-wise, so this
             # equals the reference's gather-then-score (model.py:177-193) without copying the (B, N, 2d) feature tensor
