@@ -160,7 +160,7 @@ def test_buffered_layer_loop_equals_generic_loop(cuda, monkeypatch):
     batch = triples[:6].to(cuda)
     taken = []
     original = nbf._run_layers_buffered
-    monkeypatch.setattr(nbf, "_run_layers_buffered", lambda *a: taken.append(1) or original(*a))
+    monkeypatch.setattr(nbf, "_run_layers_buffered", lambda *a, **k: taken.append(1) or original(*a, **k))
     with torch.no_grad():
         buffered = ranker.predict(batch)
     assert len(taken) == 3, "the buffered loop must serve the relation pass and both entity passes"

@@ -178,21 +178,35 @@ def _buffered_layers_supported(layers, boundary):
     return rspmm.layer_epilogue_supported(boundary, width)
 
 
-def _run_layers_buffered(layers, graph, boundary, short_cut):
+def _run_layers_buffered(layers, graph, boundary, short_cut, one_hot=None):
     """The layer loop without `torch.cat([input, update], -1)` (reference layer.py:387): two (N, B, 2d) buffers whose
     left halves hold the layer input and whose right halves receive `update + boundary` straight from the operator; the
     Linear reads a buffer as is, and the fused epilogue writes the next layer's input into the other buffer's left half.
-    Same arithmetic as `_run_layers`; returns the final buffer (left half = hidden state, right half free)."""
-    num_node, batch, width = boundary.shape
-    buffers = [torch.empty(num_node, batch, 2 * width, dtype=boundary.dtype, device=boundary.device) for _ in range(2)]
-    buffers[0][..., :width] = boundary
-    flat_boundary = boundary.flatten(1)
+    Same arithmetic as `_run_layers`; returns the final buffer (left half = hidden state, right half free).
+
+    `one_hot = (index, query)` states the boundary condition of reference model.py:106-109 in its sparse form (query[b] at
+    node index[b] of column b, zero elsewhere): `boundary` is then never materialised, and `+ boundary` is B row updates
+    per layer instead of a pass over an (N, B, d) tensor."""
+    probe = boundary if one_hot is None else one_hot[1]
+    num_node, batch, width = graph.num_node, probe.shape[-2], probe.shape[-1]
+    buffers = [torch.empty(num_node, batch, 2 * width, dtype=probe.dtype, device=probe.device) for _ in range(2)]
+    if one_hot is None:
+        buffers[0][..., :width] = boundary
+        addend = boundary.flatten(1)
+    else:
+        node, query = one_hot
+        column = torch.arange(batch, device=probe.device)
+        buffers[0][..., :width].zero_()
+        buffers[0][node, column, :width] = query
+        addend = None
     index = rspmm.graph_index(graph.adjacency.transpose(0, 1))
     for number, layer in enumerate(layers):
         current, following = buffers[number % 2], buffers[(number + 1) % 2]
         relation_input = layer.relation_input(graph, batch).contiguous()
         index.forward_blocked(relation_input, current, current, width, 0, width, MESSAGE_TO_MUL[layer.message_func],
-                              addend=flat_boundary)
+                              addend=addend)
+        if one_hot is not None:
+            current[node, column, width:] += query
         projected = F.linear(current.view(num_node * batch, 2 * width), layer.linear.weight)
         rspmm.layer_norm_relu_residual_into(
             projected.view(num_node, batch, width), following[..., :width], layer.layer_norm.weight, layer.layer_norm.bias,
@@ -280,17 +294,18 @@ class TransferNBFNet(nn.Module):
     def bellmanford(self, graph, h_index, r_index):
         batch = torch.arange(h_index.shape[0], device=h_index.device)
         query = self.query[r_index] if self.query.dim() == 2 else self.query[batch, r_index]
-        boundary = _one_hot_boundary(graph.num_node, h_index, query)
         with graph.graph():
             graph.query = query
-        with graph.node():
-            graph.boundary = boundary
-        if _buffered_layers_supported(self.layers, boundary):
-            feature = _run_layers_buffered(self.layers, graph, boundary, self.short_cut)   # (N, B, 2d): hidden | free
+        if _buffered_layers_supported(self.layers, query):
+            # (N, B, 2d): hidden | free; the one-hot boundary (model.py:106-109) is applied in its sparse form
+            feature = _run_layers_buffered(self.layers, graph, None, self.short_cut, one_hot=(h_index, query))
             if self._split_head_supported(feature):
                 return feature, query                                                      # head reads the halves apart
-            feature[..., boundary.shape[-1]:] = query                                      # cat([hidden, query]) in place
+            feature[..., query.shape[-1]:] = query                                         # cat([hidden, query]) in place
             return feature
+        boundary = _one_hot_boundary(graph.num_node, h_index, query)
+        with graph.node():
+            graph.boundary = boundary
         hidden = _run_layers(self.layers, graph, boundary, self.short_cut)
         return torch.cat([hidden, query.expand(graph.num_node, -1, -1)], dim=-1)
 
@@ -342,9 +357,12 @@ class CustomNBFNetFull(nn.Module):
 
     def forward(self, graph, h_index):
         query = torch.ones(h_index.shape[0], self.dims[0], device=h_index.device, dtype=torch.float)
-        boundary = _one_hot_boundary(graph.num_node, h_index, query)
         with graph.graph():
             graph.query = query
+        if _buffered_layers_supported(self.layers, query):
+            hidden = _run_layers_buffered(self.layers, graph, None, self.short_cut, one_hot=(h_index, query))
+            return hidden[..., :query.shape[-1]].transpose(1, 0)
+        boundary = _one_hot_boundary(graph.num_node, h_index, query)
         with graph.node():
             graph.boundary = boundary
         return _run_layers(self.layers, graph, boundary, self.short_cut).transpose(1, 0)   # (B, num_rel, dim)
