@@ -38,28 +38,31 @@ template <typename T, int SUM> __device__ __forceinline__ T reduce_identity() {
 
 // ---------------------------------------------------------------------------------------------
 // 128-bit (or scalar) global loads with explicit cache policy.
-//   gather_*: rows of the big gathered operand (input / grad_output / output): read-only path,
-//             no L1 allocation - they are reused through L2 (slab-major order), not through L1;
-//   table_* : rows of the small relation table: read-only path WITH L1 allocation, so the
-//             R' x SLAB block that the CTAs of one SM share stays on chip.
+//   gather_*     : rows of the gathered operand (input / grad_output / output) when its column slab is small or
+//                  mid-sized: read-only path with L1 allocation.  Reuse is mainly through L2 (slab-major order), but on
+//                  graphs with few nodes (the relation graph: 474 rows x 512 B = 243 KB per slab) a large share of the
+//                  gathers hits L1 and L2->SM bandwidth stops being the bound (profiles/README.md: -10..16 %);
+//   gather_*_keep: the same rows when the slab approaches the L2 capacity: no L1 allocation, evict_last in L2;
+//   table_*      : rows of the small relation table: read-only path with L1 allocation, so the R' x SLAB block that
+//                  the CTAs of one SM share stays on chip.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int VEC> struct Vec { T v[VEC]; };
 
 __device__ __forceinline__ void gather_load(const float *p, Vec<float, 4> &out) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(out.v[0]), "=f"(out.v[1]), "=f"(out.v[2]), "=f"(out.v[3]) : "l"(p));
 }
 __device__ __forceinline__ void gather_load(const float *p, Vec<float, 2> &out) {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(out.v[0]), "=f"(out.v[1]) : "l"(p));
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(out.v[0]), "=f"(out.v[1]) : "l"(p));
 }
 __device__ __forceinline__ void gather_load(const float *p, Vec<float, 1> &out) {
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(out.v[0]) : "l"(p));
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(out.v[0]) : "l"(p));
 }
 __device__ __forceinline__ void gather_load(const double *p, Vec<double, 2> &out) {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(out.v[0]), "=d"(out.v[1]) : "l"(p));
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(out.v[0]), "=d"(out.v[1]) : "l"(p));
 }
 __device__ __forceinline__ void gather_load(const double *p, Vec<double, 1> &out) {
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(out.v[0]) : "l"(p));
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(out.v[0]) : "l"(p));
 }
 
 // L2 eviction-priority policies (createpolicy): the gathered slab is marked evict_last, the streams that pass
