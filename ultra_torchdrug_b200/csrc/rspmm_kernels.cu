@@ -51,7 +51,10 @@ template <typename T> struct SegArgs {
     // blocked layout (block == 0: A and out are plain (rows, dim) matrices).  Otherwise a row of A / out is dim / block
     // blocks of `block` features, consecutive blocks a_stride / o_stride elements apart, out shifted by o_offset:
     // the (N, B, 2d) buffer whose halves are the layer input and the layer update (reference layer.py:387 `cat`)
-    long long block, a_stride, o_stride, o_offset;
+    // block_shift = log2(block) when block is a power of two, else -1; a_row / o_row = row strides in elements (= dim for
+    // plain matrices), precomputed on the host so that the kernel does no 64-bit division.
+    long long a_stride, o_stride, o_offset, a_row, o_row;
+    int block, block_shift;
 };
 
 template <typename T, int SUM> __device__ __forceinline__ void reduce_into(T &acc, T m) {
@@ -70,6 +73,14 @@ __device__ __forceinline__ unsigned id_bits(const int2 &) { return 0; }
 // row address = base + row * row_bytes as one IMAD.WIDE.U32 (row ids are int32 >= 0, row_bytes < 2^32)
 template <typename T> __device__ __forceinline__ const T *row_ptr(const char *base, int row, unsigned row_bytes) {
     return reinterpret_cast<const T *>(base + (unsigned long long)(unsigned)row * row_bytes);
+}
+
+// Column c of a logical (rows, dim) matrix stored in blocks: (c / block) * stride + c % block, in 32-bit arithmetic
+// (c < 2^30: launch_seg checks dim * sizeof(T) < 2^32) and with a shift when the block is a power of two.
+__device__ __forceinline__ long long blocked_col(long long col, int block, int shift, long long stride) {
+    const unsigned c = (unsigned)col;
+    const unsigned q = shift >= 0 ? c >> shift : c / (unsigned)block;
+    return (long long)q * stride + (c - q * (unsigned)block);
 }
 
 // The issue-slot and L1-data-pipe budgets of the inner loop are what bound these kernels once the gathers are L2
@@ -101,8 +112,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
     const long long safe_col = active ? col : 0;   // idle lanes (dim % (32 * VEC) != 0) read column 0, store nothing
     const unsigned row_bytes = (unsigned)(a.dim * sizeof(T));
     // blocked operands: column c of the logical (rows, dim) matrix lives at (c / block) * stride + c % block
-    const long long a_col = a.block ? (safe_col / a.block) * a.a_stride + safe_col % a.block : safe_col;
-    const unsigned a_row_bytes = a.block ? (unsigned)((a.dim / a.block) * a.a_stride * sizeof(T)) : row_bytes;
+    const long long a_col = a.block ? blocked_col(safe_col, a.block, a.block_shift, a.a_stride) : safe_col;
+    const unsigned a_row_bytes = (unsigned)(a.a_row * sizeof(T));
     const char *A = reinterpret_cast<const char *>(a.A + a_col);
     const char *B = reinterpret_cast<const char *>(a.B + safe_col);
     const Ids *ids = reinterpret_cast<const Ids *>(PACKED ? (const void *)a.packed : (const void *)a.edge);
@@ -140,9 +151,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) seg_reduce_kernel(const S
                     for (int v = 0; v < VEC; ++v) r.v[v] += b.v[v];
                 }
                 // (the blocked output position is recomputed here rather than kept live across the edge loop)
-                const long long o_col = a.block ? (col / a.block) * a.o_stride + a.o_offset + col % a.block : col;
-                const long long o_row = a.block ? (a.dim / a.block) * a.o_stride : a.dim;
-                stream_store(a.out + row * o_row + o_col, r);
+                const long long o_col = a.block ? blocked_col(col, a.block, a.block_shift, a.o_stride) + a.o_offset : col;
+                stream_store(a.out + row * a.o_row + o_col, r);
             } else {
                 T *p = a.partial + (long long)slot * a.dim + col;   // re-read soon by the combine pass: default policy
 #pragma unroll
@@ -534,7 +544,7 @@ template <typename T, int SUM, bool ARG>
 __global__ void combine_kernel(const int4 *__restrict__ split, int n_split, const T *__restrict__ partial,
                                const int32_t *__restrict__ partial_arg, const T *__restrict__ addend,
                                T *__restrict__ out, int32_t *__restrict__ arg_out, long long dim, long long block,
-                               long long o_stride, long long o_offset) {
+                               int block_shift, long long o_stride, long long o_offset, long long o_row) {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= dim) return;
     const int4 s = __ldg(split + blockIdx.y);
@@ -551,7 +561,7 @@ __global__ void combine_kernel(const int4 *__restrict__ split, int n_split, cons
         reduce_into<T, SUM>(acc, m);
     }
     if (addend) acc += addend[(long long)s.x * dim + col];
-    if (block) out[(long long)s.x * (dim / block) * o_stride + (col / block) * o_stride + o_offset + col % block] = acc;
+    if (block) out[(long long)s.x * o_row + blocked_col(col, (int)block, block_shift, o_stride) + o_offset] = acc;
     else out[(long long)s.x * dim + col] = acc;
     if (ARG) arg_out[(long long)s.x * dim + col] = arg;
 }
@@ -586,10 +596,18 @@ int launch_seg(const SegArgs<T> &args, cudaStream_t stream) {
     return ULTRA_RSPMM_OK;
 }
 
+struct BlockedLayout {
+    long long block = 0, a_stride = 0, o_stride = 0, o_offset = 0;
+    int shift() const { return block > 0 && (block & (block - 1)) == 0 ? __builtin_ctzll((unsigned long long)block) : -1; }
+};
+
 template <typename T, int SUM, bool ARG>
 int launch_combine(const ultra_rspmm_order_t &order, const T *partial, const int32_t *partial_arg, T *out,
-                   int32_t *arg_out, long long dim, cudaStream_t stream, const T *addend = nullptr, long long block = 0,
-                   long long o_stride = 0, long long o_offset = 0) {
+                   int32_t *arg_out, long long dim, cudaStream_t stream, const T *addend = nullptr,
+                   const BlockedLayout &layout = BlockedLayout()) {
+    const long long block = layout.block, o_stride = layout.o_stride, o_offset = layout.o_offset;
+    const long long o_row = layout.block ? (dim / layout.block) * layout.o_stride : dim;
+    const int block_shift = layout.shift();
     if (order.n_split == 0 || dim == 0) return ULTRA_RSPMM_OK;
     const dim3 grid((unsigned)((dim + 255) / 256), (unsigned)order.n_split);
     if (order.n_split > 65535) {
@@ -598,13 +616,14 @@ int launch_combine(const ultra_rspmm_order_t &order, const T *partial, const int
             const int n = order.n_split - at < 65535 ? order.n_split - at : 65535;
             combine_kernel<T, SUM, ARG><<<dim3(grid.x, n), 256, 0, stream>>>((const int4 *)order.split + at, n, partial,
                                                                               partial_arg, addend, out, arg_out, dim, block,
-                                                                              o_stride, o_offset);
+                                                                              block_shift, o_stride, o_offset, o_row);
             note_launch();
         }
         return ULTRA_RSPMM_OK;
     }
     combine_kernel<T, SUM, ARG><<<grid, 256, 0, stream>>>((const int4 *)order.split, order.n_split, partial, partial_arg,
-                                                          addend, out, arg_out, dim, block, o_stride, o_offset);
+                                                          addend, out, arg_out, dim, block, block_shift, o_stride,
+                                                          o_offset, o_row);
     note_launch();
     return ULTRA_RSPMM_OK;
 }
@@ -626,10 +645,6 @@ int pick_vec(long long dim, long long rows, std::initializer_list<const void *> 
     if (rows * 32 * vec * (long long)sizeof(T) > g_l2_budget) vec = widest;   // nothing fits: HBM-bound, widest rows are best
     return vec;
 }
-
-struct BlockedLayout {
-    long long block = 0, a_stride = 0, o_stride = 0, o_offset = 0;
-};
 
 // one reduction pass + its combine
 template <typename T, int SUM, int MSG, bool B_TABLE, bool ARG>
@@ -653,7 +668,10 @@ int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, con
     args.partial_arg = ARG ? (int32_t *)((char *)workspace + align_up((size_t)order.n_slot * dim * sizeof(T))) : nullptr;
     args.dim = dim;
     args.n_task = order.n_task;
-    args.block = layout.block;
+    args.block = (int)layout.block;
+    args.block_shift = layout.shift();
+    args.a_row = layout.block ? (dim / layout.block) * layout.a_stride : dim;
+    args.o_row = layout.block ? (dim / layout.block) * layout.o_stride : dim;
     args.a_stride = layout.a_stride;
     args.o_stride = layout.o_stride;
     args.o_offset = layout.o_offset;
@@ -674,7 +692,7 @@ int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, con
     else status = launch_seg<T, 1, SUM, MSG, B_TABLE, ARG>(args, stream);
     if (status) return status;
     return launch_combine<T, SUM, ARG>(order, args.partial, args.partial_arg, out, arg_out, dim, stream, addend,
-                                       layout.block, layout.o_stride, layout.o_offset);
+                                       layout);
 }
 
 template <typename T, int VEC, int MSG, bool P_TABLE>
