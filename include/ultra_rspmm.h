@@ -219,6 +219,16 @@ int ultra_layer_norm_relu_residual_backward(const float *dev_x, const float *dev
                                             int64_t rows, int32_t dim, float eps, int32_t relu, void *workspace,
                                             size_t workspace_bytes, void *stream);
 
+/* Fused Linear + epilogue of the layer (inference): out[r, 0:out_dim] = relu(layer_norm(input[r, 0:2*out_dim] @ W^T +
+ * linear_bias) * gamma + beta) + (shortcut ? input[r, 0:out_dim] : 0) for `rows` rows; a row of input is
+ * [layer input | update + boundary] (row stride input_stride >= 2 * out_dim, % 4 == 0), W is (out_dim, 2 * out_dim)
+ * row-major, out rows are out_stride apart.  out_dim in {32, 64}.  fp32 accuracy on the tensor cores (3xTF32 split with
+ * fp32 accumulation, see csrc/layer_linear.cu); replaces F.linear + ultra_layer_norm_relu_residual_strided. */
+int ultra_layer_linear_norm_relu_residual(const float *dev_input, int64_t input_stride, const float *dev_weight,
+                                          const float *dev_linear_bias, const float *dev_gamma, const float *dev_beta,
+                                          float *dev_out, int64_t out_stride, int64_t rows, int32_t out_dim, float eps,
+                                          int32_t relu, int32_t shortcut, void *stream);
+
 /* ---- scoring head (reference model.py:177-193, the 2-layer MLP over [hidden | query]) ---- */
 /* score[r] = bias[0] + sum_c weight[c] * relu(z[r, c] + query_bias[r % batch, c]) over `rows` rows of `dim` fp32 features
  * (dim in {4, 8, ..., 128}).  z = hidden @ W1[:, :d]^T (a cuBLAS GEMM that stays in PyTorch), query_bias (batch, dim) =

@@ -393,6 +393,52 @@ def test_layer_epilogue_strided_equals_contiguous(cuda):
         F.layer_norm_relu_residual_into(x, following[..., ::2])
 
 
+@pytest.mark.parametrize("dim,rows", [(64, 1000), (64, 128 * 150 + 37), (32, 777), (64, 5)])
+def test_fused_linear_epilogue_has_fp32_accuracy(cuda, dim, rows):
+    """Fused Linear + LayerNorm + ReLU + short-cut (3xTF32 split on the tensor cores) vs a float64 evaluation of
+    reference layer.py:386-392 + model.py:126-127: its error must be at the level of the fp32 cuBLAS path, far below
+    what a plain TF32 product gives."""
+    from ultra_torchdrug_b200 import functional as F
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(rows)
+    buffer = torch.randn(rows, 1, 2 * dim, device=cuda) * 2 + 0.3
+    linear = torch.nn.Linear(2 * dim, dim).to(cuda)
+    norm = torch.nn.LayerNorm(dim).to(cuda)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+        norm.bias.normal_()
+
+        def evaluate(dtype, tf32=False):
+            x = buffer.to(dtype)
+            if tf32:                                     # what the reference switches off: 10-bit mantissa operands
+                x = (x.view(torch.int32) & ~0x1fff).view(torch.float32)
+                w = (linear.weight.view(torch.int32) & ~0x1fff).view(torch.float32)
+            else:
+                w = linear.weight.to(dtype)
+            hidden = torch.nn.functional.linear(x, w, linear.bias.to(dtype))
+            hidden = torch.nn.functional.layer_norm(hidden, (dim,), norm.weight.to(dtype), norm.bias.to(dtype), norm.eps)
+            return torch.relu(hidden) + buffer.to(dtype)[..., :dim]
+
+        exact = evaluate(torch.float64)
+        cublas_error = float((evaluate(torch.float32).double() - exact).abs().max())
+        tf32_error = float((evaluate(torch.float32, tf32=True).double() - exact).abs().max())
+        following = torch.full((rows, 1, 2 * dim), 3.0, device=cuda)
+        F.linear_norm_relu_residual_into(buffer, linear.weight, following[..., :dim], linear.bias, norm.weight, norm.bias,
+                                         norm.eps, relu=True, shortcut=True)
+        fused_error = float((following[..., :dim].double() - exact).abs().max())
+        assert fused_error <= 4 * cublas_error + 1e-6, (fused_error, cublas_error)
+        assert fused_error < tf32_error / 50, (fused_error, tf32_error)
+        assert bool((following[..., dim:] == 3.0).all()), "columns outside the output half were written"
+        torch.testing.assert_close(following[..., :dim], evaluate(torch.float32), rtol=1e-5, atol=1e-5)
+        # no affine, no ReLU, no short-cut, contiguous output
+        plain = torch.empty(rows, 1, dim, device=cuda)
+        F.linear_norm_relu_residual_into(buffer, linear.weight, plain, None, None, None, norm.eps, relu=False, shortcut=False)
+        want = torch.nn.functional.layer_norm(torch.nn.functional.linear(buffer, linear.weight), (dim,), None, None, norm.eps)
+        torch.testing.assert_close(plain, want, rtol=1e-5, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        F.linear_norm_relu_residual_into(buffer[..., :-4], linear.weight, plain)
+
+
 @pytest.mark.parametrize("dim", [4, 32, 128])
 def test_score_head_matches_torch(cuda, dim):
     """Fused `relu(z + query_bias) . w + b` vs the separate PyTorch ops of the scoring MLP (model.py:177-193)."""

@@ -76,6 +76,9 @@ SYMBOLS = {
     "ultra_layer_norm_relu_residual_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                                c_void_p, c_void_p, c_void_p, c_int64, c_int32, ctypes.c_float,
                                                                c_int32, c_void_p, c_size_t, c_void_p]),
+    "ultra_layer_linear_norm_relu_residual": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                             c_int64, c_int64, c_int32, ctypes.c_float, c_int32, c_int32,
+                                                             c_void_p]),
     "ultra_score_head": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
 }
 

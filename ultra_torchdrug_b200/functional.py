@@ -20,7 +20,8 @@ from . import _lib
 
 __all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
            "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "rspmm_pna", "LayerEpilogueFunction",
-           "layer_norm_relu_residual_into", "score_head"]
+           "layer_norm_relu_residual_into", "score_head", "fused_linear_supported",
+           "linear_norm_relu_residual_into"]
 
 _SUM_OPS = ("add", "min", "max")
 _MUL_OPS = ("mul", "add")
@@ -262,6 +263,36 @@ def layer_norm_relu_residual_into(x, out, weight=None, bias=None, residual=None,
             ctypes.c_void_p(residual.data_ptr()) if residual is not None else ctypes.c_void_p(0),
             ctypes.c_void_p(out.data_ptr()), rows, dim, residual.stride(-2) if residual is not None else dim,
             out.stride(-2), float(eps), int(bool(relu)), _stream_handle()), "ultra_layer_norm_relu_residual_strided")
+    return out
+
+
+def fused_linear_supported(buffer, out_dim):
+    """Whether `linear_norm_relu_residual_into` serves a layer of this width (float32 CUDA, 32 or 64 output features;
+    ULTRA_FUSED_LINEAR=0 keeps the cuBLAS Linear + separate epilogue)."""
+    return (buffer.is_cuda and buffer.dtype == torch.float32 and out_dim in (32, 64)
+            and os.environ.get("ULTRA_FUSED_LINEAR", "1") != "0")
+
+
+def linear_norm_relu_residual_into(buffer, linear_weight, out, linear_bias=None, weight=None, bias=None, eps=1e-5, relu=True,
+                                   shortcut=True):
+    """`out = relu(layer_norm(buffer @ linear_weight^T + linear_bias) * weight + bias) + buffer[..., :d]` in one kernel
+    (inference): `buffer` is the contiguous (..., 2d) layer buffer [input | update + boundary], `out` a (..., d) view with
+    unit feature stride and evenly spaced rows.  3xTF32 split on the tensor cores = fp32 accuracy (csrc/layer_linear.cu)."""
+    out_dim = linear_weight.shape[0]
+    rows = buffer.numel() // max(buffer.shape[-1], 1)
+    if not fused_linear_supported(buffer, out_dim) or not buffer.is_contiguous() or buffer.shape[-1] != 2 * out_dim \
+            or linear_weight.shape != (out_dim, 2 * out_dim):
+        raise RuntimeError("linear_norm_relu_residual_into needs a contiguous float32 CUDA (..., 2d) buffer, d in {32, 64}")
+    uniform = out.dim() >= 2 and all(out.stride(axis) == out.stride(axis + 1) * out.shape[axis + 1]
+                                     for axis in range(out.dim() - 2))
+    if out.shape != buffer.shape[:-1] + (out_dim,) or out.dtype != torch.float32 or out.device != buffer.device \
+            or out.stride(-1) != 1 or not uniform or out.stride(-2) < out_dim:
+        raise RuntimeError("`out` must be a float32 (..., %d) view whose rows are evenly spaced" % out_dim)
+    with torch.cuda.device(buffer.device):
+        _lib.check(_lib.lib().ultra_layer_linear_norm_relu_residual(
+            _ptr(buffer), buffer.shape[-1], _ptr(linear_weight.contiguous()), _ptr(linear_bias), _ptr(weight), _ptr(bias),
+            ctypes.c_void_p(out.data_ptr()), out.stride(-2), rows, out_dim, float(eps), int(bool(relu)),
+            int(bool(shortcut)), _stream_handle()), "ultra_layer_linear_norm_relu_residual")
     return out
 
 

@@ -207,6 +207,11 @@ def _run_layers_buffered(layers, graph, boundary, short_cut, one_hot=None):
                               addend=addend)
         if one_hot is not None:
             current[node, column, width:] += query
+        if rspmm.fused_linear_supported(current, width):
+            rspmm.linear_norm_relu_residual_into(
+                current, layer.linear.weight, following[..., :width], layer.linear.bias, layer.layer_norm.weight,
+                layer.layer_norm.bias, layer.layer_norm.eps, relu=layer.activation is not None, shortcut=short_cut)
+            continue
         projected = F.linear(current.view(num_node * batch, 2 * width), layer.linear.weight)
         rspmm.layer_norm_relu_residual_into(
             projected.view(num_node, batch, width), following[..., :width], layer.layer_norm.weight, layer.layer_norm.bias,
