@@ -1,0 +1,68 @@
+"""Development microbenchmark of the fused layer `combine` (csrc/layer_linear.cu) against its unfused form
+(cuBLAS fp32 Linear + fused LayerNorm/ReLU/short-cut epilogue) at a named graph shape.
+
+    python tools/linear_bench.py [--graph fb15k237] [--batch 64] [--dim 64]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from ultra_torchdrug_b200 import functional as F, synthetic  # noqa: E402
+
+
+def timed(fn, iters=20, warmup=3):
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(iters):
+        fn(i)
+    stop.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(stop) / iters
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--graph", default="fb15k237")
+    parser.add_argument("--batch", type=int, default=64)
+    parser.add_argument("--dim", type=int, default=64)
+    parser.add_argument("--iters", type=int, default=20)
+    args = parser.parse_args()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    device = torch.device("cuda", 0)
+    num_node = synthetic.SHAPES[args.graph][0]
+    dim = args.dim
+    rows = num_node * args.batch
+    buffers = [torch.randn(num_node, args.batch, 2 * dim, device=device) for _ in range(2)]   # 2 x 476 MB at C2: > L2
+    linear = torch.nn.Linear(2 * dim, dim).to(device)
+    norm = torch.nn.LayerNorm(dim).to(device)
+
+    def fused(i):
+        source, target = buffers[i % 2], buffers[(i + 1) % 2]
+        F.linear_norm_relu_residual_into(source, linear.weight, target[..., :dim], linear.bias, norm.weight, norm.bias,
+                                         norm.eps, relu=True, shortcut=True)
+
+    def unfused(i):
+        source, target = buffers[i % 2], buffers[(i + 1) % 2]
+        projected = torch.nn.functional.linear(source.view(rows, 2 * dim), linear.weight)
+        F.layer_norm_relu_residual_into(projected.view(num_node, args.batch, dim), target[..., :dim], norm.weight, norm.bias,
+                                        source[..., :dim], norm.eps, True, linear.bias)
+
+    with torch.no_grad():
+        t_fused, t_unfused = timed(fused, args.iters), timed(unfused, args.iters)
+    moved = rows * (2 * dim + dim) * 4 / 1e9
+    flops = 2.0 * rows * 2 * dim * dim
+    print("rows %d  K %d  N %d" % (rows, 2 * dim, dim))
+    print("fused    %.3f ms   %.0f GB/s of compulsory bytes (%.2f GB)   %.1f TFLOP/s fp32-equivalent"
+          % (t_fused, moved / t_fused * 1e3, moved, flops / t_fused / 1e9))
+    print("unfused  %.3f ms   (cuBLAS fp32 Linear + fused epilogue)" % t_unfused)
+
+
+if __name__ == "__main__":
+    main()

@@ -14,18 +14,20 @@
 // reference switches off (script/run_full.py:19-20: a single 10-bit-mantissa product); tests/test_rspmm_gpu.py bounds the
 // error against a float64 Linear at the level of cuBLAS's fp32 SGEMM.  ULTRA_FUSED_LINEAR=0 keeps the cuBLAS path.
 //
-// Shape: persistent CTAs (one per SM, 8 warps), tile = 128 rows.  W is split once per CTA into shared memory in
-// mma-fragment order; row tiles are staged with cp.async (16 B per thread, zero-filled past the last row) into two
-// buffers, so the next tile's load overlaps this tile's MMAs and epilogue.  Warp w owns rows [16w, 16w+16) of the tile and
-// all N columns: N/8 accumulator tiles of m16n8k8.  The LayerNorm statistics of a row live in the 4 lanes that share it.
+// Shape: persistent CTAs (one per SM, 16 warps).  W is split once per CTA into shared memory in mma-fragment order.  Each
+// warp then runs its own pipeline over 16-row tiles - cp.async its rows into its own 8 KB of shared memory (zero-filled
+// past the last row), 3 x N/8 x K/8 MMAs (m16n8k8, all N columns), LayerNorm epilogue in registers (a row's statistics
+// live in the 4 lanes that share it) - with no block-wide barrier, so the loads and epilogues of some warps overlap the
+// MMAs of the others (the first version, 128-row tiles behind __syncthreads, left the tensor pipe 53 % idle).
 #include "rspmm_common.cuh"
 
 namespace ultra {
 
 namespace {
 
-constexpr int kTileRows = 128;
-constexpr int kLinearThreads = 256;
+constexpr int kWarpRows = 16;                          // rows per warp tile (one m16 MMA row block)
+constexpr int kLinearWarps = 16;
+constexpr int kLinearThreads = 32 * kLinearWarps;
 
 template <int N> struct LinearShape {
     static constexpr int K = 2 * N;
@@ -33,8 +35,8 @@ template <int N> struct LinearShape {
     static constexpr int kSteps = K / 8;
     static constexpr int kNTiles = N / 8;
     static constexpr size_t kWeightBytes = (size_t)kSteps * kNTiles * 32 * sizeof(float4);
-    static constexpr size_t kTileBytes = (size_t)kTileRows * kPad * sizeof(float);
-    static constexpr size_t kSmemBytes = kWeightBytes + 2 * kTileBytes;
+    static constexpr size_t kTileBytes = (size_t)kWarpRows * kPad * sizeof(float);
+    static constexpr size_t kSmemBytes = kWeightBytes + kLinearWarps * kTileBytes;
 };
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -47,10 +49,7 @@ __device__ __forceinline__ void cp_async_16(void *smem, const void *global, unsi
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(global), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int PENDING> __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
-}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // D(16x8, fp32) += A(16x8, tf32, row) * B(8x8, tf32, col).  Lane l: g = l / 4, t = l % 4.
 //   a0 = A[g][t], a1 = A[g+8][t], a2 = A[g][t+4], a3 = A[g+8][t+4];  b0 = B[t][g], b1 = B[t+4][g];
@@ -72,27 +71,10 @@ linear_norm_relu_residual_kernel(const float *__restrict__ A, long long lda, con
     constexpr int K = Shape::K, kPad = Shape::kPad, kSteps = Shape::kSteps, kNTiles = Shape::kNTiles;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *w_frag = reinterpret_cast<float4 *>(smem_raw);
-    float *tiles = reinterpret_cast<float *>(smem_raw + Shape::kWeightBytes);   // two staged row tiles
-    constexpr int kTileFloats = kTileRows * Shape::kPad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    const long long n_tiles = (rows + kTileRows - 1) / kTileRows;
+    float *mine = reinterpret_cast<float *>(smem_raw + Shape::kWeightBytes) + warp * (kWarpRows * kPad);   // this warp's rows
 
-    auto stage = [&](long long tile, float *dst) {
-        const long long row0 = tile * kTileRows;
-        constexpr int kChunks = K / 4;                 // 16-byte chunks per row
-        for (int c = tid; c < kTileRows * kChunks; c += kLinearThreads) {
-            const int r = c / kChunks, q = c % kChunks;
-            const long long row = row0 + r;
-            const bool live = row < rows;
-            cp_async_16(dst + r * kPad + 4 * q, A + (live ? row : 0) * lda + 4 * q, live ? 16u : 0u);
-        }
-        cp_async_commit();
-    };
-
-    long long tile = blockIdx.x;
-    if (tile < n_tiles) stage(tile, tiles);
-
-    // W (N, K) row-major -> fragment order [k-step][n-tile][lane] = (b0 hi, b1 hi, b0 lo, b1 lo)
+    // W (N, K) row-major -> fragment order [k-step][n-tile][lane] = (b0 hi, b1 hi, b0 lo, b1 lo), once per CTA
     for (int idx = tid; idx < kSteps * kNTiles * 32; idx += kLinearThreads) {
         const int l = idx & 31, j = (idx >> 5) % kNTiles, s = idx / (32 * kNTiles);
         const int n = 8 * j + (l >> 2), k = 8 * s + (l & 3);
@@ -100,23 +82,29 @@ linear_norm_relu_residual_kernel(const float *__restrict__ A, long long lda, con
         const float b0_hi = to_tf32(b0), b1_hi = to_tf32(b1);
         w_frag[idx] = make_float4(b0_hi, b1_hi, to_tf32(b0 - b0_hi), to_tf32(b1 - b1_hi));
     }
+    __syncthreads();                                   // the only block-wide barrier: from here on warps run on their own
 
+    // Every warp is its own pipeline over 16-row tiles (load -> 3 x N/8 x K/8 MMAs -> epilogue): the warps of an SM drift
+    // out of phase, so loads and epilogues of some overlap the MMAs of others without any block-wide synchronisation.
     constexpr float inv = 1.0f / N;
-    for (int buffer = 0; tile < n_tiles; tile += gridDim.x, buffer ^= 1) {
-        const float *current = tiles + buffer * kTileFloats;
-        const long long upcoming = tile + gridDim.x;
-        if (upcoming < n_tiles) {
-            stage(upcoming, tiles + (buffer ^ 1) * kTileFloats);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+    constexpr int kChunks = K / 4;                     // 16-byte chunks per row
+    const long long n_tiles = (rows + kWarpRows - 1) / kWarpRows;
+    const long long stride = (long long)gridDim.x * kLinearWarps;
+    for (long long tile = (long long)blockIdx.x * kLinearWarps + warp; tile < n_tiles; tile += stride) {
+        const long long row0 = tile * kWarpRows;
+#pragma unroll 4
+        for (int c = lane; c < kWarpRows * kChunks; c += 32) {
+            const int r = c / kChunks, q = c % kChunks;
+            const bool live = row0 + r < rows;
+            cp_async_16(mine + r * kPad + 4 * q, A + (live ? row0 + r : 0) * lda + 4 * q, live ? 16u : 0u);
         }
-        __syncthreads();                               // tile (and, first time round, the W fragments) visible to all
+        cp_async_wait_all();
+        __syncwarp();
 
         float acc[kNTiles][4];
 #pragma unroll
         for (int j = 0; j < kNTiles; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-        const float *row_upper = current + (16 * warp + g) * kPad + t;
+        const float *row_upper = mine + g * kPad + t;
         const float *row_lower = row_upper + 8 * kPad;
 #pragma unroll 2
         for (int s = 0; s < kSteps; ++s) {
@@ -139,7 +127,7 @@ linear_norm_relu_residual_kernel(const float *__restrict__ A, long long lda, con
             for (int j = 0; j < kNTiles; ++j) mma_tf32(acc[j], big, b[j].x, b[j].y);     // hi_a hi_b
         }
 
-        // epilogue: this thread holds columns {8j + 2t, 8j + 2t + 1} of tile rows 16w + g (acc[j][0..1]) and 16w + g + 8
+        // epilogue: this thread holds columns {8j + 2t, 8j + 2t + 1} of tile rows g (acc[j][0..1]) and g + 8
         // (acc[j][2..3]); the 4 lanes with the same g hold a full row between them
         float sum[2] = {0.f, 0.f};
 #pragma unroll
@@ -170,7 +158,6 @@ linear_norm_relu_residual_kernel(const float *__restrict__ A, long long lda, con
             sq[h] += __shfl_xor_sync(kFullMask, sq[h], 2);
         }
         const float rstd[2] = {rsqrtf(sq[0] * inv + eps), rsqrtf(sq[1] * inv + eps)};
-        const int local[2] = {16 * warp + g, 16 * warp + g + 8};
 #pragma unroll
         for (int j = 0; j < kNTiles; ++j) {
             const int col = 8 * j + 2 * t;
@@ -185,16 +172,15 @@ linear_norm_relu_residual_kernel(const float *__restrict__ A, long long lda, con
                                        fmaf(acc[j][2 * h + 1] * rstd[h], scale.y, shift.y));
                 if (relu) y = make_float2(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f));
                 if (shortcut) {
-                    const float2 skip = *reinterpret_cast<const float2 *>(current + local[h] * kPad + col);
+                    const float2 skip = *reinterpret_cast<const float2 *>(mine + (g + 8 * h) * kPad + col);
                     y.x += skip.x; y.y += skip.y;
                 }
-                const long long row = tile * kTileRows + local[h];
+                const long long row = row0 + g + 8 * h;
                 if (row < rows) *reinterpret_cast<float2 *>(out + row * ldo + col) = y;
             }
         }
-        __syncthreads();                               // everyone is done with `current` before it is staged into again
+        __syncwarp();                                  // all lanes are done with the staged rows before the next load
     }
-    cp_async_wait<0>();
 }
 
 template <int N>
@@ -214,8 +200,8 @@ int launch_linear(const float *A, long long lda, const float *W, const float *li
         ULTRA_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape::kSmemBytes));
         configured = true;
     }
-    const long long n_tiles = (rows + kTileRows - 1) / kTileRows;
-    const unsigned grid = (unsigned)(n_tiles < sm_count ? n_tiles : sm_count);
+    const long long n_blocks = (rows + kWarpRows * kLinearWarps - 1) / (kWarpRows * kLinearWarps);
+    const unsigned grid = (unsigned)(n_blocks < sm_count ? n_blocks : sm_count);
     kernel<<<grid, kLinearThreads, Shape::kSmemBytes, stream>>>(A, lda, W, linear_bias, gamma, beta, out, ldo, rows, eps,
                                                                  relu, shortcut);
     note_launch();
