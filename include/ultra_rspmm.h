@@ -229,6 +229,9 @@ int ultra_layer_linear_norm_relu_residual(const float *dev_input, int64_t input_
                                           float *dev_out, int64_t out_stride, int64_t rows, int32_t out_dim, float eps,
                                           int32_t relu, int32_t shortcut, void *stream);
 
+/* which implementation serves ultra_layer_linear_norm_relu_residual: 0 = library default, 1 = mma.sync, 2 = tcgen05 */
+int ultra_layer_linear_set_kernel(int32_t kind);
+
 /* ---- scoring head (reference model.py:177-193, the 2-layer MLP over [hidden | query]) ---- */
 /* score[r] = bias[0] + sum_c weight[c] * relu(z[r, c] + query_bias[r % batch, c]) over `rows` rows of `dim` fp32 features
  * (dim in {4, 8, ..., 128}).  z = hidden @ W1[:, :d]^T (a cuBLAS GEMM that stays in PyTorch), query_bias (batch, dim) =

@@ -393,8 +393,17 @@ def test_layer_epilogue_strided_equals_contiguous(cuda):
         F.layer_norm_relu_residual_into(x, following[..., ::2])
 
 
-@pytest.mark.parametrize("dim,rows", [(64, 1000), (64, 128 * 150 + 37), (32, 777), (64, 5)])
-def test_fused_linear_epilogue_has_fp32_accuracy(cuda, dim, rows):
+@pytest.fixture(params=["mma.sync", "tcgen05"])
+def linear_kernel(request):
+    from ultra_torchdrug_b200 import _lib
+    _lib.check(_lib.lib().ultra_layer_linear_set_kernel(1 if request.param == "mma.sync" else 2), "set_kernel")
+    yield request.param
+    _lib.lib().ultra_layer_linear_set_kernel(0)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("dim,rows", [(64, 1000), (64, 128 * 150 + 37), (32, 777), (64, 5), (64, 128 * 148 * 5)])
+def test_fused_linear_epilogue_has_fp32_accuracy(cuda, linear_kernel, dim, rows):
     """Fused Linear + LayerNorm + ReLU + short-cut (3xTF32 split on the tensor cores) vs a float64 evaluation of
     reference layer.py:386-392 + model.py:126-127: its error must be at the level of the fp32 cuBLAS path, far below
     what a plain TF32 product gives."""

@@ -33,8 +33,11 @@ def main():
     parser.add_argument("--batch", type=int, default=64)
     parser.add_argument("--dim", type=int, default=64)
     parser.add_argument("--iters", type=int, default=20)
+    parser.add_argument("--kernel", type=int, default=0, help="0 library default, 1 mma.sync, 2 tcgen05")
     args = parser.parse_args()
     torch.backends.cuda.matmul.allow_tf32 = False
+    from ultra_torchdrug_b200 import _lib
+    _lib.check(_lib.lib().ultra_layer_linear_set_kernel(args.kernel), "ultra_layer_linear_set_kernel")
     device = torch.device("cuda", 0)
     num_node = synthetic.SHAPES[args.graph][0]
     dim = args.dim

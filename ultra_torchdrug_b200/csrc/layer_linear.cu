@@ -25,6 +25,7 @@ namespace ultra {
 
 namespace {
 
+constexpr int kDefaultLinearKernel = 1;                // 1 = mma.sync (this file), 2 = tcgen05 (layer_linear_tc.cu)
 constexpr int kWarpRows = 16;                          // rows per warp tile (one m16 MMA row block)
 constexpr int kLinearWarps = 16;
 constexpr int kLinearThreads = 32 * kLinearWarps;
@@ -213,7 +214,21 @@ int launch_linear(const float *A, long long lda, const float *W, const float *li
 
 }  // namespace ultra
 
+namespace ultra {
+// layer_linear_tc.cu
+int layer_linear_tc(const float *A, long long lda, const float *W, const float *linear_bias, const float *gamma,
+                    const float *beta, float *out, long long ldo, long long rows, int out_dim, float eps, int relu,
+                    int shortcut, cudaStream_t stream);
+int g_linear_kernel = 0;   // 0 = default, 1 = mma.sync, 2 = tcgen05
+}  // namespace ultra
+
 using namespace ultra;
+
+extern "C" int ultra_layer_linear_set_kernel(int32_t kind) {
+    if (kind < 0 || kind > 2) return ULTRA_RSPMM_ERR_ARG;
+    g_linear_kernel = kind;
+    return ULTRA_RSPMM_OK;
+}
 
 extern "C" int ultra_layer_linear_norm_relu_residual(const float *dev_input, int64_t input_stride, const float *dev_weight,
                                                      const float *dev_linear_bias, const float *dev_gamma,
@@ -229,6 +244,12 @@ extern "C" int ultra_layer_linear_norm_relu_residual(const float *dev_input, int
         return ULTRA_RSPMM_ERR_ARG;
     if (rows == 0) return ULTRA_RSPMM_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    const bool wide_aligned = !(((uintptr_t)dev_out | (uintptr_t)dev_linear_bias | (uintptr_t)dev_gamma | (uintptr_t)dev_beta) & 15) &&
+                              out_stride % 4 == 0;
+    const int kind = g_linear_kernel ? g_linear_kernel : kDefaultLinearKernel;
+    if (kind == 2 && wide_aligned)
+        return layer_linear_tc(dev_input, input_stride, dev_weight, dev_linear_bias, dev_gamma, dev_beta, dev_out, out_stride,
+                               rows, out_dim, eps, relu, shortcut, s);
     if (out_dim == 64)
         return launch_linear<64>(dev_input, input_stride, dev_weight, dev_linear_bias, dev_gamma, dev_beta, dev_out,
                                  out_stride, rows, eps, relu, shortcut, s);
