@@ -7,13 +7,14 @@
 // Persistent CTAs, one per SM, warp-specialised (13 warps):
 //   warps 0-7   producers: read 128-row tiles of A from global memory (each warp instruction = 8 rows x 64 B), split every
 //               value into hi = tf32(x) and lo = tf32(x - hi), and store both in shared memory in the canonical K-major
-//               no-swizzle UMMA layout (8-row x 16-byte core matrices), a ring of 4 slots of 32 K-columns each;
+//               no-swizzle UMMA layout (8-row x 16-byte core matrices), a ring of 3 slots of 32 K-columns each;
 //   warp  8     one elected thread issues, per slot, 4 k-steps x 3 MMAs (lo_a hi_b, hi_a lo_b, hi_a hi_b; M = 128, N, K = 8)
 //               into one of two accumulator stages in TMEM and commits them to the slot's `empty` barrier;
-//   warps 9-12  epilogue: tcgen05.ld of their 32 TMEM lanes (one thread = one row, all N columns), LayerNorm in the thread,
-//               ReLU, short-cut (fp32 row re-read from global memory: an L2 hit), 16-byte stores.
-// Hand-offs are mbarriers: full[slot] (256 producer arrivals), empty[slot] (tcgen05.commit), tmem_full[stage]
-// (tcgen05.commit), tmem_empty[stage] (128 epilogue arrivals).  W is split into hi / lo once per CTA.
+//   warps 9-12  epilogue: tcgen05.ld of their 32 TMEM lanes (one thread = one row, all N columns), LayerNorm statistics in
+//               the thread, centred rows through warp-private shared memory, then coalesced: affine, ReLU, short-cut
+//               (fp32 row re-read from global memory: an L2 hit), 16-byte streaming stores.
+// Hand-offs are mbarriers: full[slot] (one arrival per producer warp), empty[slot] (tcgen05.commit), tmem_full[stage]
+// (tcgen05.commit), tmem_empty[stage] (one arrival per epilogue warp).  W is split into hi / lo once per CTA.
 #include "rspmm_common.cuh"
 
 namespace ultra {
@@ -23,9 +24,8 @@ namespace {
 namespace tc {
 constexpr int kRows = 128;                             // UMMA M
 constexpr int kSlotK = 32;                             // K columns per ring slot = 4 k-steps of 8
-constexpr int kSlots = 4;
+constexpr int kSlots = 3;
 constexpr int kProducerWarps = 8;
-constexpr int kProducers = 32 * kProducerWarps;
 constexpr int kMmaWarp = kProducerWarps;
 constexpr int kEpilogueWarps = 4;
 constexpr int kThreads = 32 * (kProducerWarps + 1 + kEpilogueWarps);
@@ -39,7 +39,9 @@ template <int N> struct Shape {
     static constexpr int kWeightHalfBytes = N * K * 4;
     static constexpr int kCoreBytesW = N * 16;          // LBO of the W operand
     static constexpr int kRingOffset = 2 * kWeightHalfBytes;
-    static constexpr int kBarrierOffset = kRingOffset + kSlots * 2 * kSlotHalfBytes;
+    static constexpr int kStageStride = N + 4;          // floats per staged output row (bank-conflict-free both ways)
+    static constexpr int kStagingOffset = kRingOffset + kSlots * 2 * kSlotHalfBytes;
+    static constexpr int kBarrierOffset = kStagingOffset + kEpilogueWarps * 32 * kStageStride * 4;
     static constexpr int kSmemBytes = kBarrierOffset + kBarriers * 8 + 16;
     static constexpr int kTmemColumns = 2 * N < 32 ? 32 : 2 * N;   // two accumulator stages; power of two >= 32
     // instruction descriptor: D = F32 (bits 4-5), A = B = TF32 (bits 7-9, 10-12), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
@@ -118,12 +120,12 @@ linear_norm_relu_residual_tc_kernel(const float *__restrict__ A, long long lda, 
     // ---- one-time setup: barriers, tensor memory, W split into hi / lo in UMMA layout ----------------------------------
     if (tid == 0) {
         for (int s = 0; s < tc::kSlots; ++s) {
-            mbar_init(full_bar(s), tc::kProducers);
+            mbar_init(full_bar(s), tc::kProducerWarps);
             mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tmem_full_bar(s), 1);
-            mbar_init(tmem_empty_bar(s), 32 * tc::kEpilogueWarps);
+            mbar_init(tmem_empty_bar(s), tc::kEpilogueWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -187,7 +189,8 @@ linear_norm_relu_residual_tc_kernel(const float *__restrict__ A, long long lda, 
                 *reinterpret_cast<float4 *>(at + tc::kSlotHalfBytes) = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(full_bar(slot));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(slot));                  // one arrival per warp: 8 per slot, not 256
         };
         float4 r0[4], r1[4], r2[4];                     // three slots of loads in flight per thread
         if (total > 0) issue(0, r0);
@@ -240,13 +243,24 @@ linear_norm_relu_residual_tc_kernel(const float *__restrict__ A, long long lda, 
         }
     } else {
         // ===== epilogue =================================================================================================
+        // Row phase: one thread = one row (what tcgen05.ld.32x32b hands out): bias, mean, rstd in the thread, centred row
+        // into this warp's private staging rows.  Write-back phase: the warp walks its 32 rows kRowsPerPass at a time with
+        // lane = (row, 16-byte chunk), so the short-cut loads and the result stores are coalesced (the first version stored
+        // straight from the row phase: 32 cache lines per instruction, L1 data pipe 87 % busy).
+        constexpr int kChunks = N / 4, kRowsPerPass = 32 / kChunks, kStride = S::kStageStride;
         const int quadrant = warp & 3;                                   // the TMEM lanes this warp may read
-        const int row_in_tile = 32 * quadrant + lane;
+        float *staged = reinterpret_cast<float *>(smem + S::kStagingOffset) + quadrant * 32 * kStride;
+        const int my_chunk = lane % kChunks, sub_row = lane / kChunks;
+        float4 scale = make_float4(1.f, 1.f, 1.f, 1.f), shift = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gamma) {
+            scale = __ldg(reinterpret_cast<const float4 *>(gamma + 4 * my_chunk));
+            shift = __ldg(reinterpret_cast<const float4 *>(beta + 4 * my_chunk));
+        }
         constexpr float inv = 1.0f / N;
         for (long long t = 0; t < my_tiles; ++t) {
             const int stage = (int)(t & 1);
             const unsigned accum_phase = (unsigned)((t >> 1) & 1);
-            const long long row = (first + t * gridDim.x) * tc::kRows + row_in_tile;
+            const long long row0 = (first + t * gridDim.x) * tc::kRows + 32 * quadrant;
             mbar_wait(tmem_full_bar(stage), accum_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float v[N];
@@ -259,7 +273,8 @@ linear_norm_relu_residual_tc_kernel(const float *__restrict__ A, long long lda, 
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(tmem_empty_bar(stage));                          // the MMAs of tile t + 2 may overwrite this stage
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(stage));           // the MMAs of tile t + 2 may overwrite this stage
             float sum = 0.f;
 #pragma unroll
             for (int c = 0; c < N; c += 4) {
@@ -277,25 +292,30 @@ linear_norm_relu_residual_tc_kernel(const float *__restrict__ A, long long lda, 
                 sq = fmaf(v[c], v[c], sq);
             }
             const float rstd = rsqrtf(sq * inv + eps);
-            if (row < rows) {
-                const float *skip = A + row * lda;
-                float *dst = out + row * ldo;
 #pragma unroll
-                for (int c = 0; c < N; c += 4) {
-                    float4 y = make_float4(v[c] * rstd, v[c + 1] * rstd, v[c + 2] * rstd, v[c + 3] * rstd);
-                    if (gamma) {
-                        const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + c));
-                        const float4 b = __ldg(reinterpret_cast<const float4 *>(beta + c));
-                        y = make_float4(fmaf(y.x, g.x, b.x), fmaf(y.y, g.y, b.y), fmaf(y.z, g.z, b.z), fmaf(y.w, g.w, b.w));
-                    }
-                    if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
-                    if (shortcut) {
-                        const float4 s = __ldg(reinterpret_cast<const float4 *>(skip + c));
-                        y = make_float4(y.x + s.x, y.y + s.y, y.z + s.z, y.w + s.w);
-                    }
-                    *reinterpret_cast<float4 *>(dst + c) = y;
-                }
+            for (int c = 0; c < N; c += 4)
+                *reinterpret_cast<float4 *>(staged + lane * kStride + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            __syncwarp();
+            constexpr int kPasses = 32 / kRowsPerPass;
+            float4 skip[kPasses];                                        // all short-cut loads in flight before the first use
+#pragma unroll
+            for (int pass = 0; pass < kPasses; ++pass) {
+                const long long row = row0 + pass * kRowsPerPass + sub_row;
+                skip[pass] = shortcut && row < rows ? __ldg(reinterpret_cast<const float4 *>(A + row * lda + 4 * my_chunk))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+#pragma unroll
+            for (int pass = 0; pass < kPasses; ++pass) {
+                const int r = pass * kRowsPerPass + sub_row;
+                const float rs = __shfl_sync(kFullMask, rstd, r);
+                const float4 x = *reinterpret_cast<const float4 *>(staged + r * kStride + 4 * my_chunk);
+                float4 y = make_float4(fmaf(x.x * rs, scale.x, shift.x), fmaf(x.y * rs, scale.y, shift.y),
+                                       fmaf(x.z * rs, scale.z, shift.z), fmaf(x.w * rs, scale.w, shift.w));
+                if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
+                y = make_float4(y.x + skip[pass].x, y.y + skip[pass].y, y.z + skip[pass].z, y.w + skip[pass].w);
+                if (row0 + r < rows) __stcs(reinterpret_cast<float4 *>(out + (row0 + r) * ldo + 4 * my_chunk), y);
+            }
+            __syncwarp();                                                // staging rows are rewritten by the next tile
         }
     }
 
