@@ -331,8 +331,19 @@ def test_forward_with_boundary_addend(cuda):
         assert F.graph_index(sparse).c.csr.n_split > 0
         with pytest.raises(RuntimeError):
             F.graph_index(sparse).forward(relation, input, "max", "mul", addend=boundary)
+        # under autograd: same values, gradients of the separate formulation (d boundary = upstream gradient)
+        upstream = torch.from_numpy(util.random_dense(90, 200, 4)).to(cuda)
+        for mul in ("mul", "add"):
+            fused = [t.clone().requires_grad_() for t in (relation, input, boundary)]
+            plain = [t.clone().requires_grad_() for t in (relation, input, boundary)]
+            out = F.rspmm_add_boundary(sparse, fused[0], fused[1], fused[2], mul)
+            want = F.generalized_rspmm(sparse, plain[0], plain[1], sum="add", mul=mul) + plain[2]
+            assert torch.equal(out, want)
+            out.backward(upstream)
+            want.backward(upstream)
+            assert all(torch.equal(a.grad, b.grad) for a, b in zip(fused, plain))
         with pytest.raises(RuntimeError):
-            F.rspmm_add_boundary(sparse, relation.requires_grad_(), input, boundary)
+            F.rspmm_add_boundary(sparse, relation, input, boundary[:, :-1])
     finally:
         lib.ultra_rspmm_set_tuning(256, 0, 0)
         F.clear_index_cache()

@@ -19,7 +19,7 @@ import torch
 from . import _lib
 
 __all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
-           "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "rspmm_pna", "LayerEpilogueFunction",
+           "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "RSPMMAddBoundaryFunction", "rspmm_pna", "LayerEpilogueFunction",
            "layer_norm_relu_residual_into", "score_head", "fused_linear_supported",
            "linear_norm_relu_residual_into"]
 
@@ -360,14 +360,40 @@ def graph_index(sparse):
     return index
 
 
+class RSPMMAddBoundaryFunction(torch.autograd.Function):
+    """`generalized_rspmm(sum="add") + boundary` with the addition in the kernel epilogue, differentiable: the gradient
+    w.r.t. `boundary` is the upstream gradient itself, the other two are the operator's (mul is a plain attribute)."""
+
+    @staticmethod
+    def forward(ctx, sparse, relation, input, boundary, mul):
+        index = graph_index(sparse)
+        relation, input = relation.contiguous(), input.contiguous()
+        ctx.index, ctx.mul = index, mul
+        ctx.save_for_backward(relation, input)
+        return index.forward(relation, input, "add", mul, addend=boundary.contiguous())
+
+    @staticmethod
+    def backward(ctx, output_grad):
+        relation, input = ctx.saved_tensors
+        relation_grad, input_grad = ctx.index.backward(
+            relation, input, None, output_grad.contiguous(), "add", ctx.mul,
+            need_relation=ctx.needs_input_grad[1], need_input=ctx.needs_input_grad[2])
+        return None, relation_grad, input_grad, output_grad if ctx.needs_input_grad[3] else None, None
+
+
 def rspmm_add_boundary(sparse, relation, input, boundary, mul="mul"):
     """`generalized_rspmm(sparse, relation, input, sum="add", mul=mul) + boundary` with the addition done in the
-    kernel epilogue (reference layer.py:155-156, 357-358).  Inference only (no autograd graph is recorded)."""
+    kernel epilogue (reference layer.py:155-156, 357-358): one pass fewer over an (N, D) tensor per layer, under
+    autograd as well."""
     _check_operands(sparse, relation, input)
     if mul not in _MUL_OPS:
         raise ValueError("Unknown multiplication `%s`" % mul)
+    if sparse.requires_grad:
+        raise RuntimeError("gradient w.r.t. the sparse values is outside the rspmm hot path")
+    if boundary.shape != (sparse.size(0), input.size(1)) or boundary.dtype != input.dtype or boundary.device != input.device:
+        raise RuntimeError("`boundary` must have the shape, dtype and device of the output")
     if torch.is_grad_enabled() and (relation.requires_grad or input.requires_grad or boundary.requires_grad):
-        raise RuntimeError("rspmm_add_boundary is an inference-only entry point")
+        return RSPMMAddBoundaryFunction.apply(sparse, relation, input, boundary, mul)
     index = graph_index(sparse)
     return index.forward(relation.contiguous(), input.contiguous(), "add", mul, addend=boundary.contiguous())
 

@@ -38,8 +38,7 @@ def _aggregate(adjacency, relation_input, input, boundary, degree_out, aggregate
     bounded = not aggregate_func.endswith("_nobound")
     name = aggregate_func[:-len("_nobound")] if not bounded else aggregate_func
     if name == "sum":
-        tensors = (relation_input, input, boundary)
-        if bounded and input.is_cuda and not (torch.is_grad_enabled() and any(t.requires_grad for t in tensors)):
+        if bounded and input.is_cuda and generalized_rspmm is rspmm.generalized_rspmm:
             return rspmm.rspmm_add_boundary(adjacency, relation_input, input, boundary, mul)   # one pass
         update = op("add")
         return update + boundary if bounded else update
