@@ -242,6 +242,15 @@ def layer_norm_relu_residual(x, weight=None, bias=None, residual=None, eps=1e-5,
     return _epilogue_forward(x.contiguous(), contiguous[0], contiguous[1], contiguous[2], contiguous[3], eps, relu)
 
 
+def _is_row_view(view, shape, device):
+    """True for a float32 view of `shape` whose rows (last axis, unit stride) are evenly spaced in memory - what the
+    strided kernels address as `base + row * view.stride(-2)`."""
+    if view.shape != tuple(shape) or view.dtype != torch.float32 or view.device != device or view.dim() < 2:
+        return False
+    evenly = all(view.stride(axis) == view.stride(axis + 1) * view.shape[axis + 1] for axis in range(view.dim() - 2))
+    return view.stride(-1) == 1 and evenly and view.stride(-2) >= view.shape[-1]
+
+
 def layer_norm_relu_residual_into(x, out, weight=None, bias=None, residual=None, eps=1e-5, relu=True, linear_bias=None):
     """Strided form of `layer_norm_relu_residual` (inference): `out` and `residual` are (..., dim) views whose rows are
     `stride(-2)` elements apart (e.g. the left halves of (N, B, 2 * dim) layer buffers); x is contiguous."""
@@ -250,12 +259,7 @@ def layer_norm_relu_residual_into(x, out, weight=None, bias=None, residual=None,
     if not layer_epilogue_supported(x, dim) or not x.is_contiguous():
         raise RuntimeError("layer_norm_relu_residual_into needs a contiguous float32 CUDA input with 4..128 features per row")
     for name, view in (("out", out), ("residual", residual)):
-        if view is None:
-            continue
-        uniform = view.dim() >= 2 and all(view.stride(axis) == view.stride(axis + 1) * view.shape[axis + 1]
-                                          for axis in range(view.dim() - 2))
-        if view.shape != x.shape or view.dtype != torch.float32 or view.device != x.device or view.stride(-1) != 1 \
-                or not uniform or view.stride(-2) < dim:
+        if view is not None and not _is_row_view(view, x.shape, x.device):
             raise RuntimeError("`%s` must be a float32 view of shape %s whose rows are evenly spaced" % (name, tuple(x.shape)))
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().ultra_layer_norm_relu_residual_strided(
@@ -283,10 +287,7 @@ def linear_norm_relu_residual_into(buffer, linear_weight, out, linear_bias=None,
     if not fused_linear_supported(buffer, out_dim) or not buffer.is_contiguous() or buffer.shape[-1] != 2 * out_dim \
             or linear_weight.shape != (out_dim, 2 * out_dim):
         raise RuntimeError("linear_norm_relu_residual_into needs a contiguous float32 CUDA (..., 2d) buffer, d in {32, 64}")
-    uniform = out.dim() >= 2 and all(out.stride(axis) == out.stride(axis + 1) * out.shape[axis + 1]
-                                     for axis in range(out.dim() - 2))
-    if out.shape != buffer.shape[:-1] + (out_dim,) or out.dtype != torch.float32 or out.device != buffer.device \
-            or out.stride(-1) != 1 or not uniform or out.stride(-2) < out_dim:
+    if not _is_row_view(out, buffer.shape[:-1] + (out_dim,), buffer.device):
         raise RuntimeError("`out` must be a float32 (..., %d) view whose rows are evenly spaced" % out_dim)
     with torch.cuda.device(buffer.device):
         _lib.check(_lib.lib().ultra_layer_linear_norm_relu_residual(
