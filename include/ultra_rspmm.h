@@ -240,6 +240,15 @@ int ultra_layer_linear_set_kernel(int32_t kind);
 int ultra_score_head(const float *dev_z, const float *dev_query_bias, const float *dev_weight, const float *dev_bias,
                      float *dev_score, int64_t rows, int32_t batch, int32_t dim, void *stream);
 
+/* The split scoring head in one kernel (inference): score[r] = out_bias[0] + out_weight . relu(W1[:, 0:in_dim] input[r, 0:in_dim]
+ * + query_bias[r % batch]) for `rows` rows; W1 rows are weight_stride floats apart (the first in_dim columns of the MLP's
+ * (2 in_dim, 2 in_dim) first Linear), query_bias is (batch, 2 in_dim) = query @ W1[:, in_dim:]^T + b1, out_weight (2 in_dim).
+ * in_dim in {32, 64}.  fp32 accuracy on the tensor cores (3xTF32, as ultra_layer_linear_norm_relu_residual); replaces the
+ * K = in_dim cuBLAS GEMM + ultra_score_head. */
+int ultra_score_head_linear(const float *dev_input, int64_t input_stride, const float *dev_weight, int64_t weight_stride,
+                            const float *dev_query_bias, const float *dev_out_weight, const float *dev_out_bias,
+                            float *dev_score, int64_t rows, int32_t batch, int32_t in_dim, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

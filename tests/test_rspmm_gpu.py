@@ -459,6 +459,33 @@ def test_fused_linear_epilogue_has_fp32_accuracy(cuda, linear_kernel, dim, rows)
         F.linear_norm_relu_residual_into(buffer[..., :-4], linear.weight, plain)
 
 
+@pytest.mark.parametrize("dim,nodes,batch", [(64, 300, 5), (32, 77, 3), (64, 1, 7)])
+def test_score_head_linear_has_fp32_accuracy(cuda, dim, nodes, batch):
+    """Fused scoring head (K = d GEMM on 3xTF32 + per-query bias + ReLU + 1-row Linear) vs a float64 evaluation of the
+    reference's MLP over cat([hidden, query]) (model.py:141-143, 177-193)."""
+    from ultra_torchdrug_b200 import functional as F
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(dim + nodes)
+    feature = torch.randn(nodes, batch, 2 * dim, device=cuda)
+    query = torch.randn(batch, dim, device=cuda)
+    first, second = torch.nn.Linear(2 * dim, 2 * dim).to(cuda), torch.nn.Linear(2 * dim, 1).to(cuda)
+    with torch.no_grad():
+        def evaluate(dtype):
+            joined = torch.cat([feature[..., :dim], query.expand(nodes, -1, -1)], dim=-1).to(dtype)
+            hidden = torch.relu(torch.nn.functional.linear(joined, first.weight.to(dtype), first.bias.to(dtype)))
+            return torch.nn.functional.linear(hidden, second.weight.to(dtype), second.bias.to(dtype)).squeeze(-1)
+
+        exact = evaluate(torch.float64)
+        cublas_error = float((evaluate(torch.float32).double() - exact).abs().max())
+        query_bias = torch.nn.functional.linear(query, first.weight[:, dim:], first.bias)
+        got = F.score_head_linear(feature, dim, first.weight, query_bias, second.weight, second.bias)
+        assert got.shape == (nodes, batch)
+        assert float((got.double() - exact).abs().max()) <= 4 * cublas_error + 1e-6
+        torch.testing.assert_close(got, evaluate(torch.float32), rtol=1e-5, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        F.score_head_linear(feature, dim, first.weight, query_bias[:-1], second.weight, second.bias)
+
+
 @pytest.mark.parametrize("dim", [4, 32, 128])
 def test_score_head_matches_torch(cuda, dim):
     """Fused `relu(z + query_bias) . w + b` vs the separate PyTorch ops of the scoring MLP (model.py:177-193)."""

@@ -80,6 +80,8 @@ SYMBOLS = {
                                                              c_int64, c_int64, c_int32, ctypes.c_float, c_int32, c_int32,
                                                              c_void_p]),
     "ultra_layer_linear_set_kernel": (ctypes.c_int, [c_int32]),
+    "ultra_score_head_linear": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_int64, c_int32, c_int32, c_void_p]),
     "ultra_score_head": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
 }
 

@@ -184,6 +184,136 @@ linear_norm_relu_residual_kernel(const float *__restrict__ A, long long lda, con
     }
 }
 
+// ---- scoring head (reference ultra/model.py:177-193): score[r] = b2 + w2 . relu(W1h hidden[r] + query_bias[r % batch]) -------
+// The K = d GEMM of the split head (nbf._split_head) and ultra_score_head's pass fused: the (rows, H) activations of the
+// MLP's hidden layer never reach memory.  Same machinery as the layer kernel above (3xTF32 mma.sync, one pipeline per
+// warp over 16-row tiles); H = 2K hidden units are accumulated as H / 8 tiles in two halves of 8 to bound the registers.
+template <int K> struct HeadShape {
+    static constexpr int H = 2 * K;                    // hidden units of the MLP = width of [hidden | query]
+    static constexpr int kPad = K + 4;
+    static constexpr int kSteps = K / 8;
+    static constexpr int kNTiles = H / 8;
+    static constexpr size_t kWeightBytes = (size_t)kSteps * kNTiles * 32 * sizeof(float4);
+    static constexpr size_t kTileBytes = (size_t)kWarpRows * kPad * sizeof(float);
+    static constexpr size_t kSmemBytes = kWeightBytes + kLinearWarps * kTileBytes;
+};
+
+template <int K>
+__global__ void __launch_bounds__(kLinearThreads, 1)
+score_head_linear_kernel(const float *__restrict__ A, long long lda, const float *__restrict__ W, long long ldw,
+                         const float *__restrict__ query_bias, const float *__restrict__ w2, const float *__restrict__ b2,
+                         float *__restrict__ score, long long rows, int batch) {
+    using Shape = HeadShape<K>;
+    constexpr int H = Shape::H, kPad = Shape::kPad, kSteps = Shape::kSteps, kNTiles = Shape::kNTiles;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *w_frag = reinterpret_cast<float4 *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    float *mine = reinterpret_cast<float *>(smem_raw + Shape::kWeightBytes) + warp * (kWarpRows * kPad);
+
+    // W1[:, :K] (H rows of ldw floats) -> fragment order [k-step][n-tile][lane] = (b0 hi, b1 hi, b0 lo, b1 lo)
+    for (int idx = tid; idx < kSteps * kNTiles * 32; idx += kLinearThreads) {
+        const int l = idx & 31, j = (idx >> 5) % kNTiles, s = idx / (32 * kNTiles);
+        const int n = 8 * j + (l >> 2), k = 8 * s + (l & 3);
+        const float b0 = __ldg(W + n * ldw + k), b1 = __ldg(W + n * ldw + k + 4);
+        const float b0_hi = to_tf32(b0), b1_hi = to_tf32(b1);
+        w_frag[idx] = make_float4(b0_hi, b1_hi, to_tf32(b0 - b0_hi), to_tf32(b1 - b1_hi));
+    }
+    __syncthreads();
+
+    constexpr int kChunks = K / 4;
+    const float bias = b2 ? __ldg(b2) : 0.f;
+    const long long n_tiles = (rows + kWarpRows - 1) / kWarpRows;
+    const long long stride = (long long)gridDim.x * kLinearWarps;
+    for (long long tile = (long long)blockIdx.x * kLinearWarps + warp; tile < n_tiles; tile += stride) {
+        const long long row0 = tile * kWarpRows;
+#pragma unroll 4
+        for (int c = lane; c < kWarpRows * kChunks; c += 32) {
+            const int r = c / kChunks, q = c % kChunks;
+            const bool live = row0 + r < rows;
+            cp_async_16(mine + r * kPad + 4 * q, A + (live ? row0 + r : 0) * lda + 4 * q, live ? 16u : 0u);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+
+        const float *row_upper = mine + g * kPad + t;
+        const float *row_lower = row_upper + 8 * kPad;
+        // the two rows of this thread and their queries (rows are (node, query) pairs, query fastest)
+        const long long row_a = row0 + g, row_b = row0 + g + 8;
+        const float *qb_a = query_bias + (row_a % batch) * H + 2 * t, *qb_b = query_bias + (row_b % batch) * H + 2 * t;
+        float dot[2] = {0.f, 0.f};
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            constexpr int kHalf = kNTiles / 2;
+            float acc[kHalf][4];
+#pragma unroll
+            for (int j = 0; j < kHalf; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll 2
+            for (int s = 0; s < kSteps; ++s) {
+                const float a[4] = {row_upper[8 * s], row_lower[8 * s], row_upper[8 * s + 4], row_lower[8 * s + 4]};
+                float big[4], small[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    big[i] = to_tf32(a[i]);
+                    small[i] = to_tf32(a[i] - big[i]);
+                }
+                const float4 *w = w_frag + (s * kNTiles + half * kHalf) * 32 + lane;
+                float4 b[kHalf];
+#pragma unroll
+                for (int j = 0; j < kHalf; ++j) b[j] = w[j * 32];
+#pragma unroll
+                for (int j = 0; j < kHalf; ++j) mma_tf32(acc[j], small, b[j].x, b[j].y);
+#pragma unroll
+                for (int j = 0; j < kHalf; ++j) mma_tf32(acc[j], big, b[j].z, b[j].w);
+#pragma unroll
+                for (int j = 0; j < kHalf; ++j) mma_tf32(acc[j], big, b[j].x, b[j].y);
+            }
+            // hidden units {8j + 2t, 8j + 2t + 1} of rows g (acc[j][0..1]) and g + 8 (acc[j][2..3])
+#pragma unroll
+            for (int j = 0; j < kHalf; ++j) {
+                const int col = 8 * (half * kHalf + j);
+                const float2 w = __ldg(reinterpret_cast<const float2 *>(w2 + col + 2 * t));
+                const float2 qa = __ldg(reinterpret_cast<const float2 *>(qb_a + col));
+                const float2 qb = __ldg(reinterpret_cast<const float2 *>(qb_b + col));
+                dot[0] = fmaf(fmaxf(acc[j][0] + qa.x, 0.f), w.x, dot[0]);
+                dot[0] = fmaf(fmaxf(acc[j][1] + qa.y, 0.f), w.y, dot[0]);
+                dot[1] = fmaf(fmaxf(acc[j][2] + qb.x, 0.f), w.x, dot[1]);
+                dot[1] = fmaf(fmaxf(acc[j][3] + qb.y, 0.f), w.y, dot[1]);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            dot[h] += __shfl_xor_sync(kFullMask, dot[h], 1);
+            dot[h] += __shfl_xor_sync(kFullMask, dot[h], 2);
+        }
+        if (t == 0) {
+            if (row_a < rows) score[row_a] = dot[0] + bias;
+            if (row_b < rows) score[row_b] = dot[1] + bias;
+        }
+        __syncwarp();
+    }
+}
+
+template <int K>
+int launch_score_head(const float *A, long long lda, const float *W, long long ldw, const float *query_bias, const float *w2,
+                      const float *b2, float *score, long long rows, int batch, cudaStream_t stream) {
+    using Shape = HeadShape<K>;
+    static int sm_count = 0;
+    auto kernel = score_head_linear_kernel<K>;
+    if (sm_count == 0) {                               // once per process (one process per GPU), outside any graph capture
+        int device = 0, count = 0;
+        ULTRA_CUDA_OK(cudaGetDevice(&device));
+        ULTRA_CUDA_OK(cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device));
+        ULTRA_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Shape::kSmemBytes));
+        sm_count = count;
+    }
+    const long long n_blocks = (rows + kWarpRows * kLinearWarps - 1) / (kWarpRows * kLinearWarps);
+    const unsigned grid = (unsigned)(n_blocks < sm_count ? n_blocks : sm_count);
+    kernel<<<grid, kLinearThreads, Shape::kSmemBytes, stream>>>(A, lda, W, ldw, query_bias, w2, b2, score, rows, batch);
+    note_launch();
+    ULTRA_CUDA_OK(cudaGetLastError());
+    return ULTRA_RSPMM_OK;
+}
+
 template <int N>
 int launch_linear(const float *A, long long lda, const float *W, const float *linear_bias, const float *gamma,
                   const float *beta, float *out, long long ldo, long long rows, float eps, int relu, int shortcut,
@@ -255,4 +385,22 @@ extern "C" int ultra_layer_linear_norm_relu_residual(const float *dev_input, int
                                  out_stride, rows, eps, relu, shortcut, s);
     return launch_linear<32>(dev_input, input_stride, dev_weight, dev_linear_bias, dev_gamma, dev_beta, dev_out, out_stride,
                              rows, eps, relu, shortcut, s);
+}
+
+extern "C" int ultra_score_head_linear(const float *dev_input, int64_t input_stride, const float *dev_weight,
+                                       int64_t weight_stride, const float *dev_query_bias, const float *dev_out_weight,
+                                       const float *dev_out_bias, float *dev_score, int64_t rows, int32_t batch,
+                                       int32_t in_dim, void *stream) {
+    if (rows < 0 || batch <= 0 || (rows > 0 && (!dev_input || !dev_weight || !dev_query_bias || !dev_out_weight || !dev_score)))
+        return ULTRA_RSPMM_ERR_ARG;
+    if (in_dim != 32 && in_dim != 64) return ULTRA_RSPMM_ERR_RANGE;
+    if (input_stride < in_dim || input_stride % 4 || weight_stride < in_dim) return ULTRA_RSPMM_ERR_ARG;
+    if (((uintptr_t)dev_input & 15) || (((uintptr_t)dev_query_bias | (uintptr_t)dev_out_weight) & 7)) return ULTRA_RSPMM_ERR_ARG;
+    if (rows == 0) return ULTRA_RSPMM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (in_dim == 64)
+        return launch_score_head<64>(dev_input, input_stride, dev_weight, weight_stride, dev_query_bias, dev_out_weight,
+                                     dev_out_bias, dev_score, rows, batch, s);
+    return launch_score_head<32>(dev_input, input_stride, dev_weight, weight_stride, dev_query_bias, dev_out_weight,
+                                 dev_out_bias, dev_score, rows, batch, s);
 }

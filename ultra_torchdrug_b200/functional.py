@@ -21,7 +21,7 @@ from . import _lib
 __all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
            "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "RSPMMAddBoundaryFunction", "rspmm_pna", "LayerEpilogueFunction",
            "layer_norm_relu_residual_into", "score_head", "fused_linear_supported",
-           "linear_norm_relu_residual_into"]
+           "linear_norm_relu_residual_into", "score_head_linear"]
 
 _SUM_OPS = ("add", "min", "max")
 _MUL_OPS = ("mul", "add")
@@ -310,6 +310,27 @@ def score_head(z, query_bias, weight, bias=None):
     with torch.cuda.device(z.device):
         _lib.check(_lib.lib().ultra_score_head(_ptr(z), _ptr(query_bias), _ptr(weight), _ptr(bias), _ptr(score),
                                                num_node * batch, batch, dim, _stream_handle()), "ultra_score_head")
+    return score
+
+
+def score_head_linear(feature, hidden_dim, first_weight, query_bias, out_weight, out_bias=None):
+    """Scores (N, B) of every (node, query) row of the (N, B, width) layer buffer `feature`, whose first `hidden_dim`
+    columns are the hidden state: `out_weight . relu(first_weight[:, :hidden_dim] hidden + query_bias[query]) + out_bias`
+    in one kernel (inference; `ultra_score_head_linear`).  `first_weight` is the MLP's first Linear weight (2d, 2d),
+    `query_bias` (B, 2d) its query half applied to the queries plus its bias."""
+    num_node, batch, width = feature.shape
+    hidden_units = first_weight.shape[0]
+    if not fused_linear_supported(feature, hidden_dim) or not feature.is_contiguous() or hidden_units != 2 * hidden_dim \
+            or width < hidden_dim or first_weight.stride(-1) != 1 or first_weight.shape[1] < hidden_dim:
+        raise RuntimeError("score_head_linear needs a contiguous float32 CUDA buffer and a (2d, >= d) weight, d in {32, 64}")
+    query_bias, out_weight = query_bias.contiguous(), out_weight.contiguous().view(-1)
+    if query_bias.shape != (batch, hidden_units) or out_weight.shape != (hidden_units,):
+        raise RuntimeError("score_head_linear: query_bias must be (%d, %d) and out_weight (%d,)" % (batch, hidden_units, hidden_units))
+    score = torch.empty(num_node, batch, dtype=feature.dtype, device=feature.device)
+    with torch.cuda.device(feature.device):
+        _lib.check(_lib.lib().ultra_score_head_linear(
+            _ptr(feature), width, _ptr(first_weight), first_weight.stride(0), _ptr(query_bias), _ptr(out_weight),
+            _ptr(out_bias), _ptr(score), num_node * batch, batch, hidden_dim, _stream_handle()), "ultra_score_head_linear")
     return score
 
 

@@ -291,8 +291,10 @@ class TransferNBFNet(nn.Module):
         num_node, batch, width = feature.shape
         hidden_dim = width - query.shape[-1]
         first, second = self.mlp.layers
-        z = F.linear(feature.view(num_node * batch, width)[:, :hidden_dim], first.weight[:, :hidden_dim])
         query_bias = F.linear(query, first.weight[:, hidden_dim:], first.bias)
+        if rspmm.fused_linear_supported(feature, hidden_dim) and first.out_features == 2 * hidden_dim:
+            return rspmm.score_head_linear(feature, hidden_dim, first.weight, query_bias, second.weight, second.bias)
+        z = F.linear(feature.view(num_node * batch, width)[:, :hidden_dim], first.weight[:, :hidden_dim])
         return rspmm.score_head(z.view(num_node, batch, -1), query_bias, second.weight, second.bias)   # (N, B)
 
     def bellmanford(self, graph, h_index, r_index):
