@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ULTRA_RSPMM_ABI_VERSION 3
+#define ULTRA_RSPMM_ABI_VERSION 4
 
 /* status codes (0 = ok).  For ULTRA_RSPMM_ERR_CUDA the cudaError_t is kept per thread, see
  * ultra_rspmm_last_cuda_error(). */
@@ -96,6 +96,8 @@ typedef struct ultra_rspmm_index {
     ultra_rspmm_order_t csr;  /* forward: segments = destination rows, sorted (dst, rel, src); edge = {src, rel} */
     ultra_rspmm_order_t csc;  /* backward w.r.t. input: segments = source rows, sorted (src, rel, dst); edge = {dst, rel} */
     ultra_rspmm_order_t rel;  /* backward w.r.t. relation: segments = relations, sorted (rel, dst, src); edge = {dst, src} */
+    const int32_t *merge_perm;  /* nnz_raw: the caller's edge positions in the order the build merged them            */
+    const int32_t *merge_start; /* nnz + 1: csr edge m is the sum of merge_perm[merge_start[m] .. merge_start[m + 1])  */
 } ultra_rspmm_index_t;
 
 /* ---- version / diagnostics ------------------------------------------------------------------- */
@@ -125,6 +127,15 @@ int ultra_rspmm_index_build(const int64_t *dev_indices, int64_t index_stride, co
                             int64_t nnz_raw, int32_t n_out, int32_t n_in, int32_t n_rel, int32_t dtype,
                             void *index_buffer, size_t index_bytes, void *scratch, size_t scratch_bytes,
                             ultra_rspmm_index_t *index, void *stream);
+/* The same edge structure with other values: `dev_values` holds nnz_raw new values in the
+ * caller's original edge order (the order of dev_indices at build time).  Fills *derived, a copy of *base whose w arrays
+ * and task lists (per-task "all weights are 1" flags) live in `buffer` (ultra_rspmm_index_derive_bytes; 256-byte aligned)
+ * and whose structure arrays still point into base's buffer - keep both alive.  Duplicates are summed in the build's
+ * order.  Asynchronous, no host synchronisation: a weight-0 mask over a fixed graph (what `remove_easy_edges`,
+ * reference model.py:57-74, amounts to under sum aggregation) costs three small kernels instead of an index rebuild. */
+int ultra_rspmm_index_derive_bytes(const ultra_rspmm_index_t *base, size_t *bytes);
+int ultra_rspmm_index_derive(const ultra_rspmm_index_t *base, const void *dev_values, void *buffer, size_t bytes,
+                             ultra_rspmm_index_t *derived, void *stream);
 /* 128-bit content fingerprint of (indices, values) written to dev_out[2] (uint64); lets a caller
  * recognise an edge set it already indexed without a sort.  dev_out must be zero on entry is NOT
  * required (the call clears it).  Asynchronous. */

@@ -172,3 +172,46 @@ def test_buffered_layer_loop_equals_generic_loop(cuda, monkeypatch):
     with torch.enable_grad():                        # training keeps the autograd path
         ranker.predict(batch).sum().backward()
     assert len(taken) == 3
+
+
+@pytest.mark.gpu
+def test_masking_easy_edges_equals_removing_them(cuda, monkeypatch):
+    """Training forward with `remove_easy_edges`: weight-0 masking on the full graph's index (GraphIndex.derive) gives
+    the scores and parameter gradients of the reference's edge removal (model.py:57-74) - and builds no new index."""
+    from ultra_torchdrug_b200 import functional as F, synthetic
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(3)
+    num_node, num_relation = 200, 5
+    triples = synthetic.triples(num_node, num_relation, 1500, seed=3)
+    triples = torch.cat([triples, triples[:40]])                                  # duplicate edges: merged weights
+    graph = data.Graph(triples, num_node=num_node, num_relation=num_relation).to(cuda)
+    model, rel_model = nbf.ultra_models(num_relation, hidden=32, num_layers=3)
+    model, rel_model = model.to(cuda).train(), rel_model.to(cuda).train()
+    rel_graph = nbf.construct_relation_graph(graph)
+    batch = triples[:8].to(cuda)
+    negatives = torch.randint(num_node, (8, 4), device=cuda)
+    h_index, t_index, r_index = (batch[:, i].unsqueeze(-1).repeat(1, 5) for i in range(3))
+    t_index[:4, 1:] = negatives[:4]
+    h_index[4:, 1:] = negatives[4:]
+    parameters = list(model.parameters()) + list(rel_model.parameters())
+
+    def run():
+        for p in parameters:
+            p.grad = None
+        rel_input = rel_model(rel_graph, batch[:, 2])
+        pred = model(graph, [rel_input], h_index, t_index, r_index, remove_easy_edges=True)
+        pred.square().sum().backward()
+        return pred.detach().clone(), [None if p.grad is None else p.grad.clone() for p in parameters]
+
+    run()                                                                        # builds the index of the full graph
+    built = F.cache_stats["built"]
+    masked_pred, masked_grads = run()
+    assert F.cache_stats["built"] == built, "masking must not build another index"
+    monkeypatch.setattr(nbf.TransferNBFNet, "_can_mask_easy_edges", lambda self, graph: False)
+    removed_pred, removed_grads = run()
+    assert F.cache_stats["built"] > built
+    torch.testing.assert_close(masked_pred, removed_pred, rtol=1e-4, atol=1e-5)
+    for a, b in zip(masked_grads, removed_grads):
+        assert (a is None) == (b is None)
+        if a is not None:
+            torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5 * (1 + float(b.abs().max())))

@@ -607,3 +607,38 @@ def test_parity_moderate_power_law(cuda, sum, mul):
     """4,000 nodes, 45,000 edges, Zipf destinations: hub rows split into partial rows, thousands of short rows walked in
     group tasks, empty rows - all in one index; against the oracle."""
     _run_case(cuda, 4000, 4000, 12, 45000, 260, sum, mul, seed=41, duplicates=500, weights="random", skew=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_derived_index_equals_rebuilt_index(cuda, dtype):
+    """`GraphIndex.derive(values)` (same structure, new values, no sort) gives bit for bit what an index built from
+    (indices, values) gives - forward in all three reductions, both gradients - incl. duplicates and split rows."""
+    from ultra_torchdrug_b200 import _lib, functional as F
+    lib = _lib.lib()
+    lib.ultra_rspmm_set_tuning(16, 0, 0)
+    try:
+        n, n_rel, dim = 70, 4, 36
+        indices, values = util.random_coo(n, n, n_rel, 1500, seed=9, duplicates=60, weights="random", skew=True, dtype=dtype)
+        d_indices = torch.from_numpy(indices).to(cuda)
+        base = F.GraphIndex(d_indices, torch.ones(indices.shape[1], dtype=torch.from_numpy(values).dtype, device=cuda), (n, n, n_rel))
+        assert base.c.unit_weight == 0 or base.c.nnz == base.c.nnz_raw     # duplicates merged to weight 2 make it non-unit
+        masked = values.copy()
+        masked[::7] = 0
+        for new_values in (values, masked, np.ones_like(values)):
+            d_values = torch.from_numpy(new_values).to(cuda)
+            derived, rebuilt = base.derive(d_values), F.GraphIndex(d_indices, d_values, (n, n, n_rel))
+            relation = torch.from_numpy(util.random_dense(n_rel, dim, 1, dtype)).to(cuda)
+            input = torch.from_numpy(util.random_dense(n, dim, 2, dtype)).to(cuda)
+            grad = torch.from_numpy(util.random_dense(n, dim, 3, dtype)).to(cuda)
+            for sum in ("add", "max", "min"):
+                got, got_arg = derived.forward(relation, input, sum, "mul", return_argidx=True)
+                want, want_arg = rebuilt.forward(relation, input, sum, "mul", return_argidx=True)
+                assert torch.equal(got, want), sum
+                assert sum == "add" or torch.equal(got_arg, want_arg), sum
+                for a, b in zip(derived.backward(relation, input, got, grad, sum, "mul"),
+                                rebuilt.backward(relation, input, want, grad, sum, "mul")):
+                    assert torch.equal(a, b), sum
+        with pytest.raises(RuntimeError):
+            base.derive(torch.ones(3, device=cuda))
+    finally:
+        lib.ultra_rspmm_set_tuning(256, 0, 0)

@@ -8,7 +8,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK, ERR_ARG, ERR_WORKSPACE, ERR_CUDA, ERR_INDEX, ERR_DTYPE, ERR_RANGE = range(7)
 SUM_CODE = {"add": 0, "min": 1, "max": 2}
@@ -30,7 +30,7 @@ class Index(ctypes.Structure):
     """`ultra_rspmm_index_t`"""
     _fields_ = [("nnz", c_int64), ("nnz_raw", c_int64), ("n_out", c_int32), ("n_in", c_int32), ("n_rel", c_int32),
                 ("dtype", c_int32), ("unit_weight", c_int32), ("chunk", c_int32),
-                ("csr", Order), ("csc", Order), ("rel", Order)]
+                ("csr", Order), ("csc", Order), ("rel", Order), ("merge_perm", c_void_p), ("merge_start", c_void_p)]
 
 
 #: every symbol `include/ultra_rspmm.h` declares: name -> (restype, argtypes)
@@ -45,6 +45,9 @@ SYMBOLS = {
                                                ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),
     "ultra_rspmm_index_build": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                                c_void_p, c_size_t, c_void_p, c_size_t, ctypes.POINTER(Index), c_void_p]),
+    "ultra_rspmm_index_derive_bytes": (ctypes.c_int, [ctypes.POINTER(Index), ctypes.POINTER(c_size_t)]),
+    "ultra_rspmm_index_derive": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_size_t, ctypes.POINTER(Index),
+                                                c_void_p]),
     "ultra_rspmm_fingerprint": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "ultra_rspmm_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(Index), c_int64, c_int32,
                                                    ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),

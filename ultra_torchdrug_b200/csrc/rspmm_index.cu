@@ -61,7 +61,8 @@ template <typename T>
 __global__ void merge_kernel(const unsigned long long *__restrict__ keys, const int32_t *__restrict__ vals,
                              const int32_t *__restrict__ pos, const T *__restrict__ values, int64_t nnz,
                              int64_t n_in, int64_t n_rel, int2 *__restrict__ csr_edge, T *__restrict__ csr_w,
-                             int32_t *__restrict__ row_of, int32_t *__restrict__ counters) {
+                             int32_t *__restrict__ row_of, int32_t *__restrict__ merge_start,
+                             int32_t *__restrict__ counters) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nnz) return;
     const unsigned long long key = keys[e];
@@ -74,8 +75,12 @@ __global__ void merge_kernel(const unsigned long long *__restrict__ keys, const 
     csr_edge[m] = make_int2((int32_t)(key % (unsigned long long)n_in), (int32_t)(rk % (unsigned long long)n_rel));
     csr_w[m] = w;
     row_of[m] = (int32_t)(rk / (unsigned long long)n_rel);
+    merge_start[m] = (int32_t)e;          // csr edge m = sum of the sorted raw edges [merge_start[m], merge_start[m + 1])
     if (w != T(1)) atomicOr(&counters[CNT_NONUNIT], 1);
-    if (e == 0) counters[CNT_NNZ] = pos[nnz];
+    if (e == 0) {
+        counters[CNT_NNZ] = pos[nnz];
+        merge_start[pos[nnz]] = (int32_t)nnz;
+    }
 }
 
 __global__ void csc_keys_kernel(const int2 *__restrict__ csr_edge, const int32_t *__restrict__ row_of, int32_t nnz,
@@ -355,6 +360,7 @@ struct OrderLayout {
 
 struct IndexLayout {
     OrderLayout order[3];
+    size_t merge_perm, merge_start;   // which raw edges were summed into which csr edge (ultra_rspmm_index_derive)
     size_t total;
 };
 
@@ -381,6 +387,8 @@ IndexLayout index_layout(int64_t nnz_raw, const int32_t n_seg[3], size_t elem, i
         q.split = at; at = align_up(at + sizeof(int4) * split_upper(nnz_raw, chunk));
         q.gtask = at; at = align_up(at + (o == 2 ? 0 : sizeof(int4) * task_upper(nnz_raw, n_seg[o], chunk)));
     }
+    L.merge_perm = at; at = align_up(at + sizeof(int32_t) * e);
+    L.merge_start = at; at = align_up(at + sizeof(int32_t) * (e + 1));
     L.total = at;
     return L;
 }
@@ -455,8 +463,10 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
         ULTRA_CUDA_OK(cub::DeviceScan::ExclusiveSum(cub_tmp, need, vals_a, pos, (int)nnz_raw + 1, stream));
         note_launch();
         merge_kernel<T><<<blocks_for(nnz_raw), kBuildThreads, 0, stream>>>(keys_b, vals_b, pos, dev_values, nnz_raw, n_in,
-                                                                          n_rel, csr_edge, csr_w, row_of, counters);
+                                                                          n_rel, csr_edge, csr_w, row_of,
+                                                                          (int32_t *)(ibuf + L.merge_start), counters);
         note_launch();
+        ULTRA_CUDA_OK(cudaMemcpyAsync(ibuf + L.merge_perm, vals_b, sizeof(int32_t) * (size_t)nnz_raw, cudaMemcpyDeviceToDevice, stream));
         ULTRA_CUDA_OK(cudaMemcpyAsync(host_counters, counters, 4 * CNT_SIZE, cudaMemcpyDeviceToHost, stream));
         ULTRA_CUDA_OK(cudaStreamSynchronize(stream));
         if (host_counters[CNT_ERROR]) return ULTRA_RSPMM_ERR_INDEX;
@@ -614,6 +624,107 @@ int build_typed(const int64_t *dev_indices, int64_t stride, const T *dev_values,
     index->dtype = sizeof(T) == 4 ? ULTRA_RSPMM_F32 : ULTRA_RSPMM_F64;
     index->unit_weight = host_counters[CNT_NONUNIT] ? 0 : 1;
     index->chunk = chunk;
+    index->merge_perm = (const int32_t *)(ibuf + L.merge_perm);
+    index->merge_start = (const int32_t *)(ibuf + L.merge_start);
+    return ULTRA_RSPMM_OK;
+}
+
+// ---- derived index: the same edge structure with other values (ultra_rspmm_index_derive) -----------------------------
+// csr edge m <- sum of its raw edges in the order the build summed them (sequential, fp64, rounded once); the value is
+// also scattered to the edge's canonical rank, from where the two other orders pick it up through their eid arrays.
+template <typename T>
+__global__ void derive_merge_kernel(const int32_t *__restrict__ merge_perm, const int32_t *__restrict__ merge_start,
+                                    const T *__restrict__ values, int32_t nnz, const int32_t *__restrict__ csr_eid,
+                                    T *__restrict__ csr_w, T *__restrict__ by_rank) {
+    const int32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nnz) return;
+    double total = 0.0;
+    for (int32_t q = merge_start[m]; q < merge_start[m + 1]; ++q) total += (double)values[merge_perm[q]];
+    const T w = (T)total;
+    csr_w[m] = w;
+    by_rank[csr_eid[m]] = w;
+}
+
+template <typename T>
+__global__ void derive_gather_kernel(const int32_t *__restrict__ eid, const T *__restrict__ by_rank, int32_t nnz,
+                                     T *__restrict__ w) {
+    const int32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < nnz) w[m] = by_rank[eid[m]];
+}
+
+// one warp per task: copy the task with its non-unit flag recomputed from the new values
+template <typename T>
+__global__ void derive_task_flags_kernel(const int4 *__restrict__ task_in, int32_t n_task, const T *__restrict__ w,
+                                         int4 *__restrict__ task_out) {
+    const int32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= n_task) return;
+    int4 task = task_in[t];
+    bool nonunit = false;
+    for (int32_t e = task.y + lane; e < task.z; e += 32) nonunit = nonunit || w[e] != T(1);
+    nonunit = __any_sync(0xffffffffu, nonunit);
+    task.w = nonunit ? (task.w | kNonUnitTask) : (task.w & ~kNonUnitTask);
+    if (lane == 0) task_out[t] = task;
+}
+
+struct DerivedLayout {
+    size_t by_rank, w[3], task[3], gtask[3], total;
+};
+
+DerivedLayout derived_layout(const ultra_rspmm_index_t &base) {
+    DerivedLayout D;
+    const size_t elem = base.dtype == ULTRA_RSPMM_F32 ? 4 : 8;
+    const size_t e = base.nnz > 0 ? (size_t)base.nnz : 1;
+    const ultra_rspmm_order_t *orders[3] = {&base.csr, &base.csc, &base.rel};
+    size_t at = 0;
+    D.by_rank = at; at = align_up(at + elem * e);
+    for (int o = 0; o < 3; ++o) {
+        D.w[o] = at; at = align_up(at + elem * e);
+        D.task[o] = at; at = align_up(at + sizeof(int4) * (size_t)(orders[o]->n_task > 0 ? orders[o]->n_task : 1));
+        D.gtask[o] = at; at = align_up(at + sizeof(int4) * (size_t)(orders[o]->n_gtask > 0 ? orders[o]->n_gtask : 1));
+    }
+    D.total = at;
+    return D;
+}
+
+template <typename T>
+int derive_typed(const ultra_rspmm_index_t &base, const T *values, char *buffer, ultra_rspmm_index_t *derived,
+                 cudaStream_t stream) {
+    const DerivedLayout D = derived_layout(base);
+    *derived = base;
+    derived->unit_weight = 0;               // decided per task (flag in task.w), without a host round trip
+    const int32_t nnz = (int32_t)base.nnz;
+    ultra_rspmm_order_t *orders[3] = {&derived->csr, &derived->csc, &derived->rel};
+    T *by_rank = (T *)(buffer + D.by_rank);
+    if (nnz > 0) {
+        derive_merge_kernel<T><<<blocks_for(nnz), kBuildThreads, 0, stream>>>(base.merge_perm, base.merge_start, values, nnz,
+                                                                              base.csr.eid, (T *)(buffer + D.w[0]), by_rank);
+        note_launch();
+    }
+    for (int o = 0; o < 3; ++o) {
+        ultra_rspmm_order_t &order = *orders[o];
+        T *w = (T *)(buffer + D.w[o]);
+        if (o > 0 && nnz > 0) {
+            derive_gather_kernel<T><<<blocks_for(nnz), kBuildThreads, 0, stream>>>(order.eid, by_rank, nnz, w);
+            note_launch();
+        }
+        order.w = w;
+        if (order.n_task > 0) {
+            int4 *task = (int4 *)(buffer + D.task[o]);
+            derive_task_flags_kernel<T><<<blocks_for((int64_t)order.n_task * 32), kBuildThreads, 0, stream>>>(
+                (const int4 *)order.task, order.n_task, w, task);
+            note_launch();
+            order.task = (const int32_t *)task;
+        }
+        if (order.n_gtask > 0) {
+            int4 *gtask = (int4 *)(buffer + D.gtask[o]);
+            derive_task_flags_kernel<T><<<blocks_for((int64_t)order.n_gtask * 32), kBuildThreads, 0, stream>>>(
+                (const int4 *)order.gtask, order.n_gtask, w, gtask);
+            note_launch();
+            order.gtask = (const int32_t *)gtask;
+        }
+    }
+    ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;
 }
 
@@ -683,4 +794,21 @@ extern "C" int ultra_rspmm_fingerprint(const int64_t *dev_indices, int64_t index
     note_launch();
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;
+}
+
+extern "C" int ultra_rspmm_index_derive_bytes(const ultra_rspmm_index_t *base, size_t *bytes) {
+    if (!base || !bytes) return ULTRA_RSPMM_ERR_ARG;
+    *bytes = derived_layout(*base).total;
+    return ULTRA_RSPMM_OK;
+}
+
+extern "C" int ultra_rspmm_index_derive(const ultra_rspmm_index_t *base, const void *dev_values, void *buffer, size_t bytes,
+                                        ultra_rspmm_index_t *derived, void *stream) {
+    if (!base || !derived || !buffer || (base->nnz_raw > 0 && !dev_values)) return ULTRA_RSPMM_ERR_ARG;
+    if (base->nnz > 0 && (!base->merge_perm || !base->merge_start)) return ULTRA_RSPMM_ERR_ARG;
+    if (bytes < derived_layout(*base).total) return ULTRA_RSPMM_ERR_WORKSPACE;
+    if ((uintptr_t)buffer & 255) return ULTRA_RSPMM_ERR_ARG;
+    if (base->dtype == ULTRA_RSPMM_F32)
+        return derive_typed<float>(*base, (const float *)dev_values, (char *)buffer, derived, (cudaStream_t)stream);
+    return derive_typed<double>(*base, (const double *)dev_values, (char *)buffer, derived, (cudaStream_t)stream);
 }

@@ -21,7 +21,7 @@ from . import _lib
 __all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
            "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "RSPMMAddBoundaryFunction", "rspmm_pna", "LayerEpilogueFunction",
            "layer_norm_relu_residual_into", "score_head", "fused_linear_supported",
-           "linear_norm_relu_residual_into", "score_head_linear"]
+           "linear_norm_relu_residual_into", "score_head_linear", "attach_index"]
 
 _SUM_OPS = ("add", "min", "max")
 _MUL_OPS = ("mul", "add")
@@ -83,6 +83,29 @@ class GraphIndex(object):
         del scratch
         self.nnz = int(self.c.nnz)
         self._workspace_bytes = {}
+
+    def derive(self, values):
+        """The index of the same edge structure with other edge values (`values`: one per edge of the operand this index
+        was built from, in that operand's order).  Shares the structure arrays with `self`, owns new weight arrays and
+        task flags; no sort, no host synchronisation (`ultra_rspmm_index_derive`).  Used for the weight-0 form of
+        `remove_easy_edges` (reference model.py:57-74) in training steps."""
+        if values.shape != (int(self.c.nnz_raw),) or values.dtype != self.dtype or values.device != self.device:
+            raise RuntimeError("`values` must hold one %s value per edge of the indexed operand (%d) on %s"
+                               % (self.dtype, int(self.c.nnz_raw), self.device))
+        derived = object.__new__(GraphIndex)
+        derived.shape, derived.dtype, derived.device, derived.nnz = self.shape, self.dtype, self.device, self.nnz
+        derived.base = self                       # keeps the structure arrays alive
+        derived._workspace_bytes = self._workspace_bytes
+        need = ctypes.c_size_t()
+        lib = _lib.lib()
+        _lib.check(lib.ultra_rspmm_index_derive_bytes(ctypes.byref(self.c), ctypes.byref(need)), "ultra_rspmm_index_derive_bytes")
+        with torch.cuda.device(self.device):
+            derived.buffer = torch.empty(max(need.value, 256), dtype=torch.uint8, device=self.device)
+            derived.c = _lib.Index()
+            _lib.check(lib.ultra_rspmm_index_derive(ctypes.byref(self.c), _ptr(values.detach().contiguous()),
+                                                    derived.buffer.data_ptr(), derived.buffer.numel(),
+                                                    ctypes.byref(derived.c), _stream_handle()), "ultra_rspmm_index_derive")
+        return derived
 
     def workspace_bytes(self, dim):
         if dim not in self._workspace_bytes:
@@ -332,6 +355,13 @@ def score_head_linear(feature, hidden_dim, first_weight, query_bias, out_weight,
             _ptr(feature), width, _ptr(first_weight), first_weight.stride(0), _ptr(query_bias), _ptr(out_weight),
             _ptr(out_bias), _ptr(score), num_node * batch, batch, hidden_dim, _stream_handle()), "ultra_score_head_linear")
     return score
+
+
+def attach_index(sparse, index):
+    """Make `graph_index(sparse)` return `index` (e.g. one made by `GraphIndex.derive`) while the operand's indices and
+    values are not modified in place."""
+    sparse._ultra_rspmm_index = (index, (sparse._indices()._version, sparse._values()._version))
+    return sparse
 
 
 def _fingerprint(indices, values):

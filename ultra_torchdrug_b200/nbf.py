@@ -315,15 +315,41 @@ class TransferNBFNet(nn.Module):
         hidden = _run_layers(self.layers, graph, boundary, self.short_cut)
         return torch.cat([hidden, query.expand(graph.num_node, -1, -1)], dim=-1)
 
+    def mask_easy_edges(self, graph, h_index, t_index, r_index):
+        """`remove_easy_edges` + `undirected(add_inverse=True)` without changing the edge structure: the edges that match
+        a (h, t, r) of the batch keep their place and get weight 0.  Under sum aggregation the messages of such edges are
+        0 * (relation x input) - the sums are those of the graph without them - and the operator reuses the index of the
+        full graph (`GraphIndex.derive`: three small kernels, no sort, no host synchronisation) instead of building a new
+        one for every training step (reference model.py:57-74, 146-147, 166)."""
+        base = graph.undirected(add_inverse=True)                        # memoised per graph: structure and index
+        edge = graph.edge_list
+        key = (edge[:, 0] * graph.num_node + edge[:, 1]) * graph.num_relation + edge[:, 2]
+        easy = ((h_index * graph.num_node + t_index) * graph.num_relation + r_index).flatten()
+        easy = easy.sort().values                                        # (torch.isin compares all pairs for a small set)
+        found = easy[torch.searchsorted(easy, key).clamp_(max=len(easy) - 1)]
+        keep = found != key
+        weight = (graph.edge_weight * keep).repeat_interleave(2)         # undirected() interleaves an edge and its flip
+        masked = data.Graph(base.edge_list, edge_weight=weight, num_node=base.num_node, num_relation=base.num_relation)
+        full_index = rspmm.graph_index(base.adjacency.transpose(0, 1))
+        rspmm.attach_index(masked.adjacency.transpose(0, 1), full_index.derive(weight))
+        return masked
+
+    def _can_mask_easy_edges(self, graph):
+        return (graph.edge_list.is_cuda and not graph.edge_weight.requires_grad and generalized_rspmm is rspmm.generalized_rspmm
+                and all(layer.aggregate_func == "sum" and layer.message_func in MESSAGE_TO_MUL for layer in self.layers))
+
     def forward(self, graph, rel_query_list, h_index, t_index, r_index, remove_easy_edges=False):
-        if remove_easy_edges:
-            graph = self.remove_easy_edges(graph, h_index, t_index, r_index)
         self.query = rel_query_list[0]
         for i, layer in enumerate(self.layers):
             layer.relation = rel_query_list[i + 1] if len(rel_query_list) > 1 else rel_query_list[0]
         shape = h_index.shape
         num_relation = graph.num_relation
-        graph = graph.undirected(add_inverse=True)
+        if remove_easy_edges and self._can_mask_easy_edges(graph):
+            graph = self.mask_easy_edges(graph, h_index, t_index, r_index)
+        else:
+            if remove_easy_edges:
+                graph = self.remove_easy_edges(graph, h_index, t_index, r_index)
+            graph = graph.undirected(add_inverse=True)
         h_index, t_index, r_index = self.negative_sample_to_tail(h_index, t_index, r_index, num_relation)
         # the reference asserts here that every row shares its head and relation (model.py:174-175); on CUDA
         # tensors that is two host synchronisations per pass, so the mirror only checks host tensors
