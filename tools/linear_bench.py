@@ -59,6 +59,26 @@ def main():
 
     with torch.no_grad():
         t_fused, t_unfused = timed(fused, args.iters), timed(unfused, args.iters)
+    with torch.no_grad():      # accuracy of the three ways to run the layer, against a float64 evaluation (first 200k rows)
+        sample = buffers[0][:max(1, 200000 // args.batch)]
+
+        def evaluate(dtype, tf32=False):
+            x, w = sample.to(dtype), linear.weight.to(dtype)
+            if tf32:                                   # operands cut to 10 mantissa bits: the mode the reference switches off
+                x = (x.view(torch.int32) & ~0x1fff).view(torch.float32)
+                w = (w.view(torch.int32) & ~0x1fff).view(torch.float32)
+            hidden = torch.nn.functional.linear(x, w, linear.bias.to(dtype))
+            hidden = torch.nn.functional.layer_norm(hidden, (dim,), norm.weight.to(dtype), norm.bias.to(dtype), norm.eps)
+            return torch.relu(hidden) + sample.to(dtype)[..., :dim]
+
+        exact = evaluate(torch.float64)
+        out = torch.empty_like(sample)
+        F.linear_norm_relu_residual_into(sample, linear.weight, out[..., :dim], linear.bias, norm.weight, norm.bias, norm.eps,
+                                         relu=True, shortcut=True)
+        for name, value in (("fused kernel (3xTF32)", out[..., :dim]), ("cuBLAS fp32 + PyTorch ops", evaluate(torch.float32)),
+                            ("plain TF32 operands", evaluate(torch.float32, tf32=True))):
+            error = (value.double() - exact).abs()
+            print("max |error| vs float64  %-28s %.3e   (mean %.3e)" % (name, float(error.max()), float(error.mean())))
     moved = rows * (2 * dim + dim) * 4 / 1e9
     flops = 2.0 * rows * 2 * dim * dim
     print("rows %d  K %d  N %d" % (rows, 2 * dim, dim))
