@@ -68,3 +68,25 @@ def test_mirror_layer_on_cuda(cuda, path):
     torch.backends.cuda.matmul.allow_tf32 = False
     g, update, output = _run(path, cuda)
     _compare(path, g, update, output, 2e-5)
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_easy_edge_mask_equals_graph_match(seed):
+    """`nbf.easy_edge_mask` (sort + binary search, no host sync) marks exactly the edges `graph.match` finds for the
+    (h, t, r) rows of a training batch (reference model.py:57-74), duplicates and absent triples included."""
+    generator = torch.Generator().manual_seed(seed)
+    num_node, num_relation = 12, 3
+    edge_list = torch.stack([torch.randint(num_node, (90,), generator=generator), torch.randint(num_node, (90,), generator=generator),
+                             torch.randint(num_relation, (90,), generator=generator)], dim=1)
+    graph = data.Graph(edge_list, num_node=num_node, num_relation=num_relation)
+    h_index = torch.randint(num_node, (6, 4), generator=generator)
+    t_index = torch.randint(num_node, (6, 4), generator=generator)
+    r_index = torch.randint(num_relation, (6, 4), generator=generator)
+    h_index[0], t_index[0], r_index[0] = edge_list[:4, 0], edge_list[:4, 1], edge_list[:4, 2]   # some certain matches
+    pattern = torch.stack([h_index, t_index, r_index], dim=-1).flatten(0, -2)
+    want = torch.zeros(graph.num_edge, dtype=torch.bool)
+    want[graph.match(pattern)[0]] = True
+    assert want.any()
+    assert torch.equal(nbf.easy_edge_mask(graph, h_index, t_index, r_index), want)
+    empty = torch.zeros(0, 3, dtype=torch.long)
+    assert not nbf.easy_edge_mask(graph, empty[:, 0], empty[:, 1], empty[:, 2]).any()

@@ -31,6 +31,9 @@ def step():
 for _ in range(2): step()
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
-with profile(activities=[ProfilerActivity.CUDA]) as prof:
+by_op = os.environ.get("ULTRA_PROFILE_OPS") == "1"      # aten-level view (which autograd ops the elementwise kernels are)
+activities = [ProfilerActivity.CUDA, ProfilerActivity.CPU] if by_op else [ProfilerActivity.CUDA]
+with profile(activities=activities, record_shapes=by_op) as prof:
     step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=80))
+print(prof.key_averages(group_by_input_shape=by_op).table(sort_by="cuda_time_total", row_limit=40 if by_op else 22,
+                                                         max_name_column_width=60 if by_op else 80))

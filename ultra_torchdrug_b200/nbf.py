@@ -236,6 +236,20 @@ def _one_hot_boundary(num_node, index, query):
     return boundary
 
 
+def easy_edge_mask(graph, h_index, t_index, r_index):
+    """Boolean mask over `graph.edge_list`: True for the edges equal to some (h, t, r) of the batch - the edges
+    `graph.match(pattern)` returns in `remove_easy_edges` (reference model.py:57-74) - computed with one sort of the batch
+    and a binary search per edge, without a host synchronisation."""
+    edge = graph.edge_list
+    key = (edge[:, 0] * graph.num_node + edge[:, 1]) * graph.num_relation + edge[:, 2]
+    easy = ((h_index * graph.num_node + t_index) * graph.num_relation + r_index).flatten()
+    if easy.numel() == 0:
+        return torch.zeros_like(key, dtype=torch.bool)
+    easy = easy.sort().values                                            # (torch.isin compares all pairs for a small set)
+    found = easy[torch.searchsorted(easy, key).clamp_(max=len(easy) - 1)]
+    return found == key
+
+
 class TransferNBFNet(nn.Module):
     """Query-conditioned NBFNet over the entity graph (reference ultra/model.py:17-194, evaluation/training forward)."""
 
@@ -322,12 +336,7 @@ class TransferNBFNet(nn.Module):
         full graph (`GraphIndex.derive`: three small kernels, no sort, no host synchronisation) instead of building a new
         one for every training step (reference model.py:57-74, 146-147, 166)."""
         base = graph.undirected(add_inverse=True)                        # memoised per graph: structure and index
-        edge = graph.edge_list
-        key = (edge[:, 0] * graph.num_node + edge[:, 1]) * graph.num_relation + edge[:, 2]
-        easy = ((h_index * graph.num_node + t_index) * graph.num_relation + r_index).flatten()
-        easy = easy.sort().values                                        # (torch.isin compares all pairs for a small set)
-        found = easy[torch.searchsorted(easy, key).clamp_(max=len(easy) - 1)]
-        keep = found != key
+        keep = ~easy_edge_mask(graph, h_index, t_index, r_index)
         weight = (graph.edge_weight * keep).repeat_interleave(2)         # undirected() interleaves an edge and its flip
         masked = data.Graph(base.edge_list, edge_weight=weight, num_node=base.num_node, num_relation=base.num_relation)
         full_index = rspmm.graph_index(base.adjacency.transpose(0, 1))
