@@ -70,6 +70,6 @@ def test_operator_rejects_cpu_tensors_and_unknown_ops():
         F.generalized_rspmm(sparse, torch.zeros(2, 4), torch.zeros(2, 4), mul="rotate")
     with pytest.raises(RuntimeError):
         F.generalized_rspmm(sparse, torch.zeros(2, 4), torch.zeros(2, 4, 1))
-    # torchdrug's six autograd Functions, plus the fused `+ boundary` form of this library
+    # torchdrug's six autograd Functions, plus the two fused `+ boundary` forms of this library
     assert {n for n in dir(F) if n.startswith("RSPMM")} == {
-        "RSPMM%s%sFunction" % (s, m) for s in ("Add", "Min", "Max") for m in ("Mul", "Add")} | {"RSPMMAddBoundaryFunction"}
+        "RSPMM%s%sFunction" % (s, m) for s in ("Add", "Min", "Max") for m in ("Mul", "Add")} | {"RSPMMAddBoundaryFunction", "RSPMMAddOneHotFunction"}

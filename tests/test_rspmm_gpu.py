@@ -344,6 +344,23 @@ def test_forward_with_boundary_addend(cuda):
             assert all(torch.equal(a.grad, b.grad) for a, b in zip(fused, plain))
         with pytest.raises(RuntimeError):
             F.rspmm_add_boundary(sparse, relation, input, boundary[:, :-1])
+        # one-hot boundary (model.py:106-109) in sparse form: values and gradients of the dense formulation
+        batch, width = 8, 25
+        node_index = torch.randint(90, (batch,), device=cuda)
+        query = torch.from_numpy(util.random_dense(batch, width, 5)).to(cuda)
+        for mul in ("mul", "add"):
+            fused = [t.clone().requires_grad_() for t in (relation, input, query)]
+            plain = [t.clone().requires_grad_() for t in (relation, input, query)]
+            out = F.rspmm_add_one_hot(sparse, fused[0], fused[1], node_index, fused[2], mul)
+            dense = torch.zeros(90, batch, width, device=cuda)
+            dense = dense.index_put((node_index, torch.arange(batch, device=cuda)), plain[2], accumulate=True)
+            want = F.generalized_rspmm(sparse, plain[0], plain[1], sum="add", mul=mul) + dense.flatten(1)
+            assert torch.equal(out, want)
+            out.backward(upstream)
+            want.backward(upstream)
+            assert all(torch.equal(a.grad, b.grad) for a, b in zip(fused, plain))
+        with pytest.raises(RuntimeError):
+            F.rspmm_add_one_hot(sparse, relation, input, node_index[:-1], query)
     finally:
         lib.ultra_rspmm_set_tuning(256, 0, 0)
         F.clear_index_cache()

@@ -19,7 +19,7 @@ import torch
 from . import _lib
 
 __all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
-           "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "RSPMMAddBoundaryFunction", "rspmm_pna", "LayerEpilogueFunction",
+           "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "RSPMMAddBoundaryFunction", "rspmm_add_one_hot", "RSPMMAddOneHotFunction", "rspmm_pna", "LayerEpilogueFunction",
            "layer_norm_relu_residual_into", "score_head", "fused_linear_supported",
            "linear_norm_relu_residual_into", "score_head_linear", "attach_index"]
 
@@ -431,6 +431,54 @@ class RSPMMAddBoundaryFunction(torch.autograd.Function):
             relation, input, None, output_grad.contiguous(), "add", ctx.mul,
             need_relation=ctx.needs_input_grad[1], need_input=ctx.needs_input_grad[2])
         return None, relation_grad, input_grad, output_grad if ctx.needs_input_grad[3] else None, None
+
+
+class RSPMMAddOneHotFunction(torch.autograd.Function):
+    """`generalized_rspmm(sum="add") + boundary` for the one-hot boundary condition of NBFNet (reference model.py:106-109:
+    zeros with query[b] at node index[b] of column block b): the boundary is applied as B row updates and its gradient is
+    B gathered rows, so neither the (N, D) boundary nor its (N, D) gradient - which autograd would otherwise sum over all
+    layers - is ever touched."""
+
+    @staticmethod
+    def forward(ctx, sparse, relation, input, node_index, query, mul):
+        index = graph_index(sparse)
+        relation, input = relation.contiguous(), input.contiguous()
+        ctx.index, ctx.mul = index, mul
+        ctx.save_for_backward(relation, input, node_index)
+        output = index.forward(relation, input, "add", mul)
+        batch, width = query.shape
+        columns = torch.arange(batch, device=query.device)
+        output.view(output.shape[0], batch, width)[node_index, columns] += query
+        return output
+
+    @staticmethod
+    def backward(ctx, output_grad):
+        relation, input, node_index = ctx.saved_tensors
+        output_grad = output_grad.contiguous()
+        relation_grad, input_grad = ctx.index.backward(
+            relation, input, None, output_grad, "add", ctx.mul,
+            need_relation=ctx.needs_input_grad[1], need_input=ctx.needs_input_grad[2])
+        query_grad = None
+        if ctx.needs_input_grad[4]:
+            batch = node_index.shape[0]
+            columns = torch.arange(batch, device=output_grad.device)
+            query_grad = output_grad.view(output_grad.shape[0], batch, -1)[node_index, columns]
+        return None, relation_grad, input_grad, None, query_grad, None
+
+
+def rspmm_add_one_hot(sparse, relation, input, node_index, query, mul="mul"):
+    """`generalized_rspmm(sparse, relation, input, sum="add", mul=mul) + boundary` where boundary (N, B * d) is zero except
+    `query[b]` (B, d) at row `node_index[b]`, columns [b * d, (b + 1) * d) (reference model.py:106-109 + layer.py:357-358).
+    Differentiable w.r.t. relation, input and query."""
+    _check_operands(sparse, relation, input)
+    if mul not in _MUL_OPS:
+        raise ValueError("Unknown multiplication `%s`" % mul)
+    if sparse.requires_grad:
+        raise RuntimeError("gradient w.r.t. the sparse values is outside the rspmm hot path")
+    if query.dim() != 2 or node_index.shape != (query.shape[0],) or query.shape[0] * query.shape[1] != input.shape[1] \
+            or query.dtype != input.dtype or sparse.size(0) != sparse.size(1):
+        raise RuntimeError("`query` must be (B, d) with B * d == input.size(1), `node_index` (B,), and `sparse` square")
+    return RSPMMAddOneHotFunction.apply(sparse, relation, input, node_index, query, mul)
 
 
 def rspmm_add_boundary(sparse, relation, input, boundary, mul="mul"):

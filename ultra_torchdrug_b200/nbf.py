@@ -30,8 +30,9 @@ generalized_rspmm = rspmm.generalized_rspmm
 MESSAGE_TO_MUL = {"transe": "add", "distmult": "mul"}
 
 
-def _aggregate(adjacency, relation_input, input, boundary, degree_out, aggregate_func, mul, eps):
-    """The operator calls and post-ops of one message-passing step (reference layer.py:133-180, 335-382)."""
+def _aggregate(adjacency, relation_input, input, boundary, degree_out, aggregate_func, mul, eps, one_hot=None):
+    """The operator calls and post-ops of one message-passing step (reference layer.py:133-180, 335-382).
+    `one_hot = (node_index, query)`: the boundary in its sparse form, when the caller knows it (bellmanford loops)."""
     def op(sum, rel=relation_input, x=input):
         return generalized_rspmm(adjacency, rel, x, sum=sum, mul=mul)
 
@@ -39,6 +40,8 @@ def _aggregate(adjacency, relation_input, input, boundary, degree_out, aggregate
     name = aggregate_func[:-len("_nobound")] if not bounded else aggregate_func
     if name == "sum":
         if bounded and input.is_cuda and generalized_rspmm is rspmm.generalized_rspmm:
+            if one_hot is not None:                      # B row updates instead of an (N, D) addend and its (N, D) gradient
+                return rspmm.rspmm_add_one_hot(adjacency, relation_input, input, one_hot[0], one_hot[1], mul)
             return rspmm.rspmm_add_boundary(adjacency, relation_input, input, boundary, mul)   # one pass
         update = op("add")
         return update + boundary if bounded else update
@@ -96,7 +99,7 @@ class _RelationalConvBase(nn.Module):
         relation_input = self.relation_input(graph, batch_size)
         adjacency = graph.adjacency.transpose(0, 1)
         update = _aggregate(adjacency, relation_input, flat_input, boundary, degree_out, self.aggregate_func,
-                            MESSAGE_TO_MUL[self.message_func], self.eps)
+                            MESSAGE_TO_MUL[self.message_func], self.eps, getattr(graph, "boundary_one_hot", None))
         return update.view(len(update), batch_size, -1)
 
     def combine(self, input, update, residual=None):
@@ -326,6 +329,7 @@ class TransferNBFNet(nn.Module):
         boundary = _one_hot_boundary(graph.num_node, h_index, query)
         with graph.node():
             graph.boundary = boundary
+        graph.boundary_one_hot = (h_index, query)            # the same condition in sparse form (see _aggregate)
         hidden = _run_layers(self.layers, graph, boundary, self.short_cut)
         return torch.cat([hidden, query.expand(graph.num_node, -1, -1)], dim=-1)
 
@@ -406,6 +410,7 @@ class CustomNBFNetFull(nn.Module):
         boundary = _one_hot_boundary(graph.num_node, h_index, query)
         with graph.node():
             graph.boundary = boundary
+        graph.boundary_one_hot = (h_index, query)
         return _run_layers(self.layers, graph, boundary, self.short_cut).transpose(1, 0)   # (B, num_rel, dim)
 
 
