@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ULTRA_RSPMM_ABI_VERSION 4
+#define ULTRA_RSPMM_ABI_VERSION 5
 
 /* status codes (0 = ok).  For ULTRA_RSPMM_ERR_CUDA the cudaError_t is kept per thread, see
  * ultra_rspmm_last_cuda_error(). */
@@ -107,12 +107,39 @@ const char *ultra_rspmm_status_string(int status);
 /* number of kernels this library has enqueued since load / last reset (process-wide counter) */
 int64_t ultra_rspmm_launch_count(void);
 void ultra_rspmm_launch_count_reset(void);
+/* How the most recent pass of each kind was launched (process-wide, for tests and profiles): which kernel served it
+ * and with which template switches.  pass: 0 = forward (csr order), 1 = gradient w.r.t. input (csc order),
+ * 2 = gradient w.r.t. relation. */
+enum { ULTRA_RSPMM_PASS_FORWARD = 0, ULTRA_RSPMM_PASS_GRAD_INPUT = 1, ULTRA_RSPMM_PASS_GRAD_RELATION = 2 };
+enum {
+    ULTRA_RSPMM_KERNEL_NONE = 0,
+    ULTRA_RSPMM_KERNEL_SEG_REDUCE = 1,    /* generic gather-combine-reduce (sum / min / max, all three orders)        */
+    ULTRA_RSPMM_KERNEL_SEG_GATED = 2,     /* min / max backward (all-ties gate)                                       */
+    ULTRA_RSPMM_KERNEL_SEG_PNA = 3,       /* four PNA aggregates in one pass                                          */
+    ULTRA_RSPMM_KERNEL_ROWS_IN_SMEM = 4,  /* few-row operands: the gathered slab is staged in shared memory           */
+    ULTRA_RSPMM_KERNEL_DST_BLOCKED = 5    /* grad_relation with grad_output rows of a destination block in shared memory */
+};
+typedef struct ultra_rspmm_pass_info {
+    int32_t kernel;    /* ULTRA_RSPMM_KERNEL_*                                        */
+    int32_t vec;       /* features per lane (slab = 32 * vec features; 64 for ROWS_IN_SMEM) */
+    int32_t keep;      /* L2 eviction-priority hints on (slab > 24 MiB)               */
+    int32_t grouped;   /* grouped task list (short rows share a warp task)            */
+    int32_t packed;    /* edge ids packed into one 32-bit word                        */
+    int32_t n_task;    /* tasks per slab                                              */
+    int32_t n_slab;    /* feature slabs                                               */
+    int32_t n_split;   /* segments folded from partial rows by the combine pass       */
+} ultra_rspmm_pass_info_t;
+int ultra_rspmm_last_pass_info(int32_t pass, ultra_rspmm_pass_info_t *info);
 /* tuning knobs (process-wide; 0 keeps the current value).  chunk: edges per task for indexes built
  * afterwards (default 256; rows of up to chunk / 4 edges are grouped, see `gtask`).  variant: L2 eviction-priority hints of the gather kernels - 0 = automatic
  * (on when the gathered slab exceeds 24 MiB), 1 = never, 2 = always.
  * l2_budget_bytes: L2 bytes the gathered operand's slab (rows x slab width) may occupy; the slab width
  * (512 / 256 / 128 bytes per row) is the widest that fits (default: unlimited, i.e. always 512). */
 int ultra_rspmm_set_tuning(int32_t chunk, int32_t variant, int64_t l2_budget_bytes);
+/* Rows-in-shared-memory kernel for operands with at most 864 rows (the graph of relations, reference
+ * rel_model.py:253-257): 0 = never, 1 = automatic (default: when the slab refills are small against the edge work),
+ * 2 = whenever the operand fits (tests). */
+int ultra_rspmm_set_staged(int32_t mode);
 
 /* ---- index build (replaces sparse.coalesce() + coo2csr3d) ---------- */
 /* Bytes needed for the index arrays (upper bound, from the raw edge count) and for scratch. */

@@ -87,6 +87,62 @@ def backward(csr, relation, input, output, grad_output, sum="add", mul="mul"):
     return grad_relation, grad_input
 
 
+def forward_arg(csr, relation, input, sum="max", mul="mul"):
+    """min/max forward with the arg-index (position of the first edge, in coalesced order, attaining the extremum)."""
+    relation = np.ascontiguousarray(relation, dtype=np.float32)
+    input = np.ascontiguousarray(input, dtype=np.float32)
+    output = np.empty((csr.shape[0], input.shape[1]), dtype=np.float32)
+    argidx = np.empty((csr.shape[0], input.shape[1]), dtype=np.int64)
+    status = lib().rspmm_ref_forward_arg_f32(
+        ctypes.c_int64(csr.shape[0]), ctypes.c_int64(input.shape[1]), _ptr(csr.row_ptr), _ptr(csr.col),
+        _ptr(csr.layer), _ptr(csr.val), _ptr(relation), _ptr(input), _ptr(output), _ptr(argidx),
+        ctypes.c_int(SUM_CODE[sum]), ctypes.c_int(MUL_CODE[mul]))
+    if status:
+        raise RuntimeError("rspmm_ref_forward_arg_f32 failed with %d" % status)
+    return output, argidx
+
+
+def forward_f64(csr, relation, input, mul="mul", absolute=False):
+    """sum aggregation with fp32 operands up-cast to double (the value fp32 sums are compared with);
+    `absolute=True` evaluates it on |w|, |relation|, |input|: the sum of |terms| that scales the tolerance."""
+    relation = np.ascontiguousarray(relation, dtype=np.float32)
+    input = np.ascontiguousarray(input, dtype=np.float32)
+    val = csr.val
+    if absolute:
+        relation, input, val = np.abs(relation), np.abs(input), np.abs(val)
+    output = np.empty((csr.shape[0], input.shape[1]), dtype=np.float64)
+    status = lib().rspmm_ref_forward_f64(
+        ctypes.c_int64(csr.shape[0]), ctypes.c_int64(input.shape[1]), _ptr(csr.row_ptr), _ptr(csr.col),
+        _ptr(csr.layer), _ptr(val), _ptr(relation), _ptr(input), _ptr(output), ctypes.c_int(MUL_CODE[mul]))
+    if status:
+        raise RuntimeError("rspmm_ref_forward_f64 failed with %d" % status)
+    return output
+
+
+def backward_f64(csr, relation, input, output, grad_output, sum="add", mul="mul", absolute=False):
+    """Both gradients accumulated in double; the min/max gate is evaluated in fp32 like the reference's.
+    `absolute=True`: the ungated sums of |terms| (tolerance scale)."""
+    relation = np.ascontiguousarray(relation, dtype=np.float32)
+    input = np.ascontiguousarray(input, dtype=np.float32)
+    grad_output = np.ascontiguousarray(grad_output, dtype=np.float32)
+    val = csr.val
+    if absolute:
+        relation, input, grad_output, val, sum, output = np.abs(relation), np.abs(input), np.abs(grad_output), \
+            np.abs(val), "add", None
+    if sum != "add":
+        output = np.ascontiguousarray(output, dtype=np.float32)
+    grad_relation = np.empty(relation.shape, dtype=np.float64)
+    grad_input = np.empty(input.shape, dtype=np.float64)
+    status = lib().rspmm_ref_backward_f64(
+        ctypes.c_int64(csr.shape[0]), ctypes.c_int64(csr.shape[1]), ctypes.c_int64(csr.shape[2]),
+        ctypes.c_int64(input.shape[1]), _ptr(csr.row_ptr), _ptr(csr.col), _ptr(csr.layer), _ptr(val),
+        _ptr(relation), _ptr(input), _ptr(output) if sum != "add" else ctypes.c_void_p(0), _ptr(grad_output),
+        _ptr(grad_relation), _ptr(grad_input), ctypes.c_int(SUM_CODE[sum]), ctypes.c_int(MUL_CODE[mul]))
+    if status:
+        raise RuntimeError("rspmm_ref_backward_f64 failed with %d" % status)
+    return grad_relation, grad_input
+
+
 def num_threads():
     return int(lib().rspmm_ref_num_threads())
 

@@ -130,3 +130,105 @@ int rspmm_ref_backward_f32(int64_t n_out, int64_t n_in, int64_t n_rel, int64_t d
     }
     return 0;
 }
+
+/* ---- variants used by the full-size parity tests (tests/test_full_size_gpu.py) -------------------
+ * Same loop nest as above, evaluated on a column subsample of the operands:
+ *   rspmm_ref_forward_arg_f32 : min/max forward that also records the arg-index = position (in coalesced
+ *                               order) of the FIRST edge attaining the extremum, -1 for empty rows;
+ *   rspmm_ref_forward_f64     : fp32 operands up-cast to double, accumulated in double - the "true value"
+ *                               the fp32 sums of the CUDA path are compared with (its summation order
+ *                               legitimately differs from any sequential one);
+ *   rspmm_ref_backward_f64    : likewise for the two gradients; the min/max gate compares the saved fp32
+ *                               output with the message recomputed in fp32, as the reference does. */
+int rspmm_ref_forward_arg_f32(int64_t n_out, int64_t dim, const int64_t *row_ptr, const int64_t *col,
+                              const int64_t *layer, const float *val, const float *relation,
+                              const float *input, float *output, int64_t *argidx, int sum_op, int mul_op) {
+    if (sum_op != SUM_MIN && sum_op != SUM_MAX) return 1;
+    if (mul_op < 0 || mul_op > 1) return 1;
+    const float zero = nary_zero(sum_op);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n_out; ++i) {
+        float *out = output + i * dim;
+        int64_t *arg = argidx + i * dim;
+        for (int64_t d = 0; d < dim; ++d) { out[d] = zero; arg[d] = -1; }
+        for (int64_t p = row_ptr[i]; p < row_ptr[i + 1]; ++p) {
+            const float *rel = relation + layer[p] * dim;
+            const float *in = input + col[p] * dim;
+            const float w = val[p];
+            for (int64_t d = 0; d < dim; ++d) {
+                const float x = mul_op == MUL_MUL ? rel[d] * in[d] : rel[d] + in[d];
+                const float y = w * x;
+                const int better = sum_op == SUM_MAX ? (y > out[d]) : (y < out[d]);
+                /* strict improvement moves the candidate, ties keep the earlier edge; a message equal to the
+                 * identity (+-FLT_MAX) is still attained by an edge */
+                if (better || (arg[d] < 0 && y == out[d])) arg[d] = p;
+                if (sum_op == SUM_MAX) out[d] = out[d] > y ? out[d] : y;
+                else out[d] = out[d] < y ? out[d] : y;
+            }
+        }
+    }
+    return 0;
+}
+
+int rspmm_ref_forward_f64(int64_t n_out, int64_t dim, const int64_t *row_ptr, const int64_t *col,
+                          const int64_t *layer, const float *val, const float *relation,
+                          const float *input, double *output, int mul_op) {
+    if (mul_op < 0 || mul_op > 1) return 1;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n_out; ++i) {
+        double *out = output + i * dim;
+        for (int64_t d = 0; d < dim; ++d) out[d] = 0.0;
+        for (int64_t p = row_ptr[i]; p < row_ptr[i + 1]; ++p) {
+            const float *rel = relation + layer[p] * dim;
+            const float *in = input + col[p] * dim;
+            const double w = val[p];
+            if (mul_op == MUL_MUL)
+                for (int64_t d = 0; d < dim; ++d) out[d] += w * ((double)rel[d] * (double)in[d]);
+            else
+                for (int64_t d = 0; d < dim; ++d) out[d] += w * ((double)rel[d] + (double)in[d]);
+        }
+    }
+    return 0;
+}
+
+int rspmm_ref_backward_f64(int64_t n_out, int64_t n_in, int64_t n_rel, int64_t dim,
+                           const int64_t *row_ptr, const int64_t *col, const int64_t *layer,
+                           const float *val, const float *relation, const float *input,
+                           const float *output, const float *grad_output, double *grad_relation,
+                           double *grad_input, int sum_op, int mul_op) {
+    if (sum_op < 0 || sum_op > 2 || mul_op < 0 || mul_op > 1) return 1;
+    memset(grad_relation, 0, (size_t)(n_rel * dim) * sizeof(double));
+    memset(grad_input, 0, (size_t)(n_in * dim) * sizeof(double));
+    /* feature columns are independent: every thread owns a block of columns and walks all edges in coalesced
+     * order, so the sums are sequential (deterministic) and need no atomics */
+#pragma omp parallel
+    {
+#ifdef _OPENMP
+        const int64_t threads = omp_get_num_threads(), self = omp_get_thread_num();
+#else
+        const int64_t threads = 1, self = 0;
+#endif
+        const int64_t d0 = dim * self / threads, d1 = dim * (self + 1) / threads;
+        for (int64_t i = 0; i < n_out && d0 < d1; ++i) {
+            const float *g = grad_output + i * dim;
+            const float *out = output ? output + i * dim : 0;
+            for (int64_t p = row_ptr[i]; p < row_ptr[i + 1]; ++p) {
+                const float *rel = relation + layer[p] * dim;
+                const float *in = input + col[p] * dim;
+                double *g_rel = grad_relation + layer[p] * dim;
+                double *g_in = grad_input + col[p] * dim;
+                const float w = val[p];
+                for (int64_t d = d0; d < d1; ++d) {
+                    if (sum_op != SUM_ADD) {
+                        const float x = mul_op == MUL_MUL ? rel[d] * in[d] : rel[d] + in[d];
+                        if (!(out[d] == w * x)) continue;
+                    }
+                    const double up = (double)g[d] * (double)w;
+                    g_rel[d] += mul_op == MUL_MUL ? up * (double)in[d] : up;
+                    g_in[d] += mul_op == MUL_MUL ? up * (double)rel[d] : up;
+                }
+            }
+        }
+    }
+    return 0;
+}

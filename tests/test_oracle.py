@@ -177,3 +177,34 @@ def test_invalid_arguments():
         rspmm_oracle.rspmm_forward(np.array([[0], [5], [0]]), np.ones(1), (1, 1, 1), np.zeros((1, 1)), np.zeros((1, 1)))
     with pytest.raises(ValueError):
         rspmm_oracle.rspmm_forward(np.zeros((3, 0)), np.zeros(0), (1, 2, 1), np.zeros((1, 1)), np.zeros((1, 1)))
+
+
+@pytest.mark.parametrize("sum,mul", util.OPS)
+def test_c_port_exact_variants_match_numpy_oracle(sum, mul):
+    """The double-accumulating / arg-index entry points of the C restatement (what the full-size GPU parity tests
+    compare with) against the numpy oracle, on a graph with duplicates, empty rows, random weights and exact ties."""
+    indices, values = util.random_coo(70, 50, 6, 900, seed=21, duplicates=60, weights="random", skew=True)
+    shape = (70, 50, 6)
+    relation, input = util.random_dense(6, 20, 1, ties=True), util.random_dense(50, 20, 2, ties=True)
+    grad = util.random_dense(70, 20, 3)
+    csr = cpu_ref.CsrOperand(indices, values, shape)
+    if sum == "add":
+        want, _ = rspmm_oracle.rspmm_forward(indices, values, shape, relation, input, "add", mul, dtype=np.float64)
+        np.testing.assert_allclose(cpu_ref.forward_f64(csr, relation, input, mul), want, rtol=1e-12, atol=1e-12)
+        scale, _ = rspmm_oracle.rspmm_forward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), "add", mul,
+                                              dtype=np.float64)
+        np.testing.assert_allclose(cpu_ref.forward_f64(csr, relation, input, mul, absolute=True), scale, rtol=1e-12)
+        out = want.astype(np.float32)
+    else:
+        out, arg = cpu_ref.forward_arg(csr, relation, input, sum, mul)
+        want, want_arg = rspmm_oracle.rspmm_forward(indices, values, shape, relation, input, sum, mul)
+        assert np.array_equal(out, want) and np.array_equal(arg, want_arg)
+    got = cpu_ref.backward_f64(csr, relation, input, out, grad, sum, mul)
+    want = rspmm_oracle.rspmm_backward(indices, values, shape, relation, input, out, grad, sum, mul, dtype=np.float64)
+    for a, b in zip(got, want):
+        np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-10)
+    got = cpu_ref.backward_f64(csr, relation, input, out, grad, sum, mul, absolute=True)
+    want = rspmm_oracle.rspmm_backward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), None, np.abs(grad),
+                                       "add", mul, dtype=np.float64)
+    for a, b in zip(got, want):
+        np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-10)

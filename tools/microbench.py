@@ -62,6 +62,9 @@ def main():
     parser.add_argument("--l2mb", type=int, default=0, help="L2 budget (MiB) used to pick the slab width")
     parser.add_argument("--variant", type=int, default=0, help="0 auto, 1 no L2 eviction hints, 2 hints always")
     parser.add_argument("--relgraph", action="store_true", help="dense 4-relation graph over R' nodes instead")
+    parser.add_argument("--staged", type=int, default=-1, help="rows-in-shared-memory kernel: 0 off, 1 auto, 2 always")
+    parser.add_argument("--uniform", default=None, help="E:N:R - uniform random graph (BASELINE configs[4] sweep shapes)")
+    parser.add_argument("--dim", type=int, default=0, help="feature width (overrides --batch * 64)")
     args = parser.parse_args()
     device = torch.device("cuda", 0)
     peak = 6551.4
@@ -72,13 +75,23 @@ def main():
     if args.chunk or args.l2mb or args.variant:
         from ultra_torchdrug_b200 import _lib
         _lib.lib().ultra_rspmm_set_tuning(args.chunk, args.variant, args.l2mb << 20)
-    edge_list, n, r = synthetic.named_graph(args.graph, skew=args.skew, relation_skew=args.relskew)
+    if args.staged >= 0:
+        from ultra_torchdrug_b200 import _lib
+        _lib.lib().ultra_rspmm_set_staged(args.staged)
+    if args.uniform:
+        e_raw, n, r = (int(v) for v in args.uniform.split(":"))
+        generator = torch.Generator().manual_seed(1024)
+        edge_list = torch.stack([torch.randint(n, (e_raw,), generator=generator), torch.randint(n, (e_raw,), generator=generator),
+                                 torch.randint(r, (e_raw,), generator=generator)], dim=1)
+        args.graph = "uniform " + args.uniform
+    else:
+        edge_list, n, r = synthetic.named_graph(args.graph, skew=args.skew, relation_skew=args.relskew)
     if args.relgraph:
         nodes = r
         grid = torch.cartesian_prod(torch.arange(nodes), torch.arange(nodes), torch.arange(4))
         edge_list, n, r = grid[:, [1, 0, 2]].contiguous(), nodes, 4
     sparse = synthetic.operator_operand(edge_list, n, r, device)
-    d = args.batch * 64
+    d = args.dim or args.batch * 64
     torch.cuda.synchronize()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     F.graph_index(sparse)  # warm (CUB kernels load lazily)
@@ -111,10 +124,11 @@ def main():
     if args.sum == "add":        # the two forms the layers actually call: + boundary, and the cat-free blocked layout
         results["fwd+addend"] = timed(lambda i: index.forward(relation, inputs[i % copies], "add", args.mul,
                                                                addend=grads[i % copies]), args.iters)
-        buffers = [torch.randn(n, args.batch, 128, device=device, generator=generator) for _ in range(copies)]
-        results["fwd_blocked"] = timed(lambda i: index.forward_blocked(relation, buffers[i % copies], buffers[i % copies],
-                                                                       64, 0, 64, args.mul, addend=grads[i % copies]),
-                                       args.iters)
+        if d == args.batch * 64 and n * d < (1 << 30):
+            buffers = [torch.randn(n, args.batch, 128, device=device, generator=generator) for _ in range(copies)]
+            results["fwd_blocked"] = timed(lambda i: index.forward_blocked(relation, buffers[i % copies], buffers[i % copies],
+                                                                           64, 0, 64, args.mul, addend=grads[i % copies]),
+                                           args.iters)
     for name, ms in results.items():
         gb = edge_model_bytes(n, r, e, d, name, gated=args.sum != "add") / 1e9
         print("%-13s %8.3f ms   %8.1f GB/s edge-model  (%.1f%% of measured HBM %.0f GB/s)   %.2f G edge-msg/s"

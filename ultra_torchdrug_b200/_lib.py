@@ -8,7 +8,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 OK, ERR_ARG, ERR_WORKSPACE, ERR_CUDA, ERR_INDEX, ERR_DTYPE, ERR_RANGE = range(7)
 SUM_CODE = {"add": 0, "min": 1, "max": 2}
@@ -33,8 +33,19 @@ class Index(ctypes.Structure):
                 ("csr", Order), ("csc", Order), ("rel", Order), ("merge_perm", c_void_p), ("merge_start", c_void_p)]
 
 
+class PassInfo(ctypes.Structure):
+    """`ultra_rspmm_pass_info_t`"""
+    _fields_ = [("kernel", c_int32), ("vec", c_int32), ("keep", c_int32), ("grouped", c_int32), ("packed", c_int32),
+                ("n_task", c_int32), ("n_slab", c_int32), ("n_split", c_int32)]
+
+
+PASS_FORWARD, PASS_GRAD_INPUT, PASS_GRAD_RELATION = 0, 1, 2
+KERNEL_NAMES = {0: "none", 1: "seg_reduce", 2: "seg_gated", 3: "seg_pna", 4: "rows_in_smem", 5: "dst_blocked"}
+
 #: every symbol `include/ultra_rspmm.h` declares: name -> (restype, argtypes)
 SYMBOLS = {
+    "ultra_rspmm_last_pass_info": (ctypes.c_int, [c_int32, ctypes.POINTER(PassInfo)]),
+    "ultra_rspmm_set_staged": (ctypes.c_int, [c_int32]),
     "ultra_rspmm_abi_version": (ctypes.c_int, []),
     "ultra_rspmm_last_cuda_error": (ctypes.c_int, []),
     "ultra_rspmm_status_string": (ctypes.c_char_p, [ctypes.c_int]),
@@ -127,6 +138,15 @@ def lib():
                           "`python -m ultra_torchdrug_b200.build --force`" % (handle.ultra_rspmm_abi_version(), ABI_VERSION))
     _lib = handle
     return _lib
+
+
+def pass_info(which):
+    """How the last pass of a kind (PASS_*) was launched: dict of the `ultra_rspmm_pass_info_t` fields + kernel name."""
+    info = PassInfo()
+    check(lib().ultra_rspmm_last_pass_info(which, ctypes.byref(info)), "ultra_rspmm_last_pass_info")
+    result = {name: int(getattr(info, name)) for name, _ in PassInfo._fields_}
+    result["kernel_name"] = KERNEL_NAMES.get(result["kernel"], "?")
+    return result
 
 
 def check(status, where):

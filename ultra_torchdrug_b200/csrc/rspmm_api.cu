@@ -13,10 +13,16 @@ static std::atomic<long long> g_launches{0};
 static thread_local int t_last_cuda_error = 0;
 int g_chunk = 256;
 int g_variant = 0;
+int g_staged = getenv("ULTRA_RSPMM_STAGED") ? atoi(getenv("ULTRA_RSPMM_STAGED")) : 1;
 int g_group_edges = getenv("ULTRA_RSPMM_GROUP") ? atoi(getenv("ULTRA_RSPMM_GROUP")) : -1;
 long long g_l2_budget = 1ll << 40;   // slab narrowing off by default: it lost on every measured shape (profiles/)
 
+static ultra_rspmm_pass_info_t g_pass_info[3] = {};
+
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void note_pass(int pass, const ultra_rspmm_pass_info_t &info) {
+    if (pass >= 0 && pass < 3) g_pass_info[pass] = info;
+}
 
 int fail_cuda(cudaError_t error) {
     t_last_cuda_error = (int)error;
@@ -31,6 +37,12 @@ extern "C" int ultra_rspmm_abi_version(void) { return ULTRA_RSPMM_ABI_VERSION; }
 extern "C" int ultra_rspmm_last_cuda_error(void) { return t_last_cuda_error; }
 extern "C" int64_t ultra_rspmm_launch_count(void) { return g_launches.load(); }
 extern "C" void ultra_rspmm_launch_count_reset(void) { g_launches.store(0); }
+
+extern "C" int ultra_rspmm_last_pass_info(int32_t pass, ultra_rspmm_pass_info_t *info) {
+    if (pass < 0 || pass > 2 || !info) return ULTRA_RSPMM_ERR_ARG;
+    *info = g_pass_info[pass];
+    return ULTRA_RSPMM_OK;
+}
 
 extern "C" const char *ultra_rspmm_status_string(int status) {
     switch (status) {
@@ -50,6 +62,12 @@ extern "C" int ultra_rspmm_set_tuning(int32_t chunk, int32_t variant, int64_t l2
     if (chunk > 0) g_chunk = chunk;
     g_variant = variant;
     if (l2_budget_bytes > 0) g_l2_budget = l2_budget_bytes;
+    return ULTRA_RSPMM_OK;
+}
+
+extern "C" int ultra_rspmm_set_staged(int32_t mode) {
+    if (mode < 0 || mode > 2) return ULTRA_RSPMM_ERR_ARG;
+    g_staged = mode;
     return ULTRA_RSPMM_OK;
 }
 

@@ -181,13 +181,38 @@ __host__ __device__ __forceinline__ int task_rows(int encoded) {
     return (encoded & kGroupTask) ? ((encoded >> 24) & (kGroupRows - 1)) + 1 : 1;
 }
 
+// ---- rows-in-shared-memory kernel (rspmm_staged.cu): operands with few rows, e.g. the graph of relations ------------
+constexpr int kStagedSlab = 64;         // features per slab: a half-warp reads one 256-byte row slab per LDS.128
+constexpr int kStagedMaxRows = 864;     // 864 x 256 B = 216 KB of dynamic shared memory (+ 8 KB static) <= 227 KB per CTA
+constexpr size_t kStagedMaxSmem = (size_t)kStagedMaxRows * kStagedSlab * sizeof(float);
+struct StagedArgs {
+    const int4 *task;         // plain task list of the order
+    const unsigned *packed;   // edge ids, x | y << pack_shift
+    int pack_shift;
+    const float *w;           // null when all weights are 1
+    const float *A;           // gathered operand: n_rows rows, staged slab by slab
+    const float *B;           // relation table (unused for MSG_COPY)
+    float *out;
+    const float *addend;
+    float *partial;
+    unsigned *counter;        // work counter in the workspace (zeroed by the launcher)
+    long long dim;
+    int n_task, n_slab, n_rows, tasks_per_item;
+    long long a_stride, o_stride, o_offset, a_row, o_row;   // blocked layout, as SegArgs (rspmm_kernels.cu)
+    int block, block_shift;
+};
+int launch_rows_in_smem(StagedArgs args, int msg, cudaStream_t stream);
+
 // launch bookkeeping (claimed in bench.py as `gpu_launches`)
 void note_launch();
+// how the last pass of each kind was launched (ultra_rspmm_last_pass_info; read by the parity tests)
+void note_pass(int pass, const ultra_rspmm_pass_info_t &info);
 // per-thread status plumbing shared by the translation units
 int fail_cuda(cudaError_t error);
 extern int g_chunk;    // edges per task for new indexes
 extern int g_variant;  // 0 auto, 1 generic, 2 staged
 extern int g_group_edges;  // rows of up to this many edges are grouped in the grouped task list (-1: chunk / 4, 0: off)
+extern int g_staged;   // rows-in-shared-memory kernel: 0 off, 1 automatic, 2 whenever the operand fits
 extern long long g_l2_budget;  // bytes of L2 the gathered operand's slab may occupy (slab width is chosen to fit)
 
 #define ULTRA_CUDA_OK(expr)                                      \

@@ -570,6 +570,7 @@ __global__ void combine_kernel(const int4 *__restrict__ split, int n_split, cons
 // host-side dispatch
 // ------------------------------------------------------------------------------------------------
 template <typename T> constexpr int wide_vec() { return 16 / sizeof(T); }
+constexpr int FWD = ULTRA_RSPMM_PASS_FORWARD, GIN = ULTRA_RSPMM_PASS_GRAD_INPUT, GREL = ULTRA_RSPMM_PASS_GRAD_RELATION;
 
 // Instantiation budget: the L2-hint (KEEP) and grouped-task variants exist only where they matter - float operands at the
 // full slab width; group tasks never carry an arg-index.  args.keep / args.grouped are set accordingly by run_pass.
@@ -647,10 +648,32 @@ int pick_vec(long long dim, long long rows, std::initializer_list<const void *> 
 }
 
 // one reduction pass + its combine
+// bytes of the partial rows (+ partial arg-indices) of one pass; the work counter of the staged kernel sits right after
+static size_t slot_bytes(const ultra_rspmm_order_t &order, long long dim, size_t elem, bool with_arg) {
+    size_t bytes = align_up((size_t)order.n_slot * dim * elem);
+    if (with_arg) bytes += align_up((size_t)order.n_slot * dim * sizeof(int32_t));
+    return bytes;
+}
+
+// Few-row operands (the graph of relations): the gathered operand's 64-feature slab fits shared memory and every edge
+// reads it from there (rspmm_staged.cu).  Worth it when the refills (one per CTA and slab change) are small against the
+// edge work: at least ~16 edges per staged row and SM.
 template <typename T, int SUM, int MSG, bool B_TABLE, bool ARG>
-int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, const T *B, long long rows_gathered, T *out,
-             int32_t *arg_out, long long dim, void *workspace, cudaStream_t stream, const T *addend = nullptr,
-             const BlockedLayout layout = BlockedLayout()) {
+bool staged_applies(const ultra_rspmm_order_t &order, long long rows_gathered, long long dim, int vec, long long nnz,
+                    const void *workspace, size_t workspace_bytes, size_t counter_at) {
+    if (!std::is_same<T, float>::value || SUM != ULTRA_RSPMM_SUM_ADD || !B_TABLE || ARG) return false;
+    if (g_staged == 0 || vec != 4 || order.pack_shift <= 0 || rows_gathered <= 0 || rows_gathered > kStagedMaxRows) return false;
+    if (!workspace || workspace_bytes < counter_at + sizeof(unsigned)) return false;
+    if (g_staged == 2) return true;
+    const long long slabs = (dim + kStagedSlab - 1) / kStagedSlab;
+    return nnz * slabs >= 16ll * 148 * rows_gathered;
+}
+
+template <typename T, int SUM, int MSG, bool B_TABLE, bool ARG>
+int run_pass(int pass, const ultra_rspmm_order_t &order, long long nnz, bool unit_weight, const T *A, const T *B,
+             long long rows_gathered, T *out, int32_t *arg_out, long long dim, void *workspace, size_t workspace_bytes,
+             cudaStream_t stream,
+             const T *addend = nullptr, const BlockedLayout layout = BlockedLayout()) {
     SegArgs<T> args;
     args.ptr = order.ptr;
     args.task = (const int4 *)order.task;
@@ -677,6 +700,37 @@ int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, con
     args.o_offset = layout.o_offset;
     const int vec = pick_vec<T>(dim, rows_gathered, {A, B, out, workspace, addend});
     args.n_slab = (int)((dim + 32 * vec - 1) / (32 * vec));
+    ultra_rspmm_pass_info_t info = {};
+    info.packed = order.pack_shift > 0;
+    info.n_split = order.n_split;
+    const size_t counter_at = slot_bytes(order, dim, sizeof(T), ARG);
+    if (staged_applies<T, SUM, MSG, B_TABLE, ARG>(order, rows_gathered, dim, vec, nnz, workspace, workspace_bytes, counter_at)) {
+        StagedArgs staged = {};
+        staged.task = (const int4 *)order.task;
+        staged.packed = (const unsigned *)order.packed;
+        staged.pack_shift = order.pack_shift;
+        staged.w = unit_weight ? nullptr : (const float *)order.w;
+        staged.A = (const float *)A;
+        staged.B = (const float *)B;
+        staged.out = (float *)out;
+        staged.addend = (const float *)addend;
+        staged.partial = (float *)workspace;
+        staged.counter = (unsigned *)((char *)workspace + counter_at);
+        staged.dim = dim;
+        staged.n_task = order.n_task;
+        staged.n_rows = (int)rows_gathered;
+        staged.a_stride = args.a_stride; staged.o_stride = args.o_stride; staged.o_offset = args.o_offset;
+        staged.a_row = args.a_row; staged.o_row = args.o_row;
+        staged.block = args.block; staged.block_shift = args.block_shift;
+        int status = launch_rows_in_smem(staged, MSG, stream);
+        if (status) return status;
+        info.kernel = ULTRA_RSPMM_KERNEL_ROWS_IN_SMEM;
+        info.vec = 4;
+        info.n_task = order.n_task;
+        info.n_slab = (int)((dim + kStagedSlab - 1) / kStagedSlab);
+        note_pass(pass, info);
+        return launch_combine<T, SUM, ARG>(order, args.partial, args.partial_arg, out, arg_out, dim, stream, addend, layout);
+    }
     const bool tuned = sizeof(T) == 4 && vec == 4;
     args.keep = tuned && (g_variant == 2 || (g_variant == 0 && rows_gathered * 32 * vec * (long long)sizeof(T) > (24ll << 20)));
     // short rows are walked several per warp: the grouped task list (built only for orders whose segments average
@@ -691,6 +745,13 @@ int run_pass(const ultra_rspmm_order_t &order, bool unit_weight, const T *A, con
     else if (vec == 2) status = launch_seg<T, 2, SUM, MSG, B_TABLE, ARG>(args, stream);
     else status = launch_seg<T, 1, SUM, MSG, B_TABLE, ARG>(args, stream);
     if (status) return status;
+    info.kernel = ULTRA_RSPMM_KERNEL_SEG_REDUCE;
+    info.vec = vec;
+    info.keep = args.keep;
+    info.grouped = args.grouped;
+    info.n_task = args.n_task;
+    info.n_slab = args.n_slab;
+    note_pass(pass, info);
     return launch_combine<T, SUM, ARG>(order, args.partial, args.partial_arg, out, arg_out, dim, stream, addend,
                                        layout);
 }
@@ -713,8 +774,8 @@ int launch_gated(const GatedArgs<T> &args, cudaStream_t stream) {
 }
 
 template <typename T, int MSG, bool P_TABLE>
-int run_gated(const ultra_rspmm_order_t &order, bool unit_weight, const T *G, const T *O, const T *P, const T *S,
-              long long rows_gathered, T *out, long long dim, void *workspace, cudaStream_t stream) {
+int run_gated(int pass, const ultra_rspmm_order_t &order, bool unit_weight, const T *G, const T *O, const T *P, const T *S,
+              long long rows_gathered, T *out, long long dim, void *workspace, size_t, cudaStream_t stream) {
     GatedArgs<T> args;
     args.task = (const int4 *)order.task;
     args.edge = (const int2 *)order.edge;
@@ -734,40 +795,49 @@ int run_gated(const ultra_rspmm_order_t &order, bool unit_weight, const T *G, co
     else if (vec == 2) status = launch_gated<T, 2, MSG, P_TABLE>(args, stream);
     else status = launch_gated<T, 1, MSG, P_TABLE>(args, stream);
     if (status) return status;
+    ultra_rspmm_pass_info_t info = {};
+    info.kernel = ULTRA_RSPMM_KERNEL_SEG_GATED;
+    info.vec = vec;
+    info.keep = args.keep;
+    info.packed = order.pack_shift > 0;
+    info.n_task = args.n_task;
+    info.n_slab = args.n_slab;
+    info.n_split = order.n_split;
+    note_pass(pass, info);
     return launch_combine<T, ULTRA_RSPMM_SUM_ADD, false>(order, args.partial, nullptr, out, nullptr, dim, stream);
 }
 
 template <typename T, int SUM>
 int forward_sum(const ultra_rspmm_index_t &ix, const T *relation, const T *input, T *output, int32_t *argidx,
-                long long dim, int mul_op, void *ws, cudaStream_t stream, const T *addend = nullptr) {
+                long long dim, int mul_op, void *ws, size_t ws_bytes, cudaStream_t stream, const T *addend = nullptr) {
     const bool unit = ix.unit_weight != 0;
     if (SUM != ULTRA_RSPMM_SUM_ADD && argidx) {
         if (mul_op == ULTRA_RSPMM_MUL_MUL)
-            return run_pass<T, SUM, MSG_MUL, true, true>(ix.csr, unit, input, relation, ix.n_in, output, argidx, dim, ws, stream);
-        return run_pass<T, SUM, MSG_ADD, true, true>(ix.csr, unit, input, relation, ix.n_in, output, argidx, dim, ws, stream);
+            return run_pass<T, SUM, MSG_MUL, true, true>(FWD, ix.csr, ix.nnz, unit, input, relation, ix.n_in, output, argidx, dim, ws, ws_bytes, stream);
+        return run_pass<T, SUM, MSG_ADD, true, true>(FWD, ix.csr, ix.nnz, unit, input, relation, ix.n_in, output, argidx, dim, ws, ws_bytes, stream);
     }
     if (mul_op == ULTRA_RSPMM_MUL_MUL)
-        return run_pass<T, SUM, MSG_MUL, true, false>(ix.csr, unit, input, relation, ix.n_in, output, nullptr, dim, ws, stream, addend);
-    return run_pass<T, SUM, MSG_ADD, true, false>(ix.csr, unit, input, relation, ix.n_in, output, nullptr, dim, ws, stream, addend);
+        return run_pass<T, SUM, MSG_MUL, true, false>(FWD, ix.csr, ix.nnz, unit, input, relation, ix.n_in, output, nullptr, dim, ws, ws_bytes, stream, addend);
+    return run_pass<T, SUM, MSG_ADD, true, false>(FWD, ix.csr, ix.nnz, unit, input, relation, ix.n_in, output, nullptr, dim, ws, ws_bytes, stream, addend);
 }
 
 template <typename T>
 int forward_typed(const ultra_rspmm_index_t &ix, const void *relation, const void *input, const void *addend, void *output,
-                  int32_t *argidx, long long dim, int sum_op, int mul_op, void *ws, cudaStream_t stream) {
+                  int32_t *argidx, long long dim, int sum_op, int mul_op, void *ws, size_t ws_bytes, cudaStream_t stream) {
     const T *r = (const T *)relation, *x = (const T *)input;
     T *o = (T *)output;
     switch (sum_op) {
         case ULTRA_RSPMM_SUM_ADD:
-            return forward_sum<T, ULTRA_RSPMM_SUM_ADD>(ix, r, x, o, nullptr, dim, mul_op, ws, stream, (const T *)addend);
-        case ULTRA_RSPMM_SUM_MIN: return forward_sum<T, ULTRA_RSPMM_SUM_MIN>(ix, r, x, o, argidx, dim, mul_op, ws, stream);
-        default: return forward_sum<T, ULTRA_RSPMM_SUM_MAX>(ix, r, x, o, argidx, dim, mul_op, ws, stream);
+            return forward_sum<T, ULTRA_RSPMM_SUM_ADD>(ix, r, x, o, nullptr, dim, mul_op, ws, ws_bytes, stream, (const T *)addend);
+        case ULTRA_RSPMM_SUM_MIN: return forward_sum<T, ULTRA_RSPMM_SUM_MIN>(ix, r, x, o, argidx, dim, mul_op, ws, ws_bytes, stream);
+        default: return forward_sum<T, ULTRA_RSPMM_SUM_MAX>(ix, r, x, o, argidx, dim, mul_op, ws, ws_bytes, stream);
     }
 }
 
 template <typename T>
 int backward_typed(const ultra_rspmm_index_t &ix, const void *relation, const void *input, const void *output,
                    const void *grad_output, void *grad_relation, void *grad_input, long long dim, int sum_op,
-                   int mul_op, void *ws, cudaStream_t stream) {
+                   int mul_op, void *ws, size_t ws_bytes, cudaStream_t stream) {
     const T *r = (const T *)relation, *x = (const T *)input, *o = (const T *)output, *g = (const T *)grad_output;
     T *gr = (T *)grad_relation, *gx = (T *)grad_input;
     const bool unit = ix.unit_weight != 0;
@@ -776,25 +846,25 @@ int backward_typed(const ultra_rspmm_index_t &ix, const void *relation, const vo
     if (sum_op == ULTRA_RSPMM_SUM_ADD) {
         if (gx) {
             status = mul_op == ULTRA_RSPMM_MUL_MUL
-                         ? run_pass<T, ADD, MSG_MUL, true, false>(ix.csc, unit, g, r, ix.n_out, gx, nullptr, dim, ws, stream)
-                         : run_pass<T, ADD, MSG_COPY, true, false>(ix.csc, unit, g, r, ix.n_out, gx, nullptr, dim, ws, stream);
+                         ? run_pass<T, ADD, MSG_MUL, true, false>(GIN, ix.csc, ix.nnz, unit, g, r, ix.n_out, gx, nullptr, dim, ws, ws_bytes, stream)
+                         : run_pass<T, ADD, MSG_COPY, true, false>(GIN, ix.csc, ix.nnz, unit, g, r, ix.n_out, gx, nullptr, dim, ws, ws_bytes, stream);
             if (status) return status;
         }
         if (gr) {
             status = mul_op == ULTRA_RSPMM_MUL_MUL
-                         ? run_pass<T, ADD, MSG_MUL, false, false>(ix.rel, unit, g, x, (long long)ix.n_out + ix.n_in, gr, nullptr, dim, ws, stream)
-                         : run_pass<T, ADD, MSG_COPY, true, false>(ix.rel, unit, g, x, ix.n_out, gr, nullptr, dim, ws, stream);
+                         ? run_pass<T, ADD, MSG_MUL, false, false>(GREL, ix.rel, ix.nnz, unit, g, x, (long long)ix.n_out + ix.n_in, gr, nullptr, dim, ws, ws_bytes, stream)
+                         : run_pass<T, ADD, MSG_COPY, true, false>(GREL, ix.rel, ix.nnz, unit, g, x, ix.n_out, gr, nullptr, dim, ws, ws_bytes, stream);
         }
         return status;
     }
     if (gx) {
-        status = mul_op == ULTRA_RSPMM_MUL_MUL ? run_gated<T, MSG_MUL, true>(ix.csc, unit, g, o, r, x, ix.n_out, gx, dim, ws, stream)
-                                               : run_gated<T, MSG_ADD, true>(ix.csc, unit, g, o, r, x, ix.n_out, gx, dim, ws, stream);
+        status = mul_op == ULTRA_RSPMM_MUL_MUL ? run_gated<T, MSG_MUL, true>(GIN, ix.csc, unit, g, o, r, x, ix.n_out, gx, dim, ws, ws_bytes, stream)
+                                               : run_gated<T, MSG_ADD, true>(GIN, ix.csc, unit, g, o, r, x, ix.n_out, gx, dim, ws, ws_bytes, stream);
         if (status) return status;
     }
     if (gr) {
-        status = mul_op == ULTRA_RSPMM_MUL_MUL ? run_gated<T, MSG_MUL, false>(ix.rel, unit, g, o, x, r, (long long)ix.n_out + ix.n_in, gr, dim, ws, stream)
-                                               : run_gated<T, MSG_ADD, false>(ix.rel, unit, g, o, x, r, (long long)ix.n_out + ix.n_in, gr, dim, ws, stream);
+        status = mul_op == ULTRA_RSPMM_MUL_MUL ? run_gated<T, MSG_MUL, false>(GREL, ix.rel, unit, g, o, x, r, (long long)ix.n_out + ix.n_in, gr, dim, ws, ws_bytes, stream)
+                                               : run_gated<T, MSG_ADD, false>(GREL, ix.rel, unit, g, o, x, r, (long long)ix.n_out + ix.n_in, gr, dim, ws, ws_bytes, stream);
     }
     return status;
 }
@@ -842,6 +912,15 @@ int forward_pna_typed(const ultra_rspmm_index_t &ix, const T *relation, const T 
     else if (vec == 2) status = launch_pna<T, 2, MSG>(args, stream);
     else status = launch_pna<T, 1, MSG>(args, stream);
     if (status) return status;
+    ultra_rspmm_pass_info_t info = {};
+    info.kernel = ULTRA_RSPMM_KERNEL_SEG_PNA;
+    info.vec = vec;
+    info.keep = args.keep;
+    info.packed = order.pack_shift > 0;
+    info.n_task = args.n_task;
+    info.n_slab = args.n_slab;
+    info.n_split = order.n_split;
+    note_pass(FWD, info);
     const T *partial = (const T *)workspace;
     const long long stride = args.slot_stride;
     if ((status = launch_combine<T, ULTRA_RSPMM_SUM_ADD, false>(order, partial, nullptr, out[0], nullptr, dim, stream))) return status;
@@ -859,9 +938,7 @@ int check_call(const ultra_rspmm_index_t *index, int64_t dim, int32_t dtype, int
 }
 
 size_t pass_bytes(const ultra_rspmm_order_t &order, int64_t dim, size_t elem, bool with_arg) {
-    size_t bytes = align_up((size_t)order.n_slot * dim * elem);
-    if (with_arg) bytes += align_up((size_t)order.n_slot * dim * sizeof(int32_t));
-    return bytes;
+    return slot_bytes(order, dim, elem, with_arg) + 256;   // + the work counter of the staged kernel
 }
 
 }  // namespace
@@ -897,8 +974,8 @@ extern "C" int ultra_rspmm_forward(const ultra_rspmm_index_t *index, const void 
     if (index->csr.n_slot > 0 && (!workspace || workspace_bytes < need)) return ULTRA_RSPMM_ERR_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
     status = dtype == ULTRA_RSPMM_F32
-                 ? forward_typed<float>(*index, dev_relation, dev_input, dev_addend, dev_output, dev_argidx, dim, sum_op, mul_op, workspace, s)
-                 : forward_typed<double>(*index, dev_relation, dev_input, dev_addend, dev_output, dev_argidx, dim, sum_op, mul_op, workspace, s);
+                 ? forward_typed<float>(*index, dev_relation, dev_input, dev_addend, dev_output, dev_argidx, dim, sum_op, mul_op, workspace, workspace_bytes, s)
+                 : forward_typed<double>(*index, dev_relation, dev_input, dev_addend, dev_output, dev_argidx, dim, sum_op, mul_op, workspace, workspace_bytes, s);
     if (status) return status;
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;
@@ -926,9 +1003,9 @@ extern "C" int ultra_rspmm_backward(const ultra_rspmm_index_t *index, const void
     cudaStream_t s = (cudaStream_t)stream;
     status = dtype == ULTRA_RSPMM_F32
                  ? backward_typed<float>(*index, dev_relation, dev_input, dev_output, dev_grad_output, dev_grad_relation,
-                                         dev_grad_input, dim, sum_op, mul_op, workspace, s)
+                                         dev_grad_input, dim, sum_op, mul_op, workspace, workspace_bytes, s)
                  : backward_typed<double>(*index, dev_relation, dev_input, dev_output, dev_grad_output, dev_grad_relation,
-                                          dev_grad_input, dim, sum_op, mul_op, workspace, s);
+                                          dev_grad_input, dim, sum_op, mul_op, workspace, workspace_bytes, s);
     if (status) return status;
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;
@@ -990,8 +1067,8 @@ extern "C" int ultra_rspmm_forward_blocked(const ultra_rspmm_index_t *index, con
     float *o = (float *)dev_output;
     constexpr int ADD = ULTRA_RSPMM_SUM_ADD;
     status = mul_op == ULTRA_RSPMM_MUL_MUL
-                 ? run_pass<float, ADD, MSG_MUL, true, false>(index->csr, unit, x, r, index->n_in, o, nullptr, dim, workspace, s, b, layout)
-                 : run_pass<float, ADD, MSG_ADD, true, false>(index->csr, unit, x, r, index->n_in, o, nullptr, dim, workspace, s, b, layout);
+                 ? run_pass<float, ADD, MSG_MUL, true, false>(FWD, index->csr, index->nnz, unit, x, r, index->n_in, o, nullptr, dim, workspace, workspace_bytes, s, b, layout)
+                 : run_pass<float, ADD, MSG_ADD, true, false>(FWD, index->csr, index->nnz, unit, x, r, index->n_in, o, nullptr, dim, workspace, workspace_bytes, s, b, layout);
     if (status) return status;
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;

@@ -1,0 +1,234 @@
+// Gather-combine-reduce for operands with FEW rows (sm_100a): the gathered operand's column slab lives in shared memory.
+//
+// The graph of relations that ULTRA's relation model walks (reference ultra/rel_model.py:253-257, 369-374, built by
+// :91-147) has N_r = 2R nodes (474 at the FB15k-237 shape), 4 edge types and up to 4 N_r^2 edges: every destination row
+// gathers ~1,900 source rows out of the same 474.  The generic kernel (rspmm_kernels.cu) serves those gathers from
+// L1/L2 and is bound by L2->SM bandwidth there.  Here a persistent CTA copies the whole (rows x 64 features) slab of the
+// gathered operand into shared memory once (121 KB at 474 rows) and its 32 warps then walk tasks of that slab:
+//
+//   * per edge one LDS.128 per lane - a half-warp reads the 256-byte slab of one source row, the two halves of a warp
+//     work on different edges, so one instruction moves 512 B with the minimum of 4 shared-memory wavefronts;
+//   * the relation row of the current run stays in registers (edges of a segment are grouped by relation);
+//   * edge ids are staged per warp exactly as in the generic kernel (coalesced load, LDS.128 of 4 packed ids);
+//   * work is handed out dynamically: an item = (slab, 32..128 consecutive tasks of the task list), items are numbered
+//     slab-major and fetched with one atomicAdd per item and CTA, so the CTAs drain the list evenly and refill their
+//     slab only when the slab changes.  The counter only schedules: which CTA runs a task never changes its result, and a
+//     task's edges are always summed in the same order (deterministic, no atomics on data).
+//
+// Serves sum aggregation with mul / add / copy messages (forward on the csr order, grad_input on the csc order) of fp32
+// operands whose ids pack into 32 bits; run_pass (rspmm_kernels.cu) selects it when the slab fits shared memory.
+#include "rspmm_common.cuh"
+
+namespace ultra {
+
+namespace {
+
+constexpr int kStagedWarps = 32;
+constexpr int kStagedThreads = kStagedWarps * 32;
+constexpr int kEdgesPerHalf = 4;   // edges in flight per half-warp
+
+__device__ __forceinline__ long long staged_blocked_col(long long col, int block, int shift, long long stride) {
+    const unsigned c = (unsigned)col;
+    const unsigned q = shift >= 0 ? c >> shift : c / (unsigned)block;
+    return (long long)q * stride + (c - q * (unsigned)block);
+}
+
+template <int MSG, bool UNIT>
+__device__ __forceinline__ void staged_accumulate(const float4 &x, const float4 &r, float w, float (&acc)[4]) {
+    const float xv[4] = {x.x, x.y, x.z, x.w};
+    const float rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const float m = UNIT ? message<float, MSG>(rv[v], xv[v]) : message<float, MSG>(w, rv[v], xv[v]);
+        acc[v] += m;
+    }
+}
+
+// one edge, relation row looked up if it differs from the cached one (run boundaries and the ragged tail of a task)
+template <int MSG, bool UNIT>
+__device__ __forceinline__ void staged_edge(unsigned id, float w, unsigned low, int shift, const float4 *s_rows, int l16,
+                                            const char *B, unsigned row_bytes, float4 &cached, int &cached_rel, float (&acc)[4]) {
+    const float4 x = s_rows[(id & low) * (kStagedSlab / 4) + l16];
+    if (MSG != MSG_COPY) {
+        const int rel = (int)(id >> shift);
+        if (rel != cached_rel) {   // at most n_rel times per segment: the edges of a segment are grouped by relation
+            cached = __ldg(reinterpret_cast<const float4 *>(B + (unsigned long long)(unsigned)rel * row_bytes));
+            cached_rel = rel;
+        }
+    }
+    staged_accumulate<MSG, UNIT>(x, cached, w, acc);
+}
+
+// four consecutive edges of one half-warp.  Common case: all of them use the cached relation row - four LDS.128 in
+// flight, then 16 FFMA, no table access
+template <int MSG, bool UNIT>
+__device__ __forceinline__ void staged_edges4(const unsigned (&ids)[4], const float (&ws)[4], unsigned low, int shift,
+                                              const float4 *s_rows, int l16, const char *B, unsigned row_bytes,
+                                              float4 &cached, int &cached_rel, float (&acc)[4]) {
+    bool same = true;
+    if (MSG != MSG_COPY) {
+        const unsigned c = (unsigned)cached_rel << shift;   // cached_rel = -1 never matches: ids have no bits above the relation
+        same = cached_rel >= 0 && ((((ids[0] ^ c) | (ids[1] ^ c)) | ((ids[2] ^ c) | (ids[3] ^ c))) >> shift) == 0;
+    }
+    if (same) {
+        float4 x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = s_rows[(ids[k] & low) * (kStagedSlab / 4) + l16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) staged_accumulate<MSG, UNIT>(x[k], cached, ws[k], acc);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) staged_edge<MSG, UNIT>(ids[k], ws[k], low, shift, s_rows, l16, B, row_bytes, cached, cached_rel, acc);
+    }
+}
+
+template <int MSG>
+__global__ void __launch_bounds__(kStagedThreads, 1) rows_in_smem_kernel(const StagedArgs a) {
+    extern __shared__ __align__(16) float4 s_rows[];   // n_rows x 16 float4: the slab of the gathered operand
+    __shared__ __align__(16) unsigned s_edge[kStagedWarps][32];
+    __shared__ __align__(16) float s_w[kStagedWarps][32];
+    __shared__ int s_item;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, l16 = lane & 15;
+    const int shift = a.pack_shift;
+    const unsigned low = shift >= 32 ? 0xffffffffu : ((1u << shift) - 1u);
+    const unsigned row_bytes = (unsigned)(a.dim * sizeof(float));
+    const int items_per_slab = (a.n_task + a.tasks_per_item - 1) / a.tasks_per_item;
+    const int n_item = items_per_slab * a.n_slab;
+    int resident = -1;
+    for (;;) {
+        if (threadIdx.x == 0) s_item = (int)atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_item) break;
+        const int slab = item / items_per_slab;
+        const int first = (item - slab * items_per_slab) * a.tasks_per_item;
+        const int last = min(a.n_task, first + a.tasks_per_item);
+        if (slab != resident) {   // (re)fill: 256 contiguous bytes per row, 16 lanes each
+            for (int i = threadIdx.x; i < a.n_rows * (kStagedSlab / 4); i += kStagedThreads) {
+                const int row = i >> 4;
+                const long long col = (long long)slab * kStagedSlab + (i & 15) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col < a.dim) {
+                    const long long at = a.block ? staged_blocked_col(col, a.block, a.block_shift, a.a_stride) : col;
+                    v = __ldg(reinterpret_cast<const float4 *>(a.A + (long long)row * a.a_row + at));
+                }
+                s_rows[i] = v;
+            }
+            resident = slab;
+            __syncthreads();
+        }
+        const long long col = (long long)slab * kStagedSlab + l16 * 4;
+        const bool active = col < a.dim;
+        const char *B = reinterpret_cast<const char *>(a.B + (active ? col : 0));
+        for (int t = first + warp; t < last; t += kStagedWarps) {
+            const int4 task = __ldg(a.task + t);
+            const int slot = task_slot(task.w);
+            const bool unit = a.w == nullptr || !(task.w & kNonUnitTask);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float4 cached = make_float4(0.f, 0.f, 0.f, 0.f);
+            int cached_rel = -1;
+            unsigned ahead = 0;
+            float ahead_w = 1.f;
+            if (task.y + lane < task.z) {
+                ahead = __ldg(a.packed + task.y + lane);
+                if (!unit) ahead_w = __ldg(a.w + task.y + lane);
+            }
+            for (int base = task.y; base < task.z; base += 32) {
+                const int n = min(32, task.z - base);
+                __syncwarp();
+                s_edge[warp][lane] = ahead;
+                if (!unit) s_w[warp][lane] = ahead_w;
+                __syncwarp();
+                if (base + 32 + lane < task.z) {
+                    ahead = __ldg(a.packed + base + 32 + lane);
+                    if (!unit) ahead_w = __ldg(a.w + base + 32 + lane);
+                }
+                int u = 0;
+                // full groups: each half-warp takes 4 consecutive edges (one LDS.128 of ids), no predicates
+                for (; u + 2 * kEdgesPerHalf <= n; u += 2 * kEdgesPerHalf) {
+                    const int mine = u + half * kEdgesPerHalf;
+                    const uint4 id = *reinterpret_cast<const uint4 *>(&s_edge[warp][mine]);
+                    const unsigned ids[4] = {id.x, id.y, id.z, id.w};
+                    if (unit) {
+                        const float ws[4] = {1.f, 1.f, 1.f, 1.f};
+                        staged_edges4<MSG, true>(ids, ws, low, shift, s_rows, l16, B, row_bytes, cached, cached_rel, acc);
+                    } else {
+                        const float4 w4 = *reinterpret_cast<const float4 *>(&s_w[warp][mine]);
+                        const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
+                        staged_edges4<MSG, false>(ids, ws, low, shift, s_rows, l16, B, row_bytes, cached, cached_rel, acc);
+                    }
+                }
+                // ragged tail (< 8 edges): the halves alternate, idle half-warps skip
+                for (; u < n; u += 2) {
+                    const int mine = u + half;
+                    if (mine < n) {
+                        if (unit) staged_edge<MSG, true>(s_edge[warp][mine], 1.f, low, shift, s_rows, l16, B, row_bytes, cached, cached_rel, acc);
+                        else staged_edge<MSG, false>(s_edge[warp][mine], s_w[warp][mine], low, shift, s_rows, l16, B, row_bytes, cached, cached_rel, acc);
+                    }
+                }
+            }
+            // fold the two half-warps (fixed order: lower half + upper half), lanes 0..15 write 256 bytes
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[v] += __shfl_xor_sync(kFullMask, acc[v], 16);
+            if (half == 0 && active) {
+                Vec<float, 4> r;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) r.v[v] = acc[v];
+                if (slot < 0) {
+                    const long long row = task.x;
+                    if (a.addend) {
+                        Vec<float, 4> b;
+                        gather_load(a.addend + row * a.dim + col, b);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) r.v[v] += b.v[v];
+                    }
+                    const long long o_col = a.block ? staged_blocked_col(col, a.block, a.block_shift, a.o_stride) + a.o_offset : col;
+                    stream_store(a.out + row * a.o_row + o_col, r);
+                } else {
+                    float *p = a.partial + (long long)slot * a.dim + col;
+                    *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+                }
+            }
+        }
+        __syncthreads();   // every warp is done with s_item and with the resident slab before the next fetch / refill
+    }
+}
+
+template <int MSG> int launch_typed(const StagedArgs &args, size_t smem, int blocks, cudaStream_t stream) {
+    static bool configured = false;   // per instantiation; the attribute is per device function and idempotent
+    if (!configured) {
+        ULTRA_CUDA_OK(cudaFuncSetAttribute(rows_in_smem_kernel<MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedMaxSmem));
+        configured = true;
+    }
+    rows_in_smem_kernel<MSG><<<blocks, kStagedThreads, smem, stream>>>(args);
+    note_launch();
+    return ULTRA_RSPMM_OK;
+}
+
+}  // namespace
+
+int launch_rows_in_smem(StagedArgs args, int msg, cudaStream_t stream) {
+    if (args.n_task == 0 || args.dim == 0) return ULTRA_RSPMM_OK;
+    const size_t smem = (size_t)args.n_rows * kStagedSlab * sizeof(float);
+    if (smem > kStagedMaxSmem || !args.packed || !args.counter) return ULTRA_RSPMM_ERR_ARG;
+    args.n_slab = (int)((args.dim + kStagedSlab - 1) / kStagedSlab);
+    int device = 0, sms = 0;
+    ULTRA_CUDA_OK(cudaGetDevice(&device));
+    ULTRA_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    // items: about 8 per CTA so that the tail is short, 32..128 tasks (1..4 per warp) each
+    const long long work = (long long)args.n_task * args.n_slab;
+    long long per_item = work / ((long long)sms * 8);
+    per_item = per_item < kStagedWarps ? kStagedWarps : (per_item > 4 * kStagedWarps ? 4 * kStagedWarps : per_item);
+    args.tasks_per_item = (int)((per_item + kStagedWarps - 1) / kStagedWarps * kStagedWarps);
+    const long long items = (long long)((args.n_task + args.tasks_per_item - 1) / args.tasks_per_item) * args.n_slab;
+    const int blocks = (int)(items < sms ? items : sms);
+    ULTRA_CUDA_OK(cudaMemsetAsync(args.counter, 0, sizeof(unsigned), stream));
+    switch (msg) {
+        case MSG_MUL: return launch_typed<MSG_MUL>(args, smem, blocks, stream);
+        case MSG_ADD: return launch_typed<MSG_ADD>(args, smem, blocks, stream);
+        default: return launch_typed<MSG_COPY>(args, smem, blocks, stream);
+    }
+}
+
+}  // namespace ultra
