@@ -90,3 +90,32 @@ def test_easy_edge_mask_equals_graph_match(seed):
     assert torch.equal(nbf.easy_edge_mask(graph, h_index, t_index, r_index), want)
     empty = torch.zeros(0, 3, dtype=torch.long)
     assert not nbf.easy_edge_mask(graph, empty[:, 0], empty[:, 1], empty[:, 2]).any()
+
+
+@pytest.mark.gpu
+def test_layer_uses_the_boundary_of_the_call_not_a_stale_one_hot(cuda):
+    """the sparse form of the boundary travels with the call that built it.  After a bellmanford pass
+    over a persistent graph object, a later layer call on the same graph with another `graph.boundary` must aggregate
+    with that boundary."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    num_node, num_relation, dim, batch = 30, 4, 32, 3
+    generator = torch.Generator().manual_seed(1)
+    edge_list = torch.stack([torch.randint(num_node, (200,), generator=generator), torch.randint(num_node, (200,), generator=generator),
+                             torch.randint(num_relation, (200,), generator=generator)], dim=1)
+    graph = data.Graph(edge_list, num_node=num_node, num_relation=num_relation).to(cuda)
+    model = nbf.CustomNBFNetFull(dim, [dim, dim], num_relation=num_relation, aggregate_func="sum", layer_norm=True,
+                                 short_cut=True).to(cuda)
+    h_index = torch.tensor([0, 5, 7], device=cuda)
+    first = model(graph, h_index)                 # autograd on: the per-layer path, boundary handed down as one-hot
+    assert first.requires_grad and not hasattr(graph, "boundary_one_hot")
+    layer = model.layers[0]
+    other_boundary = torch.randn(num_node, batch, dim, device=cuda)
+    with graph.node():
+        graph.boundary = other_boundary
+    input = torch.randn(num_node, batch, dim, device=cuda)
+    with torch.no_grad():
+        update = layer.message_and_aggregate(graph, input)
+        relation_input = layer.relation_input(graph, batch)
+        plain = nbf.rspmm.generalized_rspmm(graph.adjacency.transpose(0, 1), relation_input, input.flatten(1))
+    torch.testing.assert_close(update.flatten(1), plain + other_boundary.flatten(1), rtol=1e-5, atol=1e-5)

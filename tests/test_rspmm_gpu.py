@@ -659,3 +659,129 @@ def test_derived_index_equals_rebuilt_index(cuda, dtype):
             base.derive(torch.ones(3, device=cuda))
     finally:
         lib.ultra_rspmm_set_tuning(256, 0, 0)
+
+
+# ---- rows-in-shared-memory kernel (csrc/rspmm_staged.cu) --------------------------------------------------------------
+@pytest.fixture
+def staged_always():
+    from ultra_torchdrug_b200 import _lib
+    _lib.check(_lib.lib().ultra_rspmm_set_staged(2), "ultra_rspmm_set_staged")
+    yield _lib
+    _lib.check(_lib.lib().ultra_rspmm_set_staged(1), "ultra_rspmm_set_staged")
+
+
+@pytest.mark.parametrize("mul", ["mul", "add"])
+@pytest.mark.parametrize("dim", [4, 60, 64, 200, 256, 1028])
+@pytest.mark.parametrize("weights,chunk", [("unit", 0), ("random", 0), ("random", 16)])
+def test_staged_kernel_parity(cuda, staged_always, mul, dim, weights, chunk):
+    """Few-row operands through the rows-in-shared-memory kernel (forced on): ragged widths, merged duplicates with
+    non-unit weights, split rows (chunk 16), empty rows; forward and grad_input are served by it, grad_relation (two
+    gathered operands) by the generic kernel."""
+    lib = staged_always.lib()
+    if chunk:
+        lib.ultra_rspmm_set_tuning(chunk, 0, 0)
+    try:
+        from ultra_torchdrug_b200 import functional as F
+        n, n_rel, nnz = 90, 4, 5000
+        indices, values = util.random_coo(n, n - 7, n_rel, nnz, seed=dim, duplicates=200, weights=weights, skew=True)
+        shape = (n, n - 7, n_rel)
+        relation, input = util.random_dense(n_rel, dim, 1), util.random_dense(n - 7, dim, 2)
+        grad = util.random_dense(n, dim, 3)
+        index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), shape)
+        d_rel, d_in, d_grad = (torch.from_numpy(x).to(cuda) for x in (relation, input, grad))
+        out = index.forward(d_rel, d_in, "add", mul)
+        assert staged_always.pass_info(staged_always.PASS_FORWARD)["kernel_name"] == "rows_in_smem"
+        g_rel, g_in = index.backward(d_rel, d_in, out, d_grad, "add", mul)
+        assert staged_always.pass_info(staged_always.PASS_GRAD_INPUT)["kernel_name"] == "rows_in_smem"
+        exp, _ = util.oracle_forward(indices, values, shape, relation, input, "add", mul, dtype=np.float64)
+        scale, _ = util.oracle_forward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), "add", mul, dtype=np.float64)
+        _assert_sum_close(out.cpu().numpy(), exp, scale, "staged forward")
+        e_rel, e_in = util.oracle_backward(indices, values, shape, relation, input, None, grad, "add", mul, dtype=np.float64)
+        s_rel, s_in = util.oracle_backward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), None, np.abs(grad),
+                                           "add", mul, dtype=np.float64)
+        _assert_sum_close(g_rel.cpu().numpy(), e_rel, s_rel, "grad_relation")
+        _assert_sum_close(g_in.cpu().numpy(), e_in, s_in, "staged grad_input")
+        assert torch.equal(out, index.forward(d_rel, d_in, "add", mul)), "two runs differ"
+        # + boundary in the epilogue
+        with_addend = index.forward(d_rel, d_in, "add", mul, addend=d_grad)
+        _assert_sum_close(with_addend.cpu().numpy(), exp + grad, scale + np.abs(grad), "staged forward + addend")
+    finally:
+        if chunk:
+            lib.ultra_rspmm_set_tuning(256, 0, 0)
+
+
+def test_staged_kernel_blocked_layout(cuda, staged_always):
+    """The cat-free layer buffers (block 64, stride 128) through the rows-in-shared-memory kernel equal the plain call."""
+    from ultra_torchdrug_b200 import functional as F
+    n, n_rel, batch, width = 70, 4, 5, 64
+    indices, values = util.random_coo(n, n, n_rel, 4000, seed=5, duplicates=50)
+    index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), (n, n, n_rel))
+    generator = torch.Generator(device=cuda).manual_seed(3)
+    buffer = torch.randn(n, batch, 2 * width, device=cuda, generator=generator)
+    relation = torch.randn(n_rel, batch * width, device=cuda, generator=generator)
+    addend = torch.randn(n, batch * width, device=cuda, generator=generator)
+    plain = index.forward(relation, buffer[..., :width].reshape(n, -1).contiguous(), "add", "mul", addend=addend)
+    left = buffer[..., :width].clone()
+    index.forward_blocked(relation, buffer, buffer, width, 0, width, "mul", addend=addend)
+    assert staged_always.pass_info(staged_always.PASS_FORWARD)["kernel_name"] == "rows_in_smem"
+    assert torch.equal(buffer[..., width:].reshape(n, -1), plain)
+    assert torch.equal(buffer[..., :width], left), "the input halves were modified"
+
+
+def test_raw_calls_check_their_operands(cuda):
+    """The raw `GraphIndex` methods (used by the buffered inference loop without `generalized_rspmm`'s checks) reject
+    operands the kernels would read out of bounds or misinterpret - as the reference's TORCH_CHECKs do."""
+    from ultra_torchdrug_b200 import functional as F
+    indices, values = util.random_coo(30, 30, 6, 300, seed=1)
+    index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), (30, 30, 6))
+    relation, input = torch.randn(6, 128, device=cuda), torch.randn(30, 128, device=cuda)
+    grad = torch.randn(30, 128, device=cuda)
+    index.forward(relation, input)
+    for bad_relation in (relation[:5], relation.double(), relation[:, :64], relation.cpu(), relation.t().contiguous().t()):
+        with pytest.raises(RuntimeError):
+            index.forward(bad_relation, input)
+        with pytest.raises(RuntimeError):
+            index.forward_pna(bad_relation, input)
+        with pytest.raises(RuntimeError):
+            index.backward(bad_relation, input, None, grad)
+    with pytest.raises(RuntimeError):
+        index.forward(relation, input[:29])
+    with pytest.raises(RuntimeError):
+        index.backward(relation, input, None, grad[:, :64])
+    with pytest.raises(RuntimeError):
+        index.backward(relation, input, None, grad, "max", "mul")       # min / max need the saved output
+    with pytest.raises(ValueError):
+        index.forward(relation, input, "mean", "mul")
+    buffer = torch.randn(30, 2, 128, device=cuda)
+    index.forward_blocked(relation, buffer, buffer, 64, 0, 64)
+    for bad_relation in (relation[:5], relation.double(), relation[:, :64]):
+        with pytest.raises(RuntimeError):
+            index.forward_blocked(bad_relation, buffer, buffer, 64, 0, 64)
+    with pytest.raises(RuntimeError):
+        index.forward_blocked(relation, buffer, buffer, 64, 0, 96)       # output block leaves the stride
+    with pytest.raises(RuntimeError):
+        index.forward_blocked(relation, buffer, buffer, 64, 96, 64)      # input block leaves the stride
+
+
+def test_graph_index_lookup_refuses_stream_capture(cuda):
+    """An operand without an attached index needs a fingerprint read-back: inside CUDA-graph capture that is an error
+    with instructions, not a silent synchronisation."""
+    from ultra_torchdrug_b200 import functional as F
+    indices, values = util.random_coo(20, 20, 3, 100, seed=2)
+    sparse = util.to_sparse(indices, values, (20, 20, 3), cuda)
+    relation, input = torch.randn(3, 64, device=cuda), torch.randn(20, 64, device=cuda)
+    stream = torch.cuda.Stream(device=cuda)
+    graph = torch.cuda.CUDAGraph()
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="before capturing"):
+            with torch.cuda.stream(stream), torch.cuda.graph(graph, stream=stream):
+                F.generalized_rspmm(sparse, relation, input)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        expected = F.generalized_rspmm(sparse, relation, input)      # attaches the index to `sparse`
+        captured = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(captured):
+            out = F.generalized_rspmm(sparse, relation, input)
+        captured.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(out, expected)

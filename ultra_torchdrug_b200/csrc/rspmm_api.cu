@@ -190,7 +190,29 @@ extern "C" int ultra_rspmm_ctx_set_graph(ultra_rspmm_ctx_t *ctx, const int64_t *
     return ULTRA_RSPMM_OK;
 }
 
+static int ctx_run_pipeline(ultra_rspmm_ctx_t *ctx, const void *host_relation, const void *host_input,
+                            const void *host_grad_output, void *host_output, void *host_grad_relation, void *host_grad_input,
+                            int64_t dim, int32_t sum_op, int32_t mul_op, bool with_backward);
+
+// Any failure in the middle of the pipeline leaves asynchronous copies in flight on the caller's host buffers: drain
+// the three streams (best effort) before the status is returned, so the caller may free or reuse them right away.
 static int ctx_run(ultra_rspmm_ctx_t *ctx, const void *host_relation, const void *host_input,
+                   const void *host_grad_output, void *host_output, void *host_grad_relation, void *host_grad_input,
+                   int64_t dim, int32_t sum_op, int32_t mul_op, bool with_backward) {
+    const int status = ctx_run_pipeline(ctx, host_relation, host_input, host_grad_output, host_output, host_grad_relation,
+                                        host_grad_input, dim, sum_op, mul_op, with_backward);
+    if (status != ULTRA_RSPMM_OK && ctx) {
+        const int kept = t_last_cuda_error;
+        cudaStreamSynchronize(ctx->stream_in);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->stream_out);
+        cudaGetLastError();
+        t_last_cuda_error = kept;
+    }
+    return status;
+}
+
+static int ctx_run_pipeline(ultra_rspmm_ctx_t *ctx, const void *host_relation, const void *host_input,
                    const void *host_grad_output, void *host_output, void *host_grad_relation, void *host_grad_input,
                    int64_t dim, int32_t sum_op, int32_t mul_op, bool with_backward) {
     if (!ctx || !ctx->has_graph || dim < 0) return ULTRA_RSPMM_ERR_ARG;

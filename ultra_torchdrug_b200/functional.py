@@ -27,7 +27,10 @@ _SUM_OPS = ("add", "min", "max")
 _MUL_OPS = ("mul", "add")
 _DTYPE_CODE = {torch.float32: _lib.F32, torch.float64: _lib.F64}
 
+#: LRU of graph indexes found by content fingerprint: at most ULTRA_RSPMM_INDEX_CACHE entries (default 8) and
+#: ULTRA_RSPMM_INDEX_CACHE_MB of device memory (default 2048; the newest index is always kept)
 INDEX_CACHE_SIZE = int(os.environ.get("ULTRA_RSPMM_INDEX_CACHE", "8"))
+INDEX_CACHE_BYTES = int(os.environ.get("ULTRA_RSPMM_INDEX_CACHE_MB", "2048")) << 20
 _index_cache = collections.OrderedDict()
 #: statistics for tests / benchmarks: how the index of each call was obtained
 cache_stats = {"attached": 0, "fingerprint_hit": 0, "built": 0}
@@ -117,10 +120,38 @@ class GraphIndex(object):
         return self._workspace_bytes[dim]
 
     # -- raw operator calls (device tensors in, device tensors out) ---------------------------------
+    def _check_dense(self, **operands):
+        """Shape / dtype / device / layout checks of the dense operands of a raw call: `relation (n_rel, dim)`,
+        `input (n_in, dim)`, `output` / `grad_output (n_out, dim)`.  The kernels index these buffers from the graph's
+        ids, so a short relation table or a float64 tensor must fail here (the reference raises from TORCH_CHECK),
+        never reach the device."""
+        rows = {"relation": self.shape[2], "input": self.shape[1], "output": self.shape[0], "grad_output": self.shape[0]}
+        dim = None
+        for name, tensor in operands.items():
+            if tensor is None:
+                continue
+            if tensor.dim() != 2 or tensor.shape[0] != rows[name]:
+                raise RuntimeError("Expect `%s` to be a (%d, dim) matrix, but found %s" % (name, rows[name], tuple(tensor.shape)))
+            if dim is None:
+                dim = tensor.shape[1]
+            if tensor.shape[1] != dim:
+                raise RuntimeError("Expect `%s` to have %d features, but found %d" % (name, dim, tensor.shape[1]))
+            if tensor.dtype != self.dtype:
+                raise RuntimeError("Expect `%s` to be %s like the graph index, but found %s" % (name, self.dtype, tensor.dtype))
+            if tensor.device != self.device:
+                raise RuntimeError("Expect `%s` on %s like the graph index, but found %s" % (name, self.device, tensor.device))
+            if not tensor.is_contiguous():
+                raise RuntimeError("Expect `%s` to be contiguous" % name)
+        return dim
+
     def forward(self, relation, input, sum="add", mul="mul", return_argidx=False, addend=None):
+        self._check_dense(relation=relation, input=input)
+        if sum not in _SUM_OPS or mul not in _MUL_OPS:
+            raise ValueError("No generalized rspmm implementation found for summation `%s` and multiplication `%s`" % (sum, mul))
         dim = input.shape[1]
-        if addend is not None and (sum != "add" or addend.shape != (self.shape[0], dim) or addend.dtype != input.dtype):
-            raise RuntimeError("`addend` needs sum='add' and the shape / dtype of the output")
+        if addend is not None and (sum != "add" or addend.shape != (self.shape[0], dim) or addend.dtype != input.dtype
+                                   or addend.device != input.device or not addend.is_contiguous()):
+            raise RuntimeError("`addend` needs sum='add' and the shape / dtype / device of the output, contiguous")
         output = torch.empty((self.shape[0], dim), dtype=input.dtype, device=input.device)
         argidx = None
         if return_argidx and sum != "add":
@@ -140,14 +171,30 @@ class GraphIndex(object):
         `input_buffer[..., input_offset:input_offset + block]`, the result (+ addend) is written into
         `output_buffer[..., output_offset:output_offset + block]` (may be the same buffer).  Removes the
         `torch.cat([input, update], -1)` of reference layer.py:387 when the buffer is what the layer's Linear reads."""
+        if input_buffer.dim() != 3:
+            raise RuntimeError("input buffer must be a (rows, batch, stride) tensor")
         batch = input_buffer.shape[1]
         dim = batch * block
+        if mul not in _MUL_OPS:
+            raise ValueError("Unknown multiplication `%s`" % mul)
+        if block <= 0 or block % 4 or input_offset < 0 or output_offset < 0 or input_offset % 4 or output_offset % 4:
+            raise RuntimeError("block and offsets must be non-negative multiples of 4 features")
+        if relation.shape != (self.shape[2], dim) or relation.dtype != torch.float32 or relation.device != self.device \
+                or not relation.is_contiguous() or self.dtype != torch.float32:
+            raise RuntimeError("Expect `relation` to be a contiguous float32 (%d, %d) matrix on %s, but found %s %s on %s"
+                               % (self.shape[2], dim, self.device, tuple(relation.shape), relation.dtype, relation.device))
+        for name, buffer, offset in (("input", input_buffer, input_offset), ("output", output_buffer, output_offset)):
+            if buffer.dim() == 3 and offset + block > buffer.shape[2]:
+                raise RuntimeError("%s block [%d, %d) exceeds the buffer's stride %d" % (name, offset, offset + block, buffer.shape[2]))
+            if buffer.device != self.device:
+                raise RuntimeError("%s buffer must live on %s" % (name, self.device))
         for name, buffer, rows in (("input", input_buffer, self.shape[1]), ("output", output_buffer, self.shape[0])):
             if buffer.dim() != 3 or not buffer.is_contiguous() or buffer.dtype != torch.float32 or buffer.shape[0] != rows \
                     or buffer.shape[1] != batch:
                 raise RuntimeError("%s buffer must be a contiguous float32 (%d, %d, stride) tensor" % (name, rows, batch))
-        if addend is not None and (addend.shape != (self.shape[0], dim) or addend.dtype != torch.float32):
-            raise RuntimeError("`addend` must be a float32 (%d, %d) matrix" % (self.shape[0], dim))
+        if addend is not None and (addend.shape != (self.shape[0], dim) or addend.dtype != torch.float32
+                                   or not addend.is_contiguous() or addend.device != self.device):
+            raise RuntimeError("`addend` must be a contiguous float32 (%d, %d) matrix on %s" % (self.shape[0], dim, self.device))
         need = self.workspace_bytes(dim)[0]
         with torch.cuda.device(input_buffer.device):
             workspace = torch.empty(need, dtype=torch.uint8, device=input_buffer.device) if need else None
@@ -161,6 +208,9 @@ class GraphIndex(object):
     def forward_pna(self, relation, input, mul="mul"):
         """(sum, sum of squared operands, max, min) of the messages in one pass - the four operator calls of the
         reference's `pna` aggregation (layer.py:141-144, 343-346) over a single gather per edge.  Forward only."""
+        self._check_dense(relation=relation, input=input)
+        if mul not in _MUL_OPS:
+            raise ValueError("Unknown multiplication `%s`" % mul)
         dim = input.shape[1]
         outputs = [torch.empty((self.shape[0], dim), dtype=input.dtype, device=input.device) for _ in range(4)]
         need = 4 * self.workspace_bytes(dim)[0]
@@ -174,6 +224,11 @@ class GraphIndex(object):
 
     def backward(self, relation, input, output, grad_output, sum="add", mul="mul", need_relation=True,
                  need_input=True):
+        self._check_dense(relation=relation, input=input, grad_output=grad_output, output=output if sum != "add" else None)
+        if sum not in _SUM_OPS or mul not in _MUL_OPS:
+            raise ValueError("No generalized rspmm implementation found for summation `%s` and multiplication `%s`" % (sum, mul))
+        if sum != "add" and output is None:
+            raise RuntimeError("min / max backward needs the saved `output`")
         dim = input.shape[1]
         grad_relation = torch.empty_like(relation) if need_relation else None
         grad_input = torch.empty_like(input) if need_input else None
@@ -365,6 +420,10 @@ def attach_index(sparse, index):
 
 
 def _fingerprint(indices, values):
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("generalized_rspmm: this sparse operand has no graph index yet, and looking one up reads a "
+                           "fingerprint back to the host, which cannot be captured into a CUDA graph.  Call the operator "
+                           "(or functional.graph_index(sparse)) once on this tensor object before capturing.")
     out = torch.empty(2, dtype=torch.int64, device=indices.device)
     with torch.cuda.device(indices.device):
         _lib.check(_lib.lib().ultra_rspmm_fingerprint(
@@ -400,7 +459,8 @@ def graph_index(sparse):
         index = GraphIndex(indices, values, sparse.shape)
         cache_stats["built"] += 1
         _index_cache[key] = index
-        while len(_index_cache) > max(INDEX_CACHE_SIZE, 1):
+        while len(_index_cache) > 1 and (len(_index_cache) > max(INDEX_CACHE_SIZE, 1) or
+                                         sum(entry.buffer.numel() for entry in _index_cache.values()) > INDEX_CACHE_BYTES):
             _index_cache.popitem(last=False)
     else:
         cache_stats["fingerprint_hit"] += 1

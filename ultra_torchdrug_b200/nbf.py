@@ -16,6 +16,8 @@ Only the rspmm fast path is mirrored (`distmult` / `transe` messages); `rotate` 
 reference's PyTorch fallback, which is out of scope here.  tests/test_nbf_*.py pin this file
 against outputs of the reference's own modules (tests/golden/make_model_golden.py).
 """
+import os
+
 import torch
 from torch import nn
 from torch.nn import functional as F
@@ -28,6 +30,7 @@ from .compat.torchdrug.layers import MLP
 generalized_rspmm = rspmm.generalized_rspmm
 
 MESSAGE_TO_MUL = {"transe": "add", "distmult": "mul"}
+_DEVICE_ASSERTS = os.environ.get("ULTRA_NBF_ASSERT", "1") != "0"
 
 
 def _aggregate(adjacency, relation_input, input, boundary, degree_out, aggregate_func, mul, eps, one_hot=None):
@@ -89,7 +92,9 @@ class _RelationalConvBase(nn.Module):
     def relation_input(self, graph, batch_size):
         raise NotImplementedError
 
-    def message_and_aggregate(self, graph, input):
+    def message_and_aggregate(self, graph, input, one_hot=None):
+        """`one_hot = (node_index, query)`: `graph.boundary` in its sparse form, handed down by the bellmanford loop that
+        built that very boundary (never read from the graph object, whose `boundary` a caller may replace)."""
         if self.message_func not in MESSAGE_TO_MUL:
             raise ValueError("Unknown message function `%s` (only the rspmm fast path is mirrored)" % self.message_func)
         batch_size = len(graph.query)
@@ -99,7 +104,7 @@ class _RelationalConvBase(nn.Module):
         relation_input = self.relation_input(graph, batch_size)
         adjacency = graph.adjacency.transpose(0, 1)
         update = _aggregate(adjacency, relation_input, flat_input, boundary, degree_out, self.aggregate_func,
-                            MESSAGE_TO_MUL[self.message_func], self.eps, getattr(graph, "boundary_one_hot", None))
+                            MESSAGE_TO_MUL[self.message_func], self.eps, one_hot)
         return update.view(len(update), batch_size, -1)
 
     def combine(self, input, update, residual=None):
@@ -120,8 +125,8 @@ class _RelationalConvBase(nn.Module):
             output = self.activation(output)
         return output if residual is None else output + residual
 
-    def forward(self, graph, input, residual=None):
-        return self.combine(input, self.message_and_aggregate(graph, input), residual)
+    def forward(self, graph, input, residual=None, one_hot=None):
+        return self.combine(input, self.message_and_aggregate(graph, input, one_hot), residual)
 
 
 class GeneralizedRelationalConvNBF(_RelationalConvBase):
@@ -222,13 +227,14 @@ def _run_layers_buffered(layers, graph, boundary, short_cut, one_hot=None):
     return buffers[len(layers) % 2]
 
 
-def _run_layers(layers, graph, boundary, short_cut):
+def _run_layers(layers, graph, boundary, short_cut, one_hot=None):
+    """`one_hot = (node_index, query)` must describe `boundary` (the caller derived both from the same query batch)."""
     if _buffered_layers_supported(layers, boundary):
         return _run_layers_buffered(layers, graph, boundary, short_cut)[..., :boundary.shape[-1]]
     hidden = boundary
     for layer in layers:
         skip = hidden if short_cut and layer.output_dim == hidden.shape[-1] else None
-        hidden = layer(graph, hidden, residual=skip)
+        hidden = layer(graph, hidden, residual=skip, one_hot=one_hot)
     return hidden
 
 
@@ -329,8 +335,7 @@ class TransferNBFNet(nn.Module):
         boundary = _one_hot_boundary(graph.num_node, h_index, query)
         with graph.node():
             graph.boundary = boundary
-        graph.boundary_one_hot = (h_index, query)            # the same condition in sparse form (see _aggregate)
-        hidden = _run_layers(self.layers, graph, boundary, self.short_cut)
+        hidden = _run_layers(self.layers, graph, boundary, self.short_cut, one_hot=(h_index, query))
         return torch.cat([hidden, query.expand(graph.num_node, -1, -1)], dim=-1)
 
     def mask_easy_edges(self, graph, h_index, t_index, r_index):
@@ -364,10 +369,13 @@ class TransferNBFNet(nn.Module):
                 graph = self.remove_easy_edges(graph, h_index, t_index, r_index)
             graph = graph.undirected(add_inverse=True)
         h_index, t_index, r_index = self.negative_sample_to_tail(h_index, t_index, r_index, num_relation)
-        # the reference asserts here that every row shares its head and relation (model.py:174-175); on CUDA
-        # tensors that is two host synchronisations per pass, so the mirror only checks host tensors
+        # the reference asserts here that every row shares its head and relation (model.py:174-175).  On CUDA tensors
+        # the check runs on the device without a host synchronisation (a violation raises at the next synchronising
+        # call); ULTRA_NBF_ASSERT=0 drops it
         if not h_index.is_cuda:
             assert (h_index[:, :1] == h_index).all() and (r_index[:, :1] == r_index).all()
+        elif _DEVICE_ASSERTS:
+            torch._assert_async(((h_index[:, :1] == h_index) & (r_index[:, :1] == r_index)).all())
         feature = self.bellmanford(graph, h_index[:, 0], r_index[:, 0])           # (N, B, 2d)
         if isinstance(feature, tuple):
             score = self._split_head(*feature).transpose(0, 1)                    # (B, N)
@@ -410,8 +418,7 @@ class CustomNBFNetFull(nn.Module):
         boundary = _one_hot_boundary(graph.num_node, h_index, query)
         with graph.node():
             graph.boundary = boundary
-        graph.boundary_one_hot = (h_index, query)
-        return _run_layers(self.layers, graph, boundary, self.short_cut).transpose(1, 0)   # (B, num_rel, dim)
+        return _run_layers(self.layers, graph, boundary, self.short_cut, one_hot=(h_index, query)).transpose(1, 0)   # (B, num_rel, dim)
 
 
 class RelNBFNet(nn.Module):
