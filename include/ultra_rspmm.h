@@ -141,6 +141,14 @@ int ultra_rspmm_set_tuning(int32_t chunk, int32_t variant, int64_t l2_budget_byt
  * 2 = whenever the operand fits (tests). */
 int ultra_rspmm_set_staged(int32_t mode);
 
+/* Gather-bandwidth probe (diagnostics, used by bench.py for the roofline denominators it reports): every warp of
+ * `blocks` x 8 reads `iters` (multiple of 4) 512-byte row pieces at pseudo-random rows of dev_buffer (rows x
+ * row_stride_bytes, stride >= 512, % 16 == 0) - the access pattern of the rspmm gather without ids or arithmetic.
+ * A footprint of rows x 512 B well inside L2 measures the L2 -> SM ceiling, one far beyond L2 the HBM ceiling for
+ * random rows.  *bytes_read = blocks * 8 * iters * 512.  Asynchronous; the caller times the stream. */
+int ultra_probe_gather(const void *dev_buffer, int64_t rows, int64_t row_stride_bytes, int32_t iters, int32_t blocks,
+                       float *dev_sink, int64_t *bytes_read, void *stream);
+
 /* ---- index build (replaces sparse.coalesce() + coo2csr3d) ---------- */
 /* Bytes needed for the index arrays (upper bound, from the raw edge count) and for scratch. */
 int ultra_rspmm_index_bytes(int64_t nnz_raw, int32_t n_out, int32_t n_in, int32_t n_rel, int32_t dtype,

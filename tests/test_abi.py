@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     header = open(os.path.join(ROOT, "include", "ultra_rspmm.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
-    return sorted(set(re.findall(r"\b(ultra_(?:rspmm|layer|score)_[a-z_0-9]+)\s*\(", header)))
+    return sorted(set(re.findall(r"\b(ultra_(?:rspmm|layer|score|probe)_[a-z_0-9]+)\s*\(", header)))
 
 
 def test_library_exports_every_declared_symbol():

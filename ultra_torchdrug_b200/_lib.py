@@ -46,6 +46,8 @@ KERNEL_NAMES = {0: "none", 1: "seg_reduce", 2: "seg_gated", 3: "seg_pna", 4: "ro
 SYMBOLS = {
     "ultra_rspmm_last_pass_info": (ctypes.c_int, [c_int32, ctypes.POINTER(PassInfo)]),
     "ultra_rspmm_set_staged": (ctypes.c_int, [c_int32]),
+    "ultra_probe_gather": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, ctypes.POINTER(c_int64),
+                                          c_void_p]),
     "ultra_rspmm_abi_version": (ctypes.c_int, []),
     "ultra_rspmm_last_cuda_error": (ctypes.c_int, []),
     "ultra_rspmm_status_string": (ctypes.c_char_p, [ctypes.c_int]),

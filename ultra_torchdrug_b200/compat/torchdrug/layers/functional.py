@@ -15,3 +15,13 @@ def as_mask(indexes, length):
     mask = torch.zeros(length, dtype=torch.bool, device=indexes.device)
     mask[indexes] = True
     return mask
+
+
+def variadic_sample(input, size, num_sample):
+    """`num_sample` draws with replacement from each of the variadic segments of `input` (segment lengths `size`)
+    [ext-recall of torchdrug.layers.functional.variadic_sample: uniform `torch.rand`, scaled by the segment length and
+    truncated, offset by the segment start].  Reference call sites: ultra/task.py:108,113."""
+    rand = torch.rand(len(size), num_sample, device=size.device)
+    index = (rand * size.unsqueeze(-1)).long()
+    index = index + (size.cumsum(0) - size).unsqueeze(-1)
+    return input[index]
