@@ -414,9 +414,11 @@ def c4_predict(device, rank, world, steps, warmup=2):
         stop.record()
         torch.cuda.synchronize()
     mrr = float((1.0 / ranks.float()).mean())
+    with torch.no_grad():
+        spread = float(predict(batches[-1][start_q:stop_q]).float().std())   # random weights: says whether scores vary at all
     result = {"ms_per_global_batch": start.elapsed_time(stop) / steps, "global_batch": BATCH,
               "batch_per_gpu": stop_q - start_q, "mode": mode, "relation_graph_edges": int(ranker.rel_graph.num_edge),
-              "mrr_last_batch_random_weights": mrr}
+              "mrr_last_batch_random_weights": mrr, "score_std_last_batch": spread}
     del ranker, evaluator, predict, graph
     torch.cuda.empty_cache()
     return result

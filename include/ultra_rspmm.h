@@ -82,6 +82,18 @@ typedef struct ultra_rspmm_order {
                              so a short row does not pay its own task start-up); longer segments appear as in `task` */
 } ultra_rspmm_order_t;
 
+/* Optional extension of the csr / csc order for graphs with at most 4 relation types and at most 864 nodes (the graph
+ * of relations of reference rel_model.py:91-147, which has exactly 4): the edges of a segment that share their other
+ * endpoint are merged into one *pair* word  other-node id | relation mask << id_bits.  A dense graph of relations has 4
+ * edges per pair; the pair kernel reads the other node's row once for all of them. */
+typedef struct ultra_rspmm_pairs {
+    int32_t n_pair;       /* 0: not built                                                     */
+    int32_t id_bits;      /* pair word = other-node id | (bit k set: an edge of relation k) << id_bits */
+    const int32_t *ptr;   /* n_seg + 1: pairs of segment s are [ptr[s], ptr[s + 1]), ascending other-node id */
+    const uint32_t *pair; /* n_pair words                                                     */
+    const int32_t *rows;  /* n_seg: the segments by descending pair count (work order)        */
+} ultra_rspmm_pairs_t;
+
 /* Graph index: int32 device arrays describing the coalesced operand in the three edge orders the
  * kernels walk.  A POD the caller keeps on the host; every pointer points into the caller's
  * `index_buffer` (see ultra_rspmm_index_build).  Replaces coo2csr3d + the per-call
@@ -98,6 +110,14 @@ typedef struct ultra_rspmm_index {
     ultra_rspmm_order_t rel;  /* backward w.r.t. relation: segments = relations, sorted (rel, dst, src); edge = {dst, src} */
     const int32_t *merge_perm;  /* nnz_raw: the caller's edge positions in the order the build merged them            */
     const int32_t *merge_start; /* nnz + 1: csr edge m is the sum of merge_perm[merge_start[m] .. merge_start[m + 1])  */
+    /* ---- optional extensions, filled by ultra_rspmm_index_extend (all zero / null when absent) ---- */
+    ultra_rspmm_pairs_t pairs[2];   /* [0] csr order (forward), [1] csc order (gradient w.r.t. input)                 */
+    const int32_t *block_ptr;   /* n_rel x (n_block + 1): position in the rel order where the edges of relation k with
+                                   destination >= b * block_rows start - a (relation, destination block) run is a
+                                   contiguous range of the rel order (it is sorted by (rel, dst, src))                 */
+    const int32_t *block_split; /* n_rel x int4 {rel, rel * n_block, n_block, 0}: combine list of the blocked pass     */
+    int32_t block_rows;         /* destination rows per block (their grad_output slab is staged in shared memory)      */
+    int32_t n_block;
 } ultra_rspmm_index_t;
 
 /* ---- version / diagnostics ------------------------------------------------------------------- */
@@ -117,7 +137,8 @@ enum {
     ULTRA_RSPMM_KERNEL_SEG_GATED = 2,     /* min / max backward (all-ties gate)                                       */
     ULTRA_RSPMM_KERNEL_SEG_PNA = 3,       /* four PNA aggregates in one pass                                          */
     ULTRA_RSPMM_KERNEL_ROWS_IN_SMEM = 4,  /* few-row operands: the gathered slab is staged in shared memory           */
-    ULTRA_RSPMM_KERNEL_DST_BLOCKED = 5    /* grad_relation with grad_output rows of a destination block in shared memory */
+    ULTRA_RSPMM_KERNEL_DST_BLOCKED = 5,   /* grad_relation with grad_output rows of a destination block in shared memory */
+    ULTRA_RSPMM_KERNEL_PAIRS_IN_SMEM = 6  /* few-row operands with <= 4 relation types: one row read per (node, node) pair */
 };
 typedef struct ultra_rspmm_pass_info {
     int32_t kernel;    /* ULTRA_RSPMM_KERNEL_*                                        */
@@ -140,6 +161,9 @@ int ultra_rspmm_set_tuning(int32_t chunk, int32_t variant, int64_t l2_budget_byt
  * rel_model.py:253-257): 0 = never, 1 = automatic (default: when the slab refills are small against the edge work),
  * 2 = whenever the operand fits (tests). */
 int ultra_rspmm_set_staged(int32_t mode);
+/* Index extensions built by ultra_rspmm_index_extend afterwards (0 = never, 1 = automatic, 2 = whenever the graph
+ * qualifies structurally): pair lists; destination-block table. */
+int ultra_rspmm_set_extensions(int32_t pairs, int32_t blocked);
 
 /* Gather-bandwidth probe (diagnostics, used by bench.py for the roofline denominators it reports): every warp of
  * `blocks` x 8 reads `iters` (multiple of 4) 512-byte row pieces at pseudo-random rows of dev_buffer (rows x
@@ -171,6 +195,17 @@ int ultra_rspmm_index_build(const int64_t *dev_indices, int64_t index_stride, co
 int ultra_rspmm_index_derive_bytes(const ultra_rspmm_index_t *base, size_t *bytes);
 int ultra_rspmm_index_derive(const ultra_rspmm_index_t *base, const void *dev_values, void *buffer, size_t bytes,
                              ultra_rspmm_index_t *derived, void *stream);
+/* Optional extensions of a built index (call once after ultra_rspmm_index_build, before the first forward):
+ *   - pair lists (see ultra_rspmm_pairs_t) when n_rel <= 4, n_out and n_in <= 864, all weights 1 and the edges average
+ *     at least 1.5 per pair: the forward and grad_input passes then run the pair kernel;
+ *   - the destination-block table of the rel order when the two gathered slabs of the grad_relation pass exceed L2
+ *     ((n_out + n_in) x 512 B > 96 MB): grad_relation then stages grad_output rows block by block in shared memory
+ *     and gathers only input rows (3 row gathers per edge and fwd+bwd step instead of 4).
+ * Fills the extension fields of *index; `buffer` (ultra_rspmm_index_extend_bytes, 256-byte aligned) must outlive the
+ * index.  Synchronises `stream`.  Indexes made by ultra_rspmm_index_derive inherit the block table, not the pairs. */
+int ultra_rspmm_index_extend_bytes(const ultra_rspmm_index_t *index, size_t *buffer_bytes);
+int ultra_rspmm_index_extend(ultra_rspmm_index_t *index, void *buffer, size_t buffer_bytes, void *stream);
+
 /* 128-bit content fingerprint of (indices, values) written to dev_out[2] (uint64); lets a caller
  * recognise an edge set it already indexed without a sort.  dev_out must be zero on entry is NOT
  * required (the call clears it).  Asynchronous. */

@@ -28,7 +28,9 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     # ultra_rspmm_order_t: 8 x int32 + 8 pointers; ultra_rspmm_index_t: 2 x int64 + 6 x int32 + 3 orders + 2 pointers
     assert ctypes.sizeof(_lib.Order) == 8 * 4 + 8 * 8
-    assert ctypes.sizeof(_lib.Index) == 2 * 8 + 6 * 4 + 3 * ctypes.sizeof(_lib.Order) + 2 * 8
+    assert ctypes.sizeof(_lib.Pairs) == 2 * 4 + 3 * 8
+    assert ctypes.sizeof(_lib.Index) == 2 * 8 + 6 * 4 + 3 * ctypes.sizeof(_lib.Order) + 2 * 8 + 2 * ctypes.sizeof(_lib.Pairs) \
+        + 2 * 8 + 2 * 4
 
 
 def test_version_status_and_argument_validation():

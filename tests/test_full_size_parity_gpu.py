@@ -39,8 +39,13 @@ CASES = {
                expect={"fwd": dict(keep=1, grouped=1), "gin": dict(keep=1, grouped=1), "grel": dict(keep=1, split=True)}),
     "c3_wide": dict(graph="codex_l", dim=4096, slabs=(3, 30), ops=[("add", "mul"), ("max", "mul")],
                     expect={"fwd": dict(keep=1, grouped=1)}),
-    "c4": dict(graph="yago310", dim=4096, slabs=(0, 13, 31),
-               expect={"fwd": dict(keep=1, grouped=1), "gin": dict(keep=1, grouped=1), "grel": dict(keep=1, split=True)}),
+    # C4: both gathered slabs of grad_relation together (126 MB) exceed what L2 holds -> destination-blocked pass
+    "c4": dict(graph="yago310", dim=4096, slabs=(0, 13, 31), grel_kernel="dst_blocked",
+               expect={"fwd": dict(keep=1, grouped=1), "gin": dict(keep=1, grouped=1), "grel": dict(split=True)}),
+    # a shape of the configs[4] sweep (E = 4 M, N = E / 32, R' = 474): HBM-resident slabs, 1.3 M (relation, block) runs
+    "c5_4m": dict(uniform=(1 << 22, 1 << 17, 474), dim=1024, slabs=(0, 5), grel_kernel="dst_blocked",
+                  ops=[("add", "mul"), ("add", "add"), ("max", "mul")],
+                  expect={"fwd": dict(keep=1, grouped=0), "grel": dict(split=True)}),
     # WN18RR-like: in-degree 4.2 -> grouped; 21 MB slab: no hints forward, hints for grad_relation (two gathered operands)
     "wn18rr": dict(graph="wn18rr", dim=4096, slabs=(0, 16, 31),
                    expect={"fwd": dict(keep=0, grouped=1), "gin": dict(keep=0, grouped=1), "grel": dict(keep=1, split=True)}),
@@ -60,9 +65,15 @@ class _Case(object):
         from oracle import cpu_ref
         from ultra_torchdrug_b200 import functional as F, synthetic
         spec = CASES[name]
-        edge_list, n, r = synthetic.named_graph(spec["graph"], **spec.get("options", {}))
+        if "uniform" in spec:
+            e_raw, n, r = spec["uniform"]
+            generator = torch.Generator().manual_seed(1024)
+            indices = torch.stack([torch.randint(n, (e_raw,), generator=generator), torch.randint(n, (e_raw,), generator=generator),
+                                   torch.randint(r, (e_raw,), generator=generator)])
+        else:
+            edge_list, n, r = synthetic.named_graph(spec["graph"], **spec.get("options", {}))
+            indices = edge_list[:, [1, 0, 2]].t().contiguous()
         self.spec, self.n, self.r, self.dim = spec, n, r, spec["dim"]
-        indices = edge_list[:, [1, 0, 2]].t().contiguous()
         values = torch.ones(indices.shape[1])
         self.index = F.GraphIndex(indices.to(device), values.to(device), (n, n, r))
         self.csr = cpu_ref.CsrOperand(indices.numpy(), values.numpy(), (n, n, r))
@@ -135,7 +146,8 @@ def test_full_size_matches_oracle(cuda, name, sum, mul):
         assert forward_info["grouped"] == 0
     _check_info(forward_info, want, "forward")
     backward_kernel = "seg_reduce" if sum == "add" else "seg_gated"
-    assert gin_info["kernel_name"] == backward_kernel and grel_info["kernel_name"] == backward_kernel
+    assert gin_info["kernel_name"] == backward_kernel
+    assert grel_info["kernel_name"] == (case.spec.get("grel_kernel", "seg_reduce") if sum == "add" else "seg_gated"), grel_info
     if sum == "add":
         _check_info(gin_info, expect.get("gin", {}), "grad_input")
         want = dict(expect.get("grel", {}))
@@ -196,43 +208,46 @@ def _relation_graph_operand(device, name="fb15k237"):
 @pytest.mark.parametrize("mul", ["mul", "add"])
 @pytest.mark.parametrize("dim", [4096, 1000])
 def test_relation_graph_full_size_matches_oracle(cuda, mul, dim):
-    """C2's graph of relations (474 nodes, 898,704 edges, 4 edge types) at the inference width: the forward and the
-    grad_input pass must be served by the rows-in-shared-memory kernel and agree with the oracle element-wise."""
+    """C2's graph of relations (474 nodes, 898,704 edges, 4 edge types) at the inference width.  By default the forward and
+    the grad_input pass are served by the pair kernel (4 edges per (node, node) pair); without pair lists by the
+    rows-in-shared-memory kernel; without either by the generic kernel.  All three agree with the oracle element-wise."""
     from oracle import cpu_ref
     from ultra_torchdrug_b200 import functional as F, _lib
+    lib = _lib.lib()
     indices, n = _relation_graph_operand(cuda)
     values = torch.ones(indices.shape[1])
-    index = F.GraphIndex(indices.to(cuda), values.to(cuda), (n, n, 4))
     csr = cpu_ref.CsrOperand(indices.numpy(), values.numpy(), (n, n, 4))
     generator = torch.Generator(device=cuda).manual_seed(7)
     relation = torch.randn(4, dim, device=cuda, generator=generator)
     input = torch.randn(n, dim, device=cuda, generator=generator)
     grad = torch.randn(n, dim, device=cuda, generator=generator)
-    out = index.forward(relation, input, "add", mul)
-    info = _lib.pass_info(_lib.PASS_FORWARD)
-    assert info["kernel_name"] == "rows_in_smem" and info["n_split"] > 0, info
-    g_rel, g_in = index.backward(relation, input, out, grad, "add", mul)
-    torch.cuda.synchronize()
-    assert _lib.pass_info(_lib.PASS_GRAD_INPUT)["kernel_name"] == "rows_in_smem"
     columns = _columns(dim, (0, 15, 31) if dim == 4096 else None)
     pick = torch.from_numpy(columns).to(cuda)
     host = lambda t: t.index_select(1, pick).cpu().numpy()
     relation_h, input_h, grad_h = host(relation), host(input), host(grad)
-    _assert_close(host(out), cpu_ref.forward_f64(csr, relation_h, input_h, mul),
-                  cpu_ref.forward_f64(csr, relation_h, input_h, mul, absolute=True), "forward")
+    want = cpu_ref.forward_f64(csr, relation_h, input_h, mul)
+    scale = cpu_ref.forward_f64(csr, relation_h, input_h, mul, absolute=True)
     want_rel, want_in = cpu_ref.backward_f64(csr, relation_h, input_h, None, grad_h, "add", mul)
     scale_rel, scale_in = cpu_ref.backward_f64(csr, relation_h, input_h, None, grad_h, "add", mul, absolute=True)
-    _assert_close(host(g_rel), want_rel, scale_rel, "grad_relation")
-    _assert_close(host(g_in), want_in, scale_in, "grad_input")
-    # same bits as the generic kernel?  No: the two kernels sum a task's edges in different orders.  Same bits run to run:
-    again = index.forward(relation, input, "add", mul)
-    assert torch.equal(out, again)
-    # and the generic kernel on the same operands stays within the same bound
-    _lib.check(_lib.lib().ultra_rspmm_set_staged(0), "ultra_rspmm_set_staged")
+
+    def run(expected_kernel):
+        index = F.GraphIndex(indices.to(cuda), values.to(cuda), (n, n, 4))
+        out = index.forward(relation, input, "add", mul)
+        assert _lib.pass_info(_lib.PASS_FORWARD)["kernel_name"] == expected_kernel, _lib.pass_info(_lib.PASS_FORWARD)
+        g_rel, g_in = index.backward(relation, input, out, grad, "add", mul)
+        torch.cuda.synchronize()
+        assert _lib.pass_info(_lib.PASS_GRAD_INPUT)["kernel_name"] == expected_kernel
+        _assert_close(host(out), want, scale, "forward (%s)" % expected_kernel)
+        _assert_close(host(g_rel), want_rel, scale_rel, "grad_relation")
+        _assert_close(host(g_in), want_in, scale_in, "grad_input (%s)" % expected_kernel)
+        assert torch.equal(out, index.forward(relation, input, "add", mul)), "two runs differ"
+
+    run("pairs_in_smem")
     try:
-        generic = index.forward(relation, input, "add", mul)
-        assert _lib.pass_info(_lib.PASS_FORWARD)["kernel_name"] == "seg_reduce"
+        _lib.check(lib.ultra_rspmm_set_extensions(0, 1), "ultra_rspmm_set_extensions")
+        run("rows_in_smem")
+        _lib.check(lib.ultra_rspmm_set_staged(0), "ultra_rspmm_set_staged")
+        run("seg_reduce")
     finally:
-        _lib.check(_lib.lib().ultra_rspmm_set_staged(1), "ultra_rspmm_set_staged")
-    _assert_close(host(generic), cpu_ref.forward_f64(csr, relation_h, input_h, mul),
-                  cpu_ref.forward_f64(csr, relation_h, input_h, mul, absolute=True), "forward (generic kernel)")
+        _lib.check(lib.ultra_rspmm_set_extensions(1, 1), "ultra_rspmm_set_extensions")
+        _lib.check(lib.ultra_rspmm_set_staged(1), "ultra_rspmm_set_staged")

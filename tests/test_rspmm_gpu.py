@@ -785,3 +785,117 @@ def test_graph_index_lookup_refuses_stream_capture(cuda):
         captured.replay()
         torch.cuda.synchronize()
     assert torch.equal(out, expected)
+
+
+# ---- index extensions: pair lists (graph of relations) and the destination-block table ----------------------------------
+@pytest.fixture
+def extensions_always():
+    from ultra_torchdrug_b200 import _lib
+    _lib.check(_lib.lib().ultra_rspmm_set_extensions(2, 2), "ultra_rspmm_set_extensions")
+    yield _lib
+    _lib.check(_lib.lib().ultra_rspmm_set_extensions(1, 1), "ultra_rspmm_set_extensions")
+
+
+def _relation_like_graph(n, density, seed):
+    """(3, E) COO of a 4-relation graph over n nodes: every (dst, src) pair present with probability `density`, carrying a
+    random non-empty subset of the 4 relations - the structure `construct_relation_graph` produces."""
+    rng = np.random.default_rng(seed)
+    present = rng.random((n, n)) < density
+    masks = rng.integers(1, 16, (n, n)) * present
+    masks[n - 1] = 0                                                   # an empty destination row
+    rows, cols, rels = [], [], []
+    for k in range(4):
+        r, c = np.nonzero(masks & (1 << k))
+        rows.append(r); cols.append(c); rels.append(np.full(len(r), k))
+    indices = np.stack([np.concatenate(rows), np.concatenate(cols), np.concatenate(rels)]).astype(np.int64)
+    return indices[:, rng.permutation(indices.shape[1])]
+
+
+@pytest.mark.parametrize("mul", ["mul", "add"])
+@pytest.mark.parametrize("n,density,dim", [(50, 1.0, 256), (97, 0.3, 64), (200, 0.05, 132), (864, 0.02, 60)])
+def test_pair_kernel_parity(cuda, extensions_always, mul, n, density, dim):
+    """The pair kernel (<= 4 relation types, unit weights, <= 864 nodes: the graph of relations) against the oracle:
+    forward and grad_input are served by it, every (node, node) pair read once for up to 4 edges."""
+    from oracle import rspmm_oracle
+    from ultra_torchdrug_b200 import functional as F
+    lib = extensions_always
+    indices = _relation_like_graph(n, density, seed=n)
+    values = np.ones(indices.shape[1], dtype=np.float32)
+    shape = (n, n, 4)
+    index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), shape)
+    assert index.c.pairs[0].n_pair > 0 and index.c.pairs[1].n_pair > 0
+    coalesced, _, _ = rspmm_oracle.coalesce(indices, values, shape)
+    assert index.c.pairs[0].n_pair == len(np.unique(coalesced[0] * n + coalesced[1]))
+    relation, input, grad = util.random_dense(4, dim, 1), util.random_dense(n, dim, 2), util.random_dense(n, dim, 3)
+    d_rel, d_in, d_grad = (torch.from_numpy(x).to(cuda) for x in (relation, input, grad))
+    out = index.forward(d_rel, d_in, "add", mul)
+    assert lib.pass_info(lib.PASS_FORWARD)["kernel_name"] == "pairs_in_smem"
+    g_rel, g_in = index.backward(d_rel, d_in, out, d_grad, "add", mul)
+    assert lib.pass_info(lib.PASS_GRAD_INPUT)["kernel_name"] == "pairs_in_smem"
+    exp, _ = util.oracle_forward(indices, values, shape, relation, input, "add", mul, dtype=np.float64)
+    scale, _ = util.oracle_forward(indices, values, shape, np.abs(relation), np.abs(input), "add", mul, dtype=np.float64)
+    _assert_sum_close(out.cpu().numpy(), exp, scale, "pair forward")
+    e_rel, e_in = util.oracle_backward(indices, values, shape, relation, input, None, grad, "add", mul, dtype=np.float64)
+    s_rel, s_in = util.oracle_backward(indices, values, shape, np.abs(relation), np.abs(input), None, np.abs(grad), "add", mul,
+                                       dtype=np.float64)
+    _assert_sum_close(g_in.cpu().numpy(), e_in, s_in, "pair grad_input")
+    _assert_sum_close(g_rel.cpu().numpy(), e_rel, s_rel, "grad_relation")
+    assert torch.equal(out, index.forward(d_rel, d_in, "add", mul)), "two runs differ"
+    with_addend = index.forward(d_rel, d_in, "add", mul, addend=d_grad)
+    _assert_sum_close(with_addend.cpu().numpy(), exp + grad, scale + np.abs(grad), "pair forward + addend")
+    # min / max and non-unit weights keep the edge kernels
+    index.forward(d_rel, d_in, "max", mul)
+    assert lib.pass_info(lib.PASS_FORWARD)["kernel_name"] == "seg_reduce"
+
+
+def test_pair_kernel_blocked_layout_and_weighted_fallback(cuda, extensions_always):
+    from ultra_torchdrug_b200 import functional as F
+    lib = extensions_always
+    n, batch, width = 60, 3, 64
+    indices = _relation_like_graph(n, 0.5, seed=4)
+    values = np.ones(indices.shape[1], dtype=np.float32)
+    index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), (n, n, 4))
+    generator = torch.Generator(device=cuda).manual_seed(3)
+    buffer = torch.randn(n, batch, 2 * width, device=cuda, generator=generator)
+    relation = torch.randn(4, batch * width, device=cuda, generator=generator)
+    plain = index.forward(relation, buffer[..., :width].reshape(n, -1).contiguous(), "add", "mul")
+    index.forward_blocked(relation, buffer, buffer, width, 0, width, "mul")
+    assert lib.pass_info(lib.PASS_FORWARD)["kernel_name"] == "pairs_in_smem"
+    assert torch.equal(buffer[..., width:].reshape(n, -1), plain)
+    # duplicates merge into weight 2: no pair lists, the edge kernels serve the graph
+    doubled = np.concatenate([indices, indices[:, :10]], axis=1)
+    weighted = F.GraphIndex(torch.from_numpy(doubled).to(cuda), torch.ones(doubled.shape[1], device=cuda), (n, n, 4))
+    assert weighted.c.pairs[0].n_pair == 0
+    weighted.forward(relation, buffer[..., :width].reshape(n, -1).contiguous(), "add", "mul")
+    assert lib.pass_info(lib.PASS_FORWARD)["kernel_name"] in ("rows_in_smem", "seg_reduce")
+
+
+@pytest.mark.parametrize("mul", ["mul", "add"])
+@pytest.mark.parametrize("weights", ["unit", "random"])
+@pytest.mark.parametrize("n,n_rel,nnz,dim", [(2000, 7, 30000, 192), (1700, 40, 9000, 64), (800, 3, 5000, 100)])
+def test_destination_blocked_grad_relation_parity(cuda, extensions_always, mul, weights, n, n_rel, nnz, dim):
+    """grad_relation through the destination-blocked kernel (forced on): grad_output rows of a 768-row block staged in
+    shared memory, input rows gathered, one partial row per (relation, block), folded in block order."""
+    from ultra_torchdrug_b200 import functional as F
+    lib = extensions_always
+    indices, values = util.random_coo(n, n - 50, n_rel, nnz, seed=nnz, duplicates=100, weights=weights, skew=True)
+    shape = (n, n - 50, n_rel)
+    index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), shape)
+    assert index.c.n_block == (n + 767) // 768 and index.c.block_rows == 768
+    relation, input, grad = util.random_dense(n_rel, dim, 1), util.random_dense(n - 50, dim, 2), util.random_dense(n, dim, 3)
+    d_rel, d_in, d_grad = (torch.from_numpy(x).to(cuda) for x in (relation, input, grad))
+    g_rel, g_in = index.backward(d_rel, d_in, None, d_grad, "add", mul)
+    assert lib.pass_info(lib.PASS_GRAD_RELATION)["kernel_name"] == "dst_blocked"
+    e_rel, e_in = util.oracle_backward(indices, values, shape, relation, input, None, grad, "add", mul, dtype=np.float64)
+    s_rel, s_in = util.oracle_backward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), None, np.abs(grad),
+                                       "add", mul, dtype=np.float64)
+    _assert_sum_close(g_rel.cpu().numpy(), e_rel, s_rel, "blocked grad_relation")
+    _assert_sum_close(g_in.cpu().numpy(), e_in, s_in, "grad_input")
+    again, _ = index.backward(d_rel, d_in, None, d_grad, "add", mul)
+    assert torch.equal(g_rel, again), "two runs differ"
+    # a derived index (same structure, other weights) inherits the block table
+    new_values = torch.from_numpy(values).to(cuda) * 0.5
+    derived = index.derive(new_values)
+    h_rel, _ = derived.backward(d_rel, d_in, None, d_grad, "add", mul)
+    assert lib.pass_info(lib.PASS_GRAD_RELATION)["kernel_name"] == "dst_blocked"
+    _assert_sum_close(h_rel.cpu().numpy(), 0.5 * e_rel, 0.5 * s_rel, "blocked grad_relation of a derived index")

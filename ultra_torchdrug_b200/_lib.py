@@ -26,11 +26,18 @@ class Order(ctypes.Structure):
                 ("task", c_void_p), ("split", c_void_p), ("gtask", c_void_p)]
 
 
+class Pairs(ctypes.Structure):
+    """`ultra_rspmm_pairs_t`"""
+    _fields_ = [("n_pair", c_int32), ("id_bits", c_int32), ("ptr", c_void_p), ("pair", c_void_p), ("rows", c_void_p)]
+
+
 class Index(ctypes.Structure):
     """`ultra_rspmm_index_t`"""
     _fields_ = [("nnz", c_int64), ("nnz_raw", c_int64), ("n_out", c_int32), ("n_in", c_int32), ("n_rel", c_int32),
                 ("dtype", c_int32), ("unit_weight", c_int32), ("chunk", c_int32),
-                ("csr", Order), ("csc", Order), ("rel", Order), ("merge_perm", c_void_p), ("merge_start", c_void_p)]
+                ("csr", Order), ("csc", Order), ("rel", Order), ("merge_perm", c_void_p), ("merge_start", c_void_p),
+                ("pairs", Pairs * 2), ("block_ptr", c_void_p), ("block_split", c_void_p), ("block_rows", c_int32),
+                ("n_block", c_int32)]
 
 
 class PassInfo(ctypes.Structure):
@@ -40,12 +47,16 @@ class PassInfo(ctypes.Structure):
 
 
 PASS_FORWARD, PASS_GRAD_INPUT, PASS_GRAD_RELATION = 0, 1, 2
-KERNEL_NAMES = {0: "none", 1: "seg_reduce", 2: "seg_gated", 3: "seg_pna", 4: "rows_in_smem", 5: "dst_blocked"}
+KERNEL_NAMES = {0: "none", 1: "seg_reduce", 2: "seg_gated", 3: "seg_pna", 4: "rows_in_smem", 5: "dst_blocked",
+                6: "pairs_in_smem"}
 
 #: every symbol `include/ultra_rspmm.h` declares: name -> (restype, argtypes)
 SYMBOLS = {
     "ultra_rspmm_last_pass_info": (ctypes.c_int, [c_int32, ctypes.POINTER(PassInfo)]),
     "ultra_rspmm_set_staged": (ctypes.c_int, [c_int32]),
+    "ultra_rspmm_set_extensions": (ctypes.c_int, [c_int32, c_int32]),
+    "ultra_rspmm_index_extend_bytes": (ctypes.c_int, [ctypes.POINTER(Index), ctypes.POINTER(c_size_t)]),
+    "ultra_rspmm_index_extend": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_size_t, c_void_p]),
     "ultra_probe_gather": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, ctypes.POINTER(c_int64),
                                           c_void_p]),
     "ultra_rspmm_abi_version": (ctypes.c_int, []),

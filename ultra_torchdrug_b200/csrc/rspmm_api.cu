@@ -103,6 +103,7 @@ struct ultra_rspmm_ctx {
     bool has_graph = false;
     ultra_rspmm_index_t index;
     void *index_buffer = nullptr;
+    void *extension = nullptr;
     void *tmp = nullptr;
     size_t tmp_cap = 0;
     void *buf[kSets][BUF_KINDS] = {};
@@ -153,6 +154,7 @@ extern "C" int ultra_rspmm_ctx_destroy(ultra_rspmm_ctx_t *ctx) {
     }
     for (cudaEvent_t e : ctx->tick) cudaEventDestroy(e);
     if (ctx->index_buffer) cudaFree(ctx->index_buffer);
+    if (ctx->extension) cudaFree(ctx->extension);
     if (ctx->tmp) cudaFree(ctx->tmp);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream_in);
@@ -186,6 +188,14 @@ extern "C" int ultra_rspmm_ctx_set_graph(ultra_rspmm_ctx_t *ctx, const int64_t *
                                      ctx->index_buffer, index_bytes, tmp + idx_bytes + val_bytes, scratch_bytes,
                                      &ctx->index, ctx->stream);
     if (status) return status;
+    size_t extend_bytes = 0;
+    if ((status = ultra_rspmm_index_extend_bytes(&ctx->index, &extend_bytes))) return status;
+    if (ctx->extension) ULTRA_CUDA_OK(cudaFree(ctx->extension));
+    ctx->extension = nullptr;
+    if (extend_bytes) {
+        ULTRA_CUDA_OK(cudaMalloc(&ctx->extension, extend_bytes));
+        if ((status = ultra_rspmm_index_extend(&ctx->index, ctx->extension, extend_bytes, ctx->stream))) return status;
+    }
     ctx->has_graph = true;
     return ULTRA_RSPMM_OK;
 }
@@ -224,9 +234,26 @@ static int ctx_run_pipeline(ultra_rspmm_ctx_t *ctx, const void *host_relation, c
     int64_t chunk_target = kChunkCols;
     if (const char *env = getenv("ULTRA_RSPMM_CHUNK_COLS")) chunk_target = atoll(env) > 0 ? atoll(env) : kChunkCols;
     const int64_t chunk_cols = dim < chunk_target ? dim : chunk_target;
-    const int n_chunk = dim == 0 ? 0 : (int)((dim + chunk_cols - 1) / chunk_cols);
     ctx->last_ms = 0.f;
-    if (n_chunk == 0) return ULTRA_RSPMM_OK;
+    if (dim == 0) return ULTRA_RSPMM_OK;
+    // chunk boundaries.  The upload of the first chunk and the download of the last one overlap with nothing, so with
+    // four or more chunks those two are half as wide (a multiple of the 128-feature slab)
+    std::vector<int64_t> bounds;
+    bounds.push_back(0);
+    {
+        const int64_t full = (dim + chunk_cols - 1) / chunk_cols;
+        const int64_t edge = full >= 4 && chunk_cols % 256 == 0 ? chunk_cols / 2 : chunk_cols;
+        int64_t at = edge < dim ? edge : dim;
+        bounds.push_back(at);
+        while (at < dim) {
+            int64_t next = at + chunk_cols;
+            if (dim - at <= chunk_cols + edge && dim - at > edge && edge != chunk_cols) next = dim - edge;   // leave a half chunk
+            if (next > dim) next = dim;
+            bounds.push_back(next);
+            at = next;
+        }
+    }
+    const int n_chunk = (int)bounds.size() - 1;
 
     size_t fwd_ws = 0, bwd_ws = 0;
     int status = ultra_rspmm_workspace_bytes(&ix, chunk_cols, ix.dtype, &fwd_ws, &bwd_ws);
@@ -254,8 +281,8 @@ static int ctx_run_pipeline(ultra_rspmm_ctx_t *ctx, const void *host_relation, c
     const size_t host_pitch = (size_t)dim * elem;
     for (int c = 0; c < n_chunk; ++c) {
         const int s = c % kSets;
-        const int64_t col0 = (int64_t)c * chunk_cols;
-        const int64_t cols = dim - col0 < chunk_cols ? dim - col0 : chunk_cols;
+        const int64_t col0 = bounds[c];
+        const int64_t cols = bounds[c + 1] - col0;
         const size_t width = (size_t)cols * elem, offset = (size_t)col0 * elem;
         void **b = ctx->buf[s];
         // upload (the set's previous chunk must have been downloaded)

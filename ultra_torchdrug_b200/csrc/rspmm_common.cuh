@@ -203,6 +203,41 @@ struct StagedArgs {
 };
 int launch_rows_in_smem(StagedArgs args, int msg, cudaStream_t stream);
 
+// pair kernel (<= 4 relation types, unit weights): one shared-memory row read per (segment, other node) pair
+struct PairArgs {
+    const int32_t *ptr;       // n_seg + 1
+    const uint32_t *pair;     // other | mask << id_bits
+    const int32_t *rows;      // segments by descending pair count
+    int id_bits;
+    const float *A;           // gathered operand (n_rows rows, staged slab by slab)
+    const float *B;           // relation table, n_rel <= 4 rows (unused for MSG_COPY)
+    float *out;
+    const float *addend;
+    unsigned *counter;
+    long long dim;
+    int n_seg, n_rows, n_rel, n_slab;
+    long long a_stride, o_stride, o_offset, a_row, o_row;
+    int block, block_shift;
+};
+int launch_pairs_in_smem(PairArgs args, int msg, cudaStream_t stream);
+
+// grad_relation with the grad_output rows of a destination block staged in shared memory (rel order + block table)
+struct BlockedRelArgs {
+    const int32_t *block_ptr; // n_rel x (n_block + 1)
+    const int2 *edge;         // rel order: {dst, src}
+    const unsigned *packed;   // or null
+    int pack_shift;
+    const float *w;           // rel-order weights, null when all 1
+    const float *G;           // grad_output (n_out, dim): staged
+    const float *X;           // input (n_in, dim): gathered (unused for MSG_COPY)
+    float *partial;           // (n_rel * n_block, dim)
+    unsigned *counter;
+    long long dim;
+    int n_rel, n_block, block_rows, n_out, n_slab;
+};
+int launch_dst_blocked(BlockedRelArgs args, int msg, cudaStream_t stream);
+extern int g_pairs, g_blocked;
+
 // launch bookkeeping (claimed in bench.py as `gpu_launches`)
 void note_launch();
 // how the last pass of each kind was launched (ultra_rspmm_last_pass_info; read by the parity tests)

@@ -655,6 +655,12 @@ static size_t slot_bytes(const ultra_rspmm_order_t &order, long long dim, size_t
     return bytes;
 }
 
+// workspace of the destination-blocked grad_relation pass: n_rel x n_block partial rows + its work counter
+static size_t blocked_bytes(const ultra_rspmm_index_t &ix, long long dim) {
+    if (!ix.block_ptr || ix.dtype != ULTRA_RSPMM_F32) return 0;
+    return align_up((size_t)ix.n_rel * ix.n_block * dim * sizeof(float)) + 256;
+}
+
 // Few-row operands (the graph of relations): the gathered operand's 64-feature slab fits shared memory and every edge
 // reads it from there (rspmm_staged.cu).  Worth it when the refills (one per CTA and slab change) are small against the
 // edge work: at least ~16 edges per staged row and SM.
@@ -670,7 +676,7 @@ bool staged_applies(const ultra_rspmm_order_t &order, long long rows_gathered, l
 }
 
 template <typename T, int SUM, int MSG, bool B_TABLE, bool ARG>
-int run_pass(int pass, const ultra_rspmm_order_t &order, long long nnz, bool unit_weight, const T *A, const T *B,
+int run_pass(int pass, const ultra_rspmm_index_t &ix, const ultra_rspmm_order_t &order, bool unit_weight, const T *A, const T *B,
              long long rows_gathered, T *out, int32_t *arg_out, long long dim, void *workspace, size_t workspace_bytes,
              cudaStream_t stream,
              const T *addend = nullptr, const BlockedLayout layout = BlockedLayout()) {
@@ -704,7 +710,55 @@ int run_pass(int pass, const ultra_rspmm_order_t &order, long long nnz, bool uni
     info.packed = order.pack_shift > 0;
     info.n_split = order.n_split;
     const size_t counter_at = slot_bytes(order, dim, sizeof(T), ARG);
-    if (staged_applies<T, SUM, MSG, B_TABLE, ARG>(order, rows_gathered, dim, vec, nnz, workspace, workspace_bytes, counter_at)) {
+    const bool counter_ok = workspace && workspace_bytes >= counter_at + sizeof(unsigned);
+    // <= 4 relation types, few rows, unit weights, pair lists built (ultra_rspmm_index_extend): one row read per pair
+    if (std::is_same<T, float>::value && SUM == ULTRA_RSPMM_SUM_ADD && B_TABLE && !ARG && pass != GREL && vec == 4 && g_pairs != 0 &&
+        unit_weight && ix.unit_weight && ix.pairs[pass == GIN ? 1 : 0].n_pair > 0 && rows_gathered <= kStagedMaxRows && counter_ok) {
+        const ultra_rspmm_pairs_t &pairs = ix.pairs[pass == GIN ? 1 : 0];
+        PairArgs pa = {};
+        pa.ptr = pairs.ptr; pa.pair = pairs.pair; pa.rows = pairs.rows; pa.id_bits = pairs.id_bits;
+        pa.A = (const float *)A; pa.B = (const float *)B; pa.out = (float *)out; pa.addend = (const float *)addend;
+        pa.counter = (unsigned *)((char *)workspace + counter_at);
+        pa.dim = dim; pa.n_seg = order.n_seg; pa.n_rows = (int)rows_gathered; pa.n_rel = ix.n_rel;
+        pa.a_stride = args.a_stride; pa.o_stride = args.o_stride; pa.o_offset = args.o_offset;
+        pa.a_row = args.a_row; pa.o_row = args.o_row; pa.block = args.block; pa.block_shift = args.block_shift;
+        if (int status = launch_pairs_in_smem(pa, MSG, stream)) return status;
+        info.kernel = ULTRA_RSPMM_KERNEL_PAIRS_IN_SMEM;
+        info.vec = 4;
+        info.n_task = order.n_seg;
+        info.n_slab = (int)((dim + kStagedSlab - 1) / kStagedSlab);
+        info.n_split = 0;
+        note_pass(pass, info);
+        return ULTRA_RSPMM_OK;     // whole rows per warp: no partial rows, no combine
+    }
+    // grad_relation of graphs whose gathered slabs exceed L2: destination-blocked pass (3 row gathers per edge and step)
+    if (std::is_same<T, float>::value && SUM == ULTRA_RSPMM_SUM_ADD && !ARG && pass == GREL && vec == 4 && g_blocked != 0 &&
+        ix.block_ptr && !layout.block && !addend && workspace &&
+        workspace_bytes >= blocked_bytes(ix, dim) && blocked_bytes(ix, dim) <= (16ull << 30)) {
+        BlockedRelArgs ba = {};
+        ba.block_ptr = ix.block_ptr;
+        ba.edge = (const int2 *)order.edge;
+        ba.packed = order.pack_shift > 0 ? (const unsigned *)order.packed : nullptr;
+        ba.pack_shift = order.pack_shift;
+        ba.w = unit_weight ? nullptr : (const float *)order.w;
+        ba.G = (const float *)A;
+        ba.X = (const float *)B;
+        ba.partial = (float *)workspace;
+        ba.counter = (unsigned *)((char *)workspace + blocked_bytes(ix, dim) - 256);
+        ba.dim = dim; ba.n_rel = ix.n_rel; ba.n_block = ix.n_block; ba.block_rows = ix.block_rows; ba.n_out = ix.n_out;
+        if (int status = launch_dst_blocked(ba, MSG, stream)) return status;
+        info.kernel = ULTRA_RSPMM_KERNEL_DST_BLOCKED;
+        info.vec = 4;
+        info.n_task = ix.n_rel * ix.n_block;
+        info.n_slab = (int)((dim + kStagedSlab - 1) / kStagedSlab);
+        info.n_split = ix.n_rel;
+        note_pass(pass, info);
+        ultra_rspmm_order_t folded = order;      // combine list: relation k <- its n_block partial rows, in block order
+        folded.split = ix.block_split;
+        folded.n_split = ix.n_rel;
+        return launch_combine<T, SUM, ARG>(folded, (const T *)workspace, nullptr, out, nullptr, dim, stream);
+    }
+    if (staged_applies<T, SUM, MSG, B_TABLE, ARG>(order, rows_gathered, dim, vec, ix.nnz, workspace, workspace_bytes, counter_at)) {
         StagedArgs staged = {};
         staged.task = (const int4 *)order.task;
         staged.packed = (const unsigned *)order.packed;
@@ -813,12 +867,12 @@ int forward_sum(const ultra_rspmm_index_t &ix, const T *relation, const T *input
     const bool unit = ix.unit_weight != 0;
     if (SUM != ULTRA_RSPMM_SUM_ADD && argidx) {
         if (mul_op == ULTRA_RSPMM_MUL_MUL)
-            return run_pass<T, SUM, MSG_MUL, true, true>(FWD, ix.csr, ix.nnz, unit, input, relation, ix.n_in, output, argidx, dim, ws, ws_bytes, stream);
-        return run_pass<T, SUM, MSG_ADD, true, true>(FWD, ix.csr, ix.nnz, unit, input, relation, ix.n_in, output, argidx, dim, ws, ws_bytes, stream);
+            return run_pass<T, SUM, MSG_MUL, true, true>(FWD, ix, ix.csr, unit, input, relation, ix.n_in, output, argidx, dim, ws, ws_bytes, stream);
+        return run_pass<T, SUM, MSG_ADD, true, true>(FWD, ix, ix.csr, unit, input, relation, ix.n_in, output, argidx, dim, ws, ws_bytes, stream);
     }
     if (mul_op == ULTRA_RSPMM_MUL_MUL)
-        return run_pass<T, SUM, MSG_MUL, true, false>(FWD, ix.csr, ix.nnz, unit, input, relation, ix.n_in, output, nullptr, dim, ws, ws_bytes, stream, addend);
-    return run_pass<T, SUM, MSG_ADD, true, false>(FWD, ix.csr, ix.nnz, unit, input, relation, ix.n_in, output, nullptr, dim, ws, ws_bytes, stream, addend);
+        return run_pass<T, SUM, MSG_MUL, true, false>(FWD, ix, ix.csr, unit, input, relation, ix.n_in, output, nullptr, dim, ws, ws_bytes, stream, addend);
+    return run_pass<T, SUM, MSG_ADD, true, false>(FWD, ix, ix.csr, unit, input, relation, ix.n_in, output, nullptr, dim, ws, ws_bytes, stream, addend);
 }
 
 template <typename T>
@@ -846,14 +900,14 @@ int backward_typed(const ultra_rspmm_index_t &ix, const void *relation, const vo
     if (sum_op == ULTRA_RSPMM_SUM_ADD) {
         if (gx) {
             status = mul_op == ULTRA_RSPMM_MUL_MUL
-                         ? run_pass<T, ADD, MSG_MUL, true, false>(GIN, ix.csc, ix.nnz, unit, g, r, ix.n_out, gx, nullptr, dim, ws, ws_bytes, stream)
-                         : run_pass<T, ADD, MSG_COPY, true, false>(GIN, ix.csc, ix.nnz, unit, g, r, ix.n_out, gx, nullptr, dim, ws, ws_bytes, stream);
+                         ? run_pass<T, ADD, MSG_MUL, true, false>(GIN, ix, ix.csc, unit, g, r, ix.n_out, gx, nullptr, dim, ws, ws_bytes, stream)
+                         : run_pass<T, ADD, MSG_COPY, true, false>(GIN, ix, ix.csc, unit, g, r, ix.n_out, gx, nullptr, dim, ws, ws_bytes, stream);
             if (status) return status;
         }
         if (gr) {
             status = mul_op == ULTRA_RSPMM_MUL_MUL
-                         ? run_pass<T, ADD, MSG_MUL, false, false>(GREL, ix.rel, ix.nnz, unit, g, x, (long long)ix.n_out + ix.n_in, gr, nullptr, dim, ws, ws_bytes, stream)
-                         : run_pass<T, ADD, MSG_COPY, true, false>(GREL, ix.rel, ix.nnz, unit, g, x, ix.n_out, gr, nullptr, dim, ws, ws_bytes, stream);
+                         ? run_pass<T, ADD, MSG_MUL, false, false>(GREL, ix, ix.rel, unit, g, x, (long long)ix.n_out + ix.n_in, gr, nullptr, dim, ws, ws_bytes, stream)
+                         : run_pass<T, ADD, MSG_COPY, true, false>(GREL, ix, ix.rel, unit, g, x, ix.n_out, gr, nullptr, dim, ws, ws_bytes, stream);
         }
         return status;
     }
@@ -954,7 +1008,8 @@ extern "C" int ultra_rspmm_workspace_bytes(const ultra_rspmm_index_t *index, int
     if (forward_bytes) *forward_bytes = pass_bytes(index->csr, dim, elem, true);
     if (backward_bytes) {
         const size_t a = pass_bytes(index->csc, dim, elem, false), b = pass_bytes(index->rel, dim, elem, false);
-        *backward_bytes = a > b ? a : b;
+        const size_t c = dtype == ULTRA_RSPMM_F32 && blocked_bytes(*index, dim) <= (16ull << 30) ? blocked_bytes(*index, dim) : 0;
+        *backward_bytes = a > b ? (a > c ? a : c) : (b > c ? b : c);
     }
     return ULTRA_RSPMM_OK;
 }
@@ -1067,8 +1122,8 @@ extern "C" int ultra_rspmm_forward_blocked(const ultra_rspmm_index_t *index, con
     float *o = (float *)dev_output;
     constexpr int ADD = ULTRA_RSPMM_SUM_ADD;
     status = mul_op == ULTRA_RSPMM_MUL_MUL
-                 ? run_pass<float, ADD, MSG_MUL, true, false>(FWD, index->csr, index->nnz, unit, x, r, index->n_in, o, nullptr, dim, workspace, workspace_bytes, s, b, layout)
-                 : run_pass<float, ADD, MSG_ADD, true, false>(FWD, index->csr, index->nnz, unit, x, r, index->n_in, o, nullptr, dim, workspace, workspace_bytes, s, b, layout);
+                 ? run_pass<float, ADD, MSG_MUL, true, false>(FWD, *index, index->csr, unit, x, r, index->n_in, o, nullptr, dim, workspace, workspace_bytes, s, b, layout)
+                 : run_pass<float, ADD, MSG_ADD, true, false>(FWD, *index, index->csr, unit, x, r, index->n_in, o, nullptr, dim, workspace, workspace_bytes, s, b, layout);
     if (status) return status;
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;

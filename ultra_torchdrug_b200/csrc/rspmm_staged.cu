@@ -17,6 +17,8 @@
 //
 // Serves sum aggregation with mul / add / copy messages (forward on the csr order, grad_input on the csc order) of fp32
 // operands whose ids pack into 32 bits; run_pass (rspmm_kernels.cu) selects it when the slab fits shared memory.
+#include <type_traits>
+
 #include "rspmm_common.cuh"
 
 namespace ultra {
@@ -26,6 +28,13 @@ namespace {
 constexpr int kStagedWarps = 32;
 constexpr int kStagedThreads = kStagedWarps * 32;
 constexpr int kEdgesPerHalf = 4;   // edges in flight per half-warp
+
+__device__ __forceinline__ int id_first(const int2 &e) { return e.x; }
+__device__ __forceinline__ int id_second(const int2 &e) { return e.y; }
+__device__ __forceinline__ int id_first(const unsigned &) { return 0; }
+__device__ __forceinline__ int id_second(const unsigned &) { return 0; }
+__device__ __forceinline__ unsigned id_bits_of(const unsigned &e) { return e; }
+__device__ __forceinline__ unsigned id_bits_of(const int2 &) { return 0; }
 
 __device__ __forceinline__ long long staged_blocked_col(long long col, int block, int shift, long long stride) {
     const unsigned c = (unsigned)col;
@@ -195,12 +204,238 @@ __global__ void __launch_bounds__(kStagedThreads, 1) rows_in_smem_kernel(const S
     }
 }
 
-template <int MSG> int launch_typed(const StagedArgs &args, size_t smem, int blocks, cudaStream_t stream) {
-    static bool configured = false;   // per instantiation; the attribute is per device function and idempotent
-    if (!configured) {
-        ULTRA_CUDA_OK(cudaFuncSetAttribute(rows_in_smem_kernel<MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedMaxSmem));
-        configured = true;
+// ---- pair kernel -----------------------------------------------------------------------------------------------------
+// One warp per segment (rows are handed out longest first); per pair one LDS.128 of the other node's row and, for each
+// relation bit of the mask, 4 predicated FMAs with that relation's row, which stays in registers for the whole slab.
+template <int MSG>
+__device__ __forceinline__ void pair_accumulate(unsigned word, unsigned low, int id_bits, const float4 *s_rows, int l16,
+                                                const float4 (&rel)[4], float (&acc)[4]) {
+    const float4 x = s_rows[(word & low) * (kStagedSlab / 4) + l16];
+    const unsigned mask = word >> id_bits;
+    const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (mask & (1u << k)) {
+            const float rv[4] = {rel[k].x, rel[k].y, rel[k].z, rel[k].w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[v] += message<float, MSG>(rv[v], xv[v]);
+        }
     }
+}
+
+template <int MSG>
+__global__ void __launch_bounds__(kStagedThreads, 1) pairs_in_smem_kernel(const PairArgs a) {
+    extern __shared__ __align__(16) float4 s_rows[];
+    __shared__ __align__(16) unsigned s_pair[kStagedWarps][32];
+    __shared__ int s_item;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, l16 = lane & 15;
+    const unsigned low = (1u << a.id_bits) - 1u;
+    const int items_per_slab = (a.n_seg + kStagedWarps - 1) / kStagedWarps;
+    const int n_item = items_per_slab * a.n_slab;
+    int resident = -1;
+    float4 rel[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rel[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (;;) {
+        if (threadIdx.x == 0) s_item = (int)atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_item) break;
+        const int slab = item / items_per_slab;
+        const long long col = (long long)slab * kStagedSlab + l16 * 4;
+        const bool active = col < a.dim;
+        if (slab != resident) {
+            for (int i = threadIdx.x; i < a.n_rows * (kStagedSlab / 4); i += kStagedThreads) {
+                const int row = i >> 4;
+                const long long c = (long long)slab * kStagedSlab + (i & 15) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < a.dim) {
+                    const long long at = a.block ? staged_blocked_col(c, a.block, a.block_shift, a.a_stride) : c;
+                    v = __ldg(reinterpret_cast<const float4 *>(a.A + (long long)row * a.a_row + at));
+                }
+                s_rows[i] = v;
+            }
+            if (MSG != MSG_COPY) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    rel[k] = (k < a.n_rel && active) ? __ldg(reinterpret_cast<const float4 *>(a.B + (long long)k * a.dim + col))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            resident = slab;
+            __syncthreads();
+        }
+        const int position = (item - slab * items_per_slab) * kStagedWarps + warp;
+        if (position < a.n_seg) {
+            const int seg = __ldg(a.rows + position);
+            const int begin = __ldg(a.ptr + seg), end = __ldg(a.ptr + seg + 1);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            unsigned ahead = begin + lane < end ? __ldg(a.pair + begin + lane) : 0u;
+            for (int base = begin; base < end; base += 32) {
+                const int n = min(32, end - base);
+                __syncwarp();
+                s_pair[warp][lane] = ahead;
+                __syncwarp();
+                if (base + 32 + lane < end) ahead = __ldg(a.pair + base + 32 + lane);
+                int u = 0;
+                for (; u + 2 * kEdgesPerHalf <= n; u += 2 * kEdgesPerHalf) {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(&s_pair[warp][u + half * kEdgesPerHalf]);
+                    const unsigned words[4] = {w.x, w.y, w.z, w.w};
+                    float4 x[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) x[k] = s_rows[(words[k] & low) * (kStagedSlab / 4) + l16];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned mask = words[k] >> a.id_bits;
+                        const float xv[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (mask & (1u << q)) {
+                                const float rv[4] = {rel[q].x, rel[q].y, rel[q].z, rel[q].w};
+#pragma unroll
+                                for (int v = 0; v < 4; ++v) acc[v] += message<float, MSG>(rv[v], xv[v]);
+                            }
+                        }
+                    }
+                }
+                for (; u < n; u += 2) {
+                    const int mine = u + half;
+                    if (mine < n) pair_accumulate<MSG>(s_pair[warp][mine], low, a.id_bits, s_rows, l16, rel, acc);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[v] += __shfl_xor_sync(kFullMask, acc[v], 16);
+            if (half == 0 && active) {
+                Vec<float, 4> r;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) r.v[v] = acc[v];
+                if (a.addend) {
+                    Vec<float, 4> b;
+                    gather_load(a.addend + (long long)seg * a.dim + col, b);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) r.v[v] += b.v[v];
+                }
+                const long long o_col = a.block ? staged_blocked_col(col, a.block, a.block_shift, a.o_stride) + a.o_offset : col;
+                stream_store(a.out + (long long)seg * a.o_row + o_col, r);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- destination-blocked grad_relation ------------------------------------------------------------------------------------
+// item = (slab, destination block b): the CTA stages grad_output rows [b * block_rows, (b + 1) * block_rows) of the slab,
+// then warp w reduces the (relation k, block b) runs for k = w, w + 32, ...:  acc += g[dst] (x) x[src]  with g from shared
+// memory and x gathered (half-warp per edge, LDG.128).  Every (k, b) run writes one partial row (zeros when empty); the
+// combine pass folds the n_block partial rows of a relation in block order - deterministic, no atomics on data.
+template <int MSG, bool PACKED>
+__global__ void __launch_bounds__(kStagedThreads, 1) dst_blocked_kernel(const BlockedRelArgs a) {
+    using Ids = typename std::conditional<PACKED, unsigned, int2>::type;
+    extern __shared__ __align__(16) float4 s_rows[];
+    __shared__ __align__(16) Ids s_edge[kStagedWarps][32];
+    __shared__ __align__(16) float s_w[kStagedWarps][32];
+    __shared__ int s_item;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, l16 = lane & 15;
+    const int shift = a.pack_shift;
+    const unsigned low = PACKED ? ((1u << shift) - 1u) : 0u;
+    const unsigned row_bytes = (unsigned)(a.dim * sizeof(float));
+    const int n_item = a.n_block * a.n_slab;
+    const Ids *ids = reinterpret_cast<const Ids *>(PACKED ? (const void *)a.packed : (const void *)a.edge);
+    for (;;) {
+        if (threadIdx.x == 0) s_item = (int)atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_item) break;
+        const int slab = item / a.n_block, b = item - slab * a.n_block;
+        const int first_row = b * a.block_rows;
+        const int rows = min(a.block_rows, a.n_out - first_row);
+        for (int i = threadIdx.x; i < rows * (kStagedSlab / 4); i += kStagedThreads) {
+            const long long c = (long long)slab * kStagedSlab + (i & 15) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < a.dim) v = __ldg(reinterpret_cast<const float4 *>(a.G + (long long)(first_row + (i >> 4)) * a.dim + c));
+            s_rows[i] = v;
+        }
+        __syncthreads();
+        const long long col = (long long)slab * kStagedSlab + l16 * 4;
+        const bool active = col < a.dim;
+        const char *X = reinterpret_cast<const char *>(a.X + (active ? col : 0));
+        for (int k = warp; k < a.n_rel; k += kStagedWarps) {
+            const int begin = __ldg(a.block_ptr + (long long)k * (a.n_block + 1) + b);
+            const int end = __ldg(a.block_ptr + (long long)k * (a.n_block + 1) + b + 1);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            auto one = [&](const Ids &e, float w) {
+                const int dst = PACKED ? (int)(id_bits_of(e) & low) : id_first(e);
+                const int src = PACKED ? (int)(id_bits_of(e) >> shift) : id_second(e);
+                const float4 g = s_rows[(dst - first_row) * (kStagedSlab / 4) + l16];
+                float4 x = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (MSG == MSG_MUL) {
+                    Vec<float, 4> v;
+                    gather_load(reinterpret_cast<const float *>(X + (unsigned long long)(unsigned)src * row_bytes), v);
+                    x = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+                }
+                const float gv[4] = {g.x, g.y, g.z, g.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[v] += MSG == MSG_MUL ? w * (gv[v] * xv[v]) : w * gv[v];
+            };
+            Ids ahead = Ids();
+            float ahead_w = 1.f;
+            if (begin + lane < end) {
+                ahead = __ldg(ids + begin + lane);
+                if (a.w) ahead_w = __ldg(a.w + begin + lane);
+            }
+            for (int base = begin; base < end; base += 32) {
+                const int n = min(32, end - base);
+                __syncwarp();
+                s_edge[warp][lane] = ahead;
+                s_w[warp][lane] = ahead_w;
+                __syncwarp();
+                if (base + 32 + lane < end) {
+                    ahead = __ldg(ids + base + 32 + lane);
+                    if (a.w) ahead_w = __ldg(a.w + base + 32 + lane);
+                }
+                int u = 0;
+                for (; u + 2 * kEdgesPerHalf <= n; u += 2 * kEdgesPerHalf) {
+                    const int mine = u + half * kEdgesPerHalf;
+                    Ids e[4];
+                    float w[4];
+                    float4 g[4];
+                    Vec<float, 4> x[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        e[q] = s_edge[warp][mine + q];
+                        w[q] = s_w[warp][mine + q];
+                        const int dst = PACKED ? (int)(id_bits_of(e[q]) & low) : id_first(e[q]);
+                        const int src = PACKED ? (int)(id_bits_of(e[q]) >> shift) : id_second(e[q]);
+                        if (MSG == MSG_MUL) gather_load(reinterpret_cast<const float *>(X + (unsigned long long)(unsigned)src * row_bytes), x[q]);
+                        g[q] = s_rows[(dst - first_row) * (kStagedSlab / 4) + l16];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float gv[4] = {g[q].x, g[q].y, g[q].z, g[q].w};
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) acc[v] += MSG == MSG_MUL ? w[q] * (gv[v] * x[q].v[v]) : w[q] * gv[v];
+                    }
+                }
+                for (; u < n; u += 2) {
+                    const int mine = u + half;
+                    if (mine < n) one(s_edge[warp][mine], s_w[warp][mine]);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[v] += __shfl_xor_sync(kFullMask, acc[v], 16);
+            if (half == 0 && active) {
+                float *p = a.partial + ((long long)k * a.n_block + b) * a.dim + col;
+                *reinterpret_cast<float4 *>(p) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int MSG> int launch_typed(const StagedArgs &args, size_t smem, int blocks, cudaStream_t stream) {
+    // every launch: the attribute belongs to the current device's copy of the function (one process may drive several)
+    ULTRA_CUDA_OK(cudaFuncSetAttribute(rows_in_smem_kernel<MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedMaxSmem));
     rows_in_smem_kernel<MSG><<<blocks, kStagedThreads, smem, stream>>>(args);
     note_launch();
     return ULTRA_RSPMM_OK;
@@ -229,6 +464,59 @@ int launch_rows_in_smem(StagedArgs args, int msg, cudaStream_t stream) {
         case MSG_ADD: return launch_typed<MSG_ADD>(args, smem, blocks, stream);
         default: return launch_typed<MSG_COPY>(args, smem, blocks, stream);
     }
+}
+
+static int sm_count(int *sms) {
+    int device = 0;
+    ULTRA_CUDA_OK(cudaGetDevice(&device));
+    ULTRA_CUDA_OK(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, device));
+    return ULTRA_RSPMM_OK;
+}
+
+int launch_pairs_in_smem(PairArgs args, int msg, cudaStream_t stream) {
+    if (args.n_seg == 0 || args.dim == 0) return ULTRA_RSPMM_OK;
+    const size_t smem = (size_t)args.n_rows * kStagedSlab * sizeof(float);
+    if (smem > kStagedMaxSmem || !args.pair || !args.counter || args.n_rel > 4) return ULTRA_RSPMM_ERR_ARG;
+    args.n_slab = (int)((args.dim + kStagedSlab - 1) / kStagedSlab);
+    int sms = 0;
+    if (int status = sm_count(&sms)) return status;
+    const long long items = (long long)((args.n_seg + kStagedWarps - 1) / kStagedWarps) * args.n_slab;
+    const int blocks = (int)(items < sms ? items : sms);
+    ULTRA_CUDA_OK(cudaMemsetAsync(args.counter, 0, sizeof(unsigned), stream));
+#define ULTRA_PAIRS(M)                                                                                                        \
+    do {                                                                                                                       \
+        ULTRA_CUDA_OK(cudaFuncSetAttribute(pairs_in_smem_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedMaxSmem)); \
+        pairs_in_smem_kernel<M><<<blocks, kStagedThreads, smem, stream>>>(args);                                              \
+    } while (0)
+    if (msg == MSG_MUL) ULTRA_PAIRS(MSG_MUL);
+    else if (msg == MSG_ADD) ULTRA_PAIRS(MSG_ADD);
+    else ULTRA_PAIRS(MSG_COPY);
+#undef ULTRA_PAIRS
+    note_launch();
+    return ULTRA_RSPMM_OK;
+}
+
+int launch_dst_blocked(BlockedRelArgs args, int msg, cudaStream_t stream) {
+    if (args.n_rel == 0 || args.n_block == 0 || args.dim == 0) return ULTRA_RSPMM_OK;
+    const size_t smem = (size_t)args.block_rows * kStagedSlab * sizeof(float);
+    if (smem > kStagedMaxSmem || !args.block_ptr || !args.counter || (msg != MSG_MUL && msg != MSG_COPY)) return ULTRA_RSPMM_ERR_ARG;
+    args.n_slab = (int)((args.dim + kStagedSlab - 1) / kStagedSlab);
+    int sms = 0;
+    if (int status = sm_count(&sms)) return status;
+    const long long items = (long long)args.n_block * args.n_slab;
+    const int blocks = (int)(items < sms ? items : sms);
+    ULTRA_CUDA_OK(cudaMemsetAsync(args.counter, 0, sizeof(unsigned), stream));
+#define ULTRA_BLOCKED(M, P)                                                                                                   \
+    do {                                                                                                                       \
+        ULTRA_CUDA_OK(cudaFuncSetAttribute(dst_blocked_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedMaxSmem)); \
+        dst_blocked_kernel<M, P><<<blocks, kStagedThreads, smem, stream>>>(args);                                             \
+    } while (0)
+    const bool packed = args.packed != nullptr && args.pack_shift > 0;
+    if (msg == MSG_MUL) { if (packed) ULTRA_BLOCKED(MSG_MUL, true); else ULTRA_BLOCKED(MSG_MUL, false); }
+    else { if (packed) ULTRA_BLOCKED(MSG_COPY, true); else ULTRA_BLOCKED(MSG_COPY, false); }
+#undef ULTRA_BLOCKED
+    note_launch();
+    return ULTRA_RSPMM_OK;
 }
 
 }  // namespace ultra

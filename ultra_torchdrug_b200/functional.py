@@ -83,7 +83,16 @@ class GraphIndex(object):
                 _ptr(indices), indices.stride(0) if nnz else 0, _ptr(values), nnz, self.shape[0], self.shape[1],
                 self.shape[2], code, self.buffer.data_ptr(), self.buffer.numel(), scratch.data_ptr(),
                 scratch.numel(), ctypes.byref(self.c), _stream_handle()), "ultra_rspmm_index_build")
-        del scratch
+            del scratch
+            # optional extensions: pair lists (<= 4 relation types, few nodes), destination-block table (huge graphs)
+            extend_bytes = ctypes.c_size_t()
+            _lib.check(lib.ultra_rspmm_index_extend_bytes(ctypes.byref(self.c), ctypes.byref(extend_bytes)),
+                       "ultra_rspmm_index_extend_bytes")
+            self.extension = None
+            if extend_bytes.value:
+                self.extension = torch.empty(extend_bytes.value, dtype=torch.uint8, device=self.device)
+                _lib.check(lib.ultra_rspmm_index_extend(ctypes.byref(self.c), self.extension.data_ptr(), self.extension.numel(),
+                                                        _stream_handle()), "ultra_rspmm_index_extend")
         self.nnz = int(self.c.nnz)
         self._workspace_bytes = {}
 
