@@ -87,3 +87,32 @@ def test_reference_layer_fast_path_equals_its_fallback(reference, aggregate_func
         graph.requires_grad = True
         slow = layer.message_and_aggregate(graph, input)
     np.testing.assert_allclose(fast.numpy(), slow.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_reference_concat_hidden_equals_mirror(reference, monkeypatch):
+    """`concat_hidden=True` (reference model.py:49, 134-136: every layer's state feeds the scoring MLP) - unused by the
+    shipped configs, mirrored all the same."""
+    from oracle.rspmm_oracle import generalized_rspmm_oracle
+    from torchdrug import data
+    from ultra_torchdrug_b200 import nbf, synthetic
+    monkeypatch.setattr(nbf, "generalized_rspmm", generalized_rspmm_oracle)
+    torch.manual_seed(5)
+    num_node, num_relation, hidden, layers = 35, 4, 8, 3
+    triples = synthetic.triples(num_node, num_relation, 140, seed=5)
+    graph = data.Graph(triples, num_node=num_node, num_relation=num_relation)
+    arguments = dict(input_dim=hidden, hidden_dims=[hidden] * layers, num_relation=num_relation, message_func="distmult",
+                     aggregate_func="sum", short_cut=True, layer_norm=True, project=True, mod=True, concat_hidden=True)
+    ref_model = reference["model"].TransferNBFNet(**arguments).eval()
+    model = nbf.TransferNBFNet(**arguments).eval()
+    model.load_state_dict(ref_model.state_dict(), strict=True)
+    assert model.mlp.layers[0].in_features == hidden * layers + hidden
+    batch = triples[:4]
+    pos_h, pos_t, pos_r = batch.t()
+    rel_input = torch.randn(len(batch), 2 * num_relation, hidden)
+    candidates = torch.arange(num_node)
+    r_index = pos_r.unsqueeze(-1).expand(-1, num_node)
+    h_index, t_index = torch.meshgrid(pos_h, candidates, indexing="ij")
+    with torch.no_grad():
+        want = ref_model(graph, [rel_input], h_index, t_index, r_index)
+        got = model(graph, [rel_input], h_index, t_index, r_index)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)

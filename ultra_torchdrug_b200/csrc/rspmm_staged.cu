@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1) dst_blocked_kernel(const Bl
 
 template <int MSG> int launch_typed(const StagedArgs &args, size_t smem, int blocks, cudaStream_t stream) {
     // every launch: the attribute belongs to the current device's copy of the function (one process may drive several)
-    ULTRA_CUDA_OK(cudaFuncSetAttribute(rows_in_smem_kernel<MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedMaxSmem));
+    ULTRA_CUDA_OK(cudaFuncSetAttribute(rows_in_smem_kernel<MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rows_in_smem_kernel<MSG><<<blocks, kStagedThreads, smem, stream>>>(args);
     note_launch();
     return ULTRA_RSPMM_OK;
@@ -485,7 +485,7 @@ int launch_pairs_in_smem(PairArgs args, int msg, cudaStream_t stream) {
     ULTRA_CUDA_OK(cudaMemsetAsync(args.counter, 0, sizeof(unsigned), stream));
 #define ULTRA_PAIRS(M)                                                                                                        \
     do {                                                                                                                       \
-        ULTRA_CUDA_OK(cudaFuncSetAttribute(pairs_in_smem_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedMaxSmem)); \
+        ULTRA_CUDA_OK(cudaFuncSetAttribute(pairs_in_smem_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         pairs_in_smem_kernel<M><<<blocks, kStagedThreads, smem, stream>>>(args);                                              \
     } while (0)
     if (msg == MSG_MUL) ULTRA_PAIRS(MSG_MUL);
@@ -498,8 +498,8 @@ int launch_pairs_in_smem(PairArgs args, int msg, cudaStream_t stream) {
 
 int launch_dst_blocked(BlockedRelArgs args, int msg, cudaStream_t stream) {
     if (args.n_rel == 0 || args.n_block == 0 || args.dim == 0) return ULTRA_RSPMM_OK;
-    const size_t smem = (size_t)args.block_rows * kStagedSlab * sizeof(float);
-    if (smem > kStagedMaxSmem || !args.block_ptr || !args.counter || (msg != MSG_MUL && msg != MSG_COPY)) return ULTRA_RSPMM_ERR_ARG;
+    const size_t smem = (size_t)args.block_rows * kStagedSlab * sizeof(float);   // + 12.3 KB static (unpacked ids): <= 227 KB
+    if (smem > kStagedMaxSmem - 8192 || !args.block_ptr || !args.counter || (msg != MSG_MUL && msg != MSG_COPY)) return ULTRA_RSPMM_ERR_ARG;
     args.n_slab = (int)((args.dim + kStagedSlab - 1) / kStagedSlab);
     int sms = 0;
     if (int status = sm_count(&sms)) return status;
@@ -508,7 +508,7 @@ int launch_dst_blocked(BlockedRelArgs args, int msg, cudaStream_t stream) {
     ULTRA_CUDA_OK(cudaMemsetAsync(args.counter, 0, sizeof(unsigned), stream));
 #define ULTRA_BLOCKED(M, P)                                                                                                   \
     do {                                                                                                                       \
-        ULTRA_CUDA_OK(cudaFuncSetAttribute(dst_blocked_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedMaxSmem)); \
+        ULTRA_CUDA_OK(cudaFuncSetAttribute(dst_blocked_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         dst_blocked_kernel<M, P><<<blocks, kStagedThreads, smem, stream>>>(args);                                             \
     } while (0)
     const bool packed = args.packed != nullptr && args.pack_shift > 0;

@@ -272,13 +272,11 @@ class TransferNBFNet(nn.Module):
         double_relation = 1 if num_relation is None else 2 * self.num_relation
         self.short_cut = short_cut
         self.concat_hidden = concat_hidden
-        if concat_hidden:
-            raise NotImplementedError("concat_hidden is not used by the shipped configs")
         layer_type = GeneralizedRelationalConvNBFMod if mod else GeneralizedRelationalConvNBF
         self.layers = nn.ModuleList(
             layer_type(self.dims[i], self.dims[i + 1], double_relation, self.dims[0], message_func, aggregate_func,
                        layer_norm, activation, project) for i in range(len(self.dims) - 1))
-        feature_dim = hidden_dims[-1] + input_dim
+        feature_dim = hidden_dims[-1] * (len(hidden_dims) if concat_hidden else 1) + input_dim   # reference model.py:49
         self.query = None
         self.mlp = MLP(feature_dim, [feature_dim] * (num_mlp_layer - 1) + [1])
         self.dist_embed = nn.Embedding(10, input_dim)   # unused by forward; kept for state-dict parity
@@ -325,7 +323,7 @@ class TransferNBFNet(nn.Module):
         query = self.query[r_index] if self.query.dim() == 2 else self.query[batch, r_index]
         with graph.graph():
             graph.query = query
-        if _buffered_layers_supported(self.layers, query):
+        if not self.concat_hidden and _buffered_layers_supported(self.layers, query):
             # (N, B, 2d): hidden | free; the one-hot boundary (model.py:106-109) is applied in its sparse form
             feature = _run_layers_buffered(self.layers, graph, None, self.short_cut, one_hot=(h_index, query))
             if self._split_head_supported(feature):
@@ -335,6 +333,13 @@ class TransferNBFNet(nn.Module):
         boundary = _one_hot_boundary(graph.num_node, h_index, query)
         with graph.node():
             graph.boundary = boundary
+        if self.concat_hidden:                              # every layer's state feeds the scoring MLP (model.py:134-136)
+            hiddens, hidden = [], boundary
+            for layer in self.layers:
+                skip = hidden if self.short_cut and layer.output_dim == hidden.shape[-1] else None
+                hidden = layer(graph, hidden, residual=skip, one_hot=(h_index, query))
+                hiddens.append(hidden)
+            return torch.cat(hiddens + [query.expand(graph.num_node, -1, -1)], dim=-1)
         hidden = _run_layers(self.layers, graph, boundary, self.short_cut, one_hot=(h_index, query))
         return torch.cat([hidden, query.expand(graph.num_node, -1, -1)], dim=-1)
 
