@@ -25,7 +25,7 @@ namespace ultra {
 
 namespace {
 
-constexpr int kDefaultLinearKernel = 1;                // 1 = mma.sync (this file), 2 = tcgen05 (layer_linear_tc.cu)
+constexpr int kDefaultLinearKernel = 2;                // 1 = mma.sync (this file), 2 = tcgen05 + TMA (layer_linear_tc.cu)
 constexpr int kWarpRows = 16;                          // rows per warp tile (one m16 MMA row block)
 constexpr int kLinearWarps = 16;
 constexpr int kLinearThreads = 32 * kLinearWarps;

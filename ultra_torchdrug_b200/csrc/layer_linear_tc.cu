@@ -1,20 +1,27 @@
-// tcgen05 / TMEM version of the fused `combine` (see layer_linear.cu for what is computed and for the 3xTF32 arithmetic):
+// tcgen05 / TMEM / TMA version of the fused `combine` (see layer_linear.cu for what is computed and for the 3xTF32 arithmetic):
 //     out[r, 0:N] = relu(layer_norm(A[r, 0:2N] @ W^T + b) * gamma + beta) + A[r, 0:N]
-// The mma.sync version is bound by the legacy HMMA pipe (0.18 ms per C2 layer at best, 0.27 ms measured); here the MMAs run
-// on the 5th-generation tensor cores (tcgen05.mma.kind::tf32, one issuing thread, accumulators in tensor memory), which
-// need ~0.04 ms for the same work, so the kernel is bound by what it must move: 0.71 GB per C2 layer.
+// The mma.sync version is bound by the legacy HMMA pipe (0.18 ms per C2 layer at best, 0.27 ms measured).  Here the MMAs
+// run on the 5th-generation tensor cores (tcgen05.mma.kind::tf32, one issuing thread, accumulators in tensor memory:
+// ~0.04 ms for the same work) and the 64 KB row tiles reach shared memory by TMA, so the load/store unit only sees the
+// hi / lo split and the epilogue - the kernel is bound by what it must move (0.71 GB per C2 layer).
 //
-// Persistent CTAs, one per SM, warp-specialised (13 warps):
-//   warps 0-7   producers: read 128-row tiles of A from global memory (each warp instruction = 8 rows x 64 B), split every
-//               value into hi = tf32(x) and lo = tf32(x - hi), and store both in shared memory in the canonical K-major
-//               no-swizzle UMMA layout (8-row x 16-byte core matrices), a ring of 3 slots of 32 K-columns each;
-//   warp  8     one elected thread issues, per slot, 4 k-steps x 3 MMAs (lo_a hi_b, hi_a lo_b, hi_a hi_b; M = 128, N, K = 8)
+// Persistent CTAs, one per SM, warp-specialised (10 warps):
+//   warp  0     TMA producer (one thread): per 128-row tile and 32-column K slot one cp.async.bulk.tensor.2d (box
+//               32 floats x 128 rows = 16 KB, SWIZZLE_128B: the canonical K-major UMMA layout) into a ring of 3 slots;
+//   warps 2-5   split: each 16-byte chunk of a landed slot is read once and rewritten in place as hi = tf32(x), its
+//               remainder lo = tf32(x - hi) goes to the slot's second half at the same (swizzled) position;
+//   warp  1     one elected thread issues, per slot, 4 k-steps x 3 MMAs (lo_a hi_b, hi_a lo_b, hi_a hi_b; M = 128, N, K = 8)
 //               into one of two accumulator stages in TMEM and commits them to the slot's `empty` barrier;
-//   warps 9-12  epilogue: tcgen05.ld of their 32 TMEM lanes (one thread = one row, all N columns), LayerNorm statistics in
+//   warps 6-9   epilogue: tcgen05.ld of their 32 TMEM lanes (one thread = one row, all N columns), LayerNorm statistics in
 //               the thread, centred rows through warp-private shared memory, then coalesced: affine, ReLU, short-cut
 //               (fp32 row re-read from global memory: an L2 hit), 16-byte streaming stores.
-// Hand-offs are mbarriers: full[slot] (one arrival per producer warp), empty[slot] (tcgen05.commit), tmem_full[stage]
-// (tcgen05.commit), tmem_empty[stage] (one arrival per epilogue warp).  W is split into hi / lo once per CTA.
+// Hand-offs are mbarriers: landed[slot] (TMA complete_tx), full[slot] (one arrival per split warp), empty[slot]
+// (tcgen05.commit), tmem_full[stage] (tcgen05.commit), tmem_empty[stage] (one arrival per epilogue warp).  W is split into
+// hi / lo once per CTA (no-swizzle K-major layout; the two operands' layouts are independent).
+#include <cuda.h>
+
+#include <mutex>
+
 #include "rspmm_common.cuh"
 
 namespace ultra {
@@ -25,20 +32,22 @@ namespace tc {
 constexpr int kRows = 128;                             // UMMA M
 constexpr int kSlotK = 32;                             // K columns per ring slot = 4 k-steps of 8
 constexpr int kSlots = 3;
-constexpr int kProducerWarps = 8;
-constexpr int kMmaWarp = kProducerWarps;
+constexpr int kTmaWarp = 0;
+constexpr int kMmaWarp = 1;
+constexpr int kSplitWarp0 = 2;
+constexpr int kSplitWarps = 4;
+constexpr int kEpilogueWarp0 = kSplitWarp0 + kSplitWarps;
 constexpr int kEpilogueWarps = 4;
-constexpr int kThreads = 32 * (kProducerWarps + 1 + kEpilogueWarps);
-constexpr int kSlotHalfBytes = kRows * kSlotK * 4;     // hi (or lo) part of a slot: 16 KB
-constexpr int kCoreBytesA = kRows * 16;                // K-direction core-matrix stride of an A slot (LBO)
-constexpr int kBarriers = 2 * kSlots + 4;
+constexpr int kThreads = 32 * (kEpilogueWarp0 + kEpilogueWarps);
+constexpr int kSlotHalfBytes = kRows * kSlotK * 4;     // hi (or lo) part of a slot: 16 KB = one TMA box
+constexpr int kBarriers = 3 * kSlots + 4;
 
 template <int N> struct Shape {
     static constexpr int K = 2 * N;
     static constexpr int kSlotsPerTile = K / kSlotK;
     static constexpr int kWeightHalfBytes = N * K * 4;
     static constexpr int kCoreBytesW = N * 16;          // LBO of the W operand
-    static constexpr int kRingOffset = 2 * kWeightHalfBytes;
+    static constexpr int kRingOffset = (2 * kWeightHalfBytes + 1023) / 1024 * 1024;   // SWIZZLE_128B slots: 1024-byte aligned
     static constexpr int kStageStride = N + 4;          // floats per staged output row (bank-conflict-free both ways)
     static constexpr int kStagingOffset = kRingOffset + kSlots * 2 * kSlotHalfBytes;
     static constexpr int kBarrierOffset = kStagingOffset + kEpilogueWarps * 32 * kStageStride * 4;
@@ -77,6 +86,18 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr, unsi
     return (unsigned long long)((smem_addr >> 4) & 0x3fff) | ((unsigned long long)((lbo_bytes >> 4) & 0x3fff) << 16) |
            ((unsigned long long)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
 }
+// K-major SWIZZLE_128B operand (rows of 128 bytes, 16-byte chunks XOR-ed with row % 8 - what TMA writes): SBO = 1024 bytes
+// between 8-row groups, LBO unused, layout type 2 in bits 61-63; a k-step of 8 tf32 advances the start address by 32 bytes
+__device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned smem_addr) {
+    return (unsigned long long)((smem_addr >> 4) & 0x3fff) | ((unsigned long long)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned smem_dst, const CUtensorMap *map, int c0, int c1, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long a, unsigned long long b, unsigned instr,
                                           unsigned accumulate) {
     asm volatile(
@@ -101,27 +122,30 @@ __device__ __forceinline__ void tmem_load16(unsigned taddr, float (&v)[16]) {
 
 template <int N>
 __global__ void __launch_bounds__(tc::kThreads, 1)
-linear_norm_relu_residual_tc_kernel(const float *__restrict__ A, long long lda, const float *__restrict__ W,
+linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, const float *__restrict__ A, long long lda,
+                                    const float *__restrict__ W,
                                     const float *__restrict__ linear_bias, const float *__restrict__ gamma,
                                     const float *__restrict__ beta, float *__restrict__ out, long long ldo, long long rows,
                                     float eps, int relu, int shortcut) {
     using S = tc::Shape<N>;
     constexpr int K = S::K, kSlotsPerTile = S::kSlotsPerTile;
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
     const unsigned bar_base = smem_base + S::kBarrierOffset;
     auto full_bar = [&](int slot) { return bar_base + 8u * slot; };
     auto empty_bar = [&](int slot) { return bar_base + 8u * (tc::kSlots + slot); };
-    auto tmem_full_bar = [&](int stage) { return bar_base + 8u * (2 * tc::kSlots + stage); };
-    auto tmem_empty_bar = [&](int stage) { return bar_base + 8u * (2 * tc::kSlots + 2 + stage); };
+    auto landed_bar = [&](int slot) { return bar_base + 8u * (2 * tc::kSlots + slot); };
+    auto tmem_full_bar = [&](int stage) { return bar_base + 8u * (3 * tc::kSlots + stage); };
+    auto tmem_empty_bar = [&](int stage) { return bar_base + 8u * (3 * tc::kSlots + 2 + stage); };
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + S::kBarrierOffset + tc::kBarriers * 8);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- one-time setup: barriers, tensor memory, W split into hi / lo in UMMA layout ----------------------------------
     if (tid == 0) {
         for (int s = 0; s < tc::kSlots; ++s) {
-            mbar_init(full_bar(s), tc::kProducerWarps);
+            mbar_init(full_bar(s), tc::kSplitWarps);
             mbar_init(empty_bar(s), 1);
+            mbar_init(landed_bar(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tmem_full_bar(s), 1);
@@ -153,59 +177,48 @@ linear_norm_relu_residual_tc_kernel(const float *__restrict__ A, long long lda, 
     const long long first = blockIdx.x;
     const long long my_tiles = first < n_tiles ? (n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
 
-    if (warp < tc::kProducerWarps) {
-        // ===== producers ================================================================================================
-        // A warp instruction covers 8 rows x 4 chunks of 16 B; thread (warp, i) handles row group (4 warp + i) / 2 and the
-        // K-half (4 warp + i) % 2 of the slot: global reads of 64 B per row, shared-memory stores of 128 contiguous bytes
-        // per quarter warp (conflict-free).
-        const long long total = my_tiles * kSlotsPerTile;
-        const int r_in_group = lane & 7, chunk_in_half = lane >> 3;
-        auto issue = [&](long long it, float4 (&regs)[4]) {
-            const long long tile = first + (it / kSlotsPerTile) * gridDim.x;
-            const int k0 = (int)(it % kSlotsPerTile) * tc::kSlotK;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int idx = 4 * warp + i;
-                const long long row = tile * tc::kRows + (idx >> 1) * 8 + r_in_group;
-                const int kc = (idx & 1) * 4 + chunk_in_half;
-                regs[i] = row < rows ? __ldcs(reinterpret_cast<const float4 *>(A + row * lda + k0 + 4 * kc))
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == tc::kTmaWarp) {
+        // ===== TMA producer (one thread) ================================================================================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&a_map) : "memory");
+            const long long total = my_tiles * kSlotsPerTile;
+            for (long long it = 0; it < total; ++it) {
+                const int slot = (int)(it % tc::kSlots);
+                const unsigned phase = (unsigned)((it / tc::kSlots) & 1);
+                const long long tile = first + (it / kSlotsPerTile) * gridDim.x;
+                const int k0 = (int)(it % kSlotsPerTile) * tc::kSlotK;
+                mbar_wait(empty_bar(slot), phase ^ 1u);                  // the MMAs that read this slot have completed
+                mbar_expect_tx(landed_bar(slot), tc::kSlotHalfBytes);
+                tma_load_2d(smem_base + S::kRingOffset + slot * 2 * tc::kSlotHalfBytes, &a_map, k0, (int)(tile * tc::kRows),
+                            landed_bar(slot));                           // rows past the end are filled with zeros
             }
-        };
-        auto consume = [&](long long it, const float4 (&regs)[4]) {
+        }
+    } else if (warp >= tc::kSplitWarp0 && warp < tc::kEpilogueWarp0) {
+        // ===== split: hi in place, lo beside it (elementwise, so the swizzled positions carry over) ========================
+        const int t = tid - 32 * tc::kSplitWarp0;                        // 0 .. 127
+        const long long total = my_tiles * kSlotsPerTile;
+        for (long long it = 0; it < total; ++it) {
             const int slot = (int)(it % tc::kSlots);
             const unsigned phase = (unsigned)((it / tc::kSlots) & 1);
-            mbar_wait(empty_bar(slot), phase ^ 1u);
-            unsigned char *slot_hi = smem + S::kRingOffset + slot * 2 * tc::kSlotHalfBytes;
+            mbar_wait(landed_bar(slot), phase);
+            unsigned char *hi_at = smem + S::kRingOffset + slot * 2 * tc::kSlotHalfBytes;
+            constexpr int kChunksPerThread = tc::kSlotHalfBytes / 16 / (32 * tc::kSplitWarps);
+            float4 x[kChunksPerThread];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int idx = 4 * warp + i;
-                const int row = (idx >> 1) * 8 + r_in_group, kc = (idx & 1) * 4 + chunk_in_half;
-                const float4 x = regs[i];
-                const float4 hi = make_float4(tc_tf32(x.x), tc_tf32(x.y), tc_tf32(x.z), tc_tf32(x.w));
-                const float4 lo = make_float4(tc_tf32(x.x - hi.x), tc_tf32(x.y - hi.y), tc_tf32(x.z - hi.z), tc_tf32(x.w - hi.w));
-                unsigned char *at = slot_hi + kc * tc::kCoreBytesA + row * 16;
+            for (int q = 0; q < kChunksPerThread; ++q)
+                x[q] = *reinterpret_cast<const float4 *>(hi_at + 16 * (t + q * 32 * tc::kSplitWarps));
+#pragma unroll
+            for (int q = 0; q < kChunksPerThread; ++q) {
+                const float4 hi = make_float4(tc_tf32(x[q].x), tc_tf32(x[q].y), tc_tf32(x[q].z), tc_tf32(x[q].w));
+                const float4 lo = make_float4(tc_tf32(x[q].x - hi.x), tc_tf32(x[q].y - hi.y), tc_tf32(x[q].z - hi.z),
+                                              tc_tf32(x[q].w - hi.w));
+                unsigned char *at = hi_at + 16 * (t + q * 32 * tc::kSplitWarps);
                 *reinterpret_cast<float4 *>(at) = hi;
                 *reinterpret_cast<float4 *>(at + tc::kSlotHalfBytes) = lo;
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor cores
             __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(slot));                  // one arrival per warp: 8 per slot, not 256
-        };
-        float4 r0[4], r1[4], r2[4];                     // three slots of loads in flight per thread
-        if (total > 0) issue(0, r0);
-        if (total > 1) issue(1, r1);
-        for (long long it = 0; it < total; it += 3) {
-            if (it + 2 < total) issue(it + 2, r2);
-            consume(it, r0);
-            if (it + 1 < total) {
-                if (it + 3 < total) issue(it + 3, r0);
-                consume(it + 1, r1);
-            }
-            if (it + 2 < total) {
-                if (it + 4 < total) issue(it + 4, r1);
-                consume(it + 2, r2);
-            }
+            if (lane == 0) mbar_arrive(full_bar(slot));
         }
     } else if (warp == tc::kMmaWarp) {
         // ===== MMA issuer (one thread) ==================================================================================
@@ -228,8 +241,8 @@ linear_norm_relu_residual_tc_kernel(const float *__restrict__ A, long long lda, 
 #pragma unroll
                     for (int ks = 0; ks < tc::kSlotK / 8; ++ks) {
                         const int kg = q * (tc::kSlotK / 8) + ks;        // k-step within the tile: two core matrices each
-                        const unsigned long long da_hi = umma_desc(a_hi + ks * 2 * tc::kCoreBytesA, tc::kCoreBytesA, 128);
-                        const unsigned long long da_lo = umma_desc(a_lo + ks * 2 * tc::kCoreBytesA, tc::kCoreBytesA, 128);
+                        const unsigned long long da_hi = umma_desc_sw128(a_hi + ks * 32);
+                        const unsigned long long da_lo = umma_desc_sw128(a_lo + ks * 32);
                         const unsigned long long db_hi = umma_desc(w_hi + kg * 2 * S::kCoreBytesW, S::kCoreBytesW, 128);
                         const unsigned long long db_lo = umma_desc(w_lo + kg * 2 * S::kCoreBytesW, S::kCoreBytesW, 128);
                         umma_tf32(tmem_d, da_lo, db_hi, S::kInstr, kg > 0 ? 1u : 0u);
@@ -241,7 +254,7 @@ linear_norm_relu_residual_tc_kernel(const float *__restrict__ A, long long lda, 
                 umma_commit(tmem_full_bar(stage));                       // accumulator complete
             }
         }
-    } else {
+    } else if (warp >= tc::kEpilogueWarp0) {
         // ===== epilogue =================================================================================================
         // Row phase: one thread = one row (what tcgen05.ld.32x32b hands out): bias, mean, rstd in the thread, centred row
         // into this warp's private staging rows.  Write-back phase: the warp walks its 32 rows kRowsPerPass at a time with
@@ -328,23 +341,50 @@ linear_norm_relu_residual_tc_kernel(const float *__restrict__ A, long long lda, 
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_tiled(EncodeTiled *out) {
+    static EncodeTiled cached = nullptr;
+    static std::mutex guard;
+    std::lock_guard<std::mutex> lock(guard);
+    if (!cached) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult found;
+        ULTRA_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &found));
+        if (found != cudaDriverEntryPointSuccess || !fn) return fail_cuda(cudaErrorNotSupported);
+        cached = (EncodeTiled)fn;
+    }
+    *out = cached;
+    return ULTRA_RSPMM_OK;
+}
+
 template <int N>
 int launch_linear_tc(const float *A, long long lda, const float *W, const float *linear_bias, const float *gamma,
                      const float *beta, float *out, long long ldo, long long rows, float eps, int relu, int shortcut,
                      cudaStream_t stream) {
     using S = tc::Shape<N>;
-    static int sm_count = 0;
     auto kernel = linear_norm_relu_residual_tc_kernel<N>;
-    if (sm_count == 0) {                               // once per process (one process per GPU), outside any graph capture
-        int device = 0, count = 0;
-        ULTRA_CUDA_OK(cudaGetDevice(&device));
-        ULTRA_CUDA_OK(cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device));
-        ULTRA_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmemBytes));
-        sm_count = count;
-    }
+    int device = 0, sm_count = 0;
+    ULTRA_CUDA_OK(cudaGetDevice(&device));
+    ULTRA_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    ULTRA_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmemBytes));
+    // the (rows, 2N) operand as a 2-D tensor: inner dimension = the 2N columns the Linear reads, rows lda floats apart
+    EncodeTiled encode = nullptr;
+    if (int status = encode_tiled(&encode)) return status;
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)S::K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)lda * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::kSlotK, (cuuint32_t)tc::kRows};
+    const cuuint32_t element_strides[2] = {1, 1};
+    if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)A, dims, strides, box, element_strides, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return fail_cuda(cudaErrorInvalidValue);
     const long long n_tiles = (rows + tc::kRows - 1) / tc::kRows;
     const unsigned grid = (unsigned)(n_tiles < sm_count ? n_tiles : sm_count);
-    kernel<<<grid, tc::kThreads, S::kSmemBytes, stream>>>(A, lda, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu,
+    kernel<<<grid, tc::kThreads, S::kSmemBytes, stream>>>(map, A, lda, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu,
                                                          shortcut);
     note_launch();
     ULTRA_CUDA_OK(cudaGetLastError());
