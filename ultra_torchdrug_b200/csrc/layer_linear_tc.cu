@@ -7,9 +7,10 @@
 //
 // Persistent CTAs, one per SM, warp-specialised (10 warps):
 //   warp  0     TMA producer (one thread): per 128-row tile and 32-column K slot one cp.async.bulk.tensor.2d (box
-//               32 floats x 128 rows = 16 KB, SWIZZLE_128B: the canonical K-major UMMA layout) into a ring of 3 slots;
+//               32 floats x 128 rows = 16 KB, SWIZZLE_128B: the canonical K-major UMMA layout) into a ring of 5 slots
+//               (80 KB in flight per SM: the kernel is bound by HBM latency x bytes in flight, ncu: DRAM 42 % at 3 slots);
 //   warps 2-5   split: each 16-byte chunk of a landed slot is read once and rewritten in place as hi = tf32(x), its
-//               remainder lo = tf32(x - hi) goes to the slot's second half at the same (swizzled) position;
+//               remainder lo = tf32(x - hi) goes to one of two lo tiles at the same (swizzled) position;
 //   warp  1     one elected thread issues, per slot, 4 k-steps x 3 MMAs (lo_a hi_b, hi_a lo_b, hi_a hi_b; M = 128, N, K = 8)
 //               into one of two accumulator stages in TMEM and commits them to the slot's `empty` barrier;
 //   warps 6-9   epilogue: tcgen05.ld of their 32 TMEM lanes (one thread = one row, all N columns), LayerNorm statistics in
@@ -31,7 +32,8 @@ namespace {
 namespace tc {
 constexpr int kRows = 128;                             // UMMA M
 constexpr int kSlotK = 32;                             // K columns per ring slot = 4 k-steps of 8
-constexpr int kSlots = 3;
+constexpr int kSlots = 5;                              // landing / hi slots: 80 KB of TMA loads in flight per SM
+constexpr int kLoSlots = 2;                            // lo tiles live only from the split to the end of their MMAs
 constexpr int kTmaWarp = 0;
 constexpr int kMmaWarp = 1;
 constexpr int kSplitWarp0 = 2;
@@ -40,7 +42,7 @@ constexpr int kEpilogueWarp0 = kSplitWarp0 + kSplitWarps;
 constexpr int kEpilogueWarps = 4;
 constexpr int kThreads = 32 * (kEpilogueWarp0 + kEpilogueWarps);
 constexpr int kSlotHalfBytes = kRows * kSlotK * 4;     // hi (or lo) part of a slot: 16 KB = one TMA box
-constexpr int kBarriers = 3 * kSlots + 4;
+constexpr int kBarriers = 3 * kSlots + kLoSlots + 4;
 
 template <int N> struct Shape {
     static constexpr int K = 2 * N;
@@ -49,7 +51,8 @@ template <int N> struct Shape {
     static constexpr int kCoreBytesW = N * 16;          // LBO of the W operand
     static constexpr int kRingOffset = (2 * kWeightHalfBytes + 1023) / 1024 * 1024;   // SWIZZLE_128B slots: 1024-byte aligned
     static constexpr int kStageStride = N + 4;          // floats per staged output row (bank-conflict-free both ways)
-    static constexpr int kStagingOffset = kRingOffset + kSlots * 2 * kSlotHalfBytes;
+    static constexpr int kLoOffset = kRingOffset + kSlots * kSlotHalfBytes;
+    static constexpr int kStagingOffset = kLoOffset + kLoSlots * kSlotHalfBytes;
     static constexpr int kBarrierOffset = kStagingOffset + kEpilogueWarps * 32 * kStageStride * 4;
     static constexpr int kSmemBytes = kBarrierOffset + kBarriers * 8 + 16;
     static constexpr int kTmemColumns = 2 * N < 32 ? 32 : 2 * N;   // two accumulator stages; power of two >= 32
@@ -135,8 +138,9 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
     auto full_bar = [&](int slot) { return bar_base + 8u * slot; };
     auto empty_bar = [&](int slot) { return bar_base + 8u * (tc::kSlots + slot); };
     auto landed_bar = [&](int slot) { return bar_base + 8u * (2 * tc::kSlots + slot); };
-    auto tmem_full_bar = [&](int stage) { return bar_base + 8u * (3 * tc::kSlots + stage); };
-    auto tmem_empty_bar = [&](int stage) { return bar_base + 8u * (3 * tc::kSlots + 2 + stage); };
+    auto lo_empty_bar = [&](int slot) { return bar_base + 8u * (3 * tc::kSlots + slot); };
+    auto tmem_full_bar = [&](int stage) { return bar_base + 8u * (3 * tc::kSlots + tc::kLoSlots + stage); };
+    auto tmem_empty_bar = [&](int stage) { return bar_base + 8u * (3 * tc::kSlots + tc::kLoSlots + 2 + stage); };
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + S::kBarrierOffset + tc::kBarriers * 8);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -147,6 +151,7 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
             mbar_init(empty_bar(s), 1);
             mbar_init(landed_bar(s), 1);
         }
+        for (int s = 0; s < tc::kLoSlots; ++s) mbar_init(lo_empty_bar(s), 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(tmem_full_bar(s), 1);
             mbar_init(tmem_empty_bar(s), tc::kEpilogueWarps);
@@ -189,7 +194,7 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
                 const int k0 = (int)(it % kSlotsPerTile) * tc::kSlotK;
                 mbar_wait(empty_bar(slot), phase ^ 1u);                  // the MMAs that read this slot have completed
                 mbar_expect_tx(landed_bar(slot), tc::kSlotHalfBytes);
-                tma_load_2d(smem_base + S::kRingOffset + slot * 2 * tc::kSlotHalfBytes, &a_map, k0, (int)(tile * tc::kRows),
+                tma_load_2d(smem_base + S::kRingOffset + slot * tc::kSlotHalfBytes, &a_map, k0, (int)(tile * tc::kRows),
                             landed_bar(slot));                           // rows past the end are filled with zeros
             }
         }
@@ -200,8 +205,12 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
         for (long long it = 0; it < total; ++it) {
             const int slot = (int)(it % tc::kSlots);
             const unsigned phase = (unsigned)((it / tc::kSlots) & 1);
+            const int lo_slot = (int)(it % tc::kLoSlots);
+            const unsigned lo_phase = (unsigned)((it / tc::kLoSlots) & 1);
             mbar_wait(landed_bar(slot), phase);
-            unsigned char *hi_at = smem + S::kRingOffset + slot * 2 * tc::kSlotHalfBytes;
+            mbar_wait(lo_empty_bar(lo_slot), lo_phase ^ 1u);              // the MMAs that read this lo tile have completed
+            unsigned char *hi_at = smem + S::kRingOffset + slot * tc::kSlotHalfBytes;
+            unsigned char *lo_at = smem + S::kLoOffset + lo_slot * tc::kSlotHalfBytes;
             constexpr int kChunksPerThread = tc::kSlotHalfBytes / 16 / (32 * tc::kSplitWarps);
             float4 x[kChunksPerThread];
 #pragma unroll
@@ -212,9 +221,9 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
                 const float4 hi = make_float4(tc_tf32(x[q].x), tc_tf32(x[q].y), tc_tf32(x[q].z), tc_tf32(x[q].w));
                 const float4 lo = make_float4(tc_tf32(x[q].x - hi.x), tc_tf32(x[q].y - hi.y), tc_tf32(x[q].z - hi.z),
                                               tc_tf32(x[q].w - hi.w));
-                unsigned char *at = hi_at + 16 * (t + q * 32 * tc::kSplitWarps);
-                *reinterpret_cast<float4 *>(at) = hi;
-                *reinterpret_cast<float4 *>(at + tc::kSlotHalfBytes) = lo;
+                const int offset = 16 * (t + q * 32 * tc::kSplitWarps);
+                *reinterpret_cast<float4 *>(hi_at + offset) = hi;
+                *reinterpret_cast<float4 *>(lo_at + offset) = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor cores
             __syncwarp();
@@ -236,8 +245,9 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
                     const unsigned phase = (unsigned)((it / tc::kSlots) & 1);
                     mbar_wait(full_bar(slot), phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const unsigned a_hi = smem_base + S::kRingOffset + slot * 2 * tc::kSlotHalfBytes;
-                    const unsigned a_lo = a_hi + tc::kSlotHalfBytes;
+                    const int lo_slot = (int)(it % tc::kLoSlots);
+                    const unsigned a_hi = smem_base + S::kRingOffset + slot * tc::kSlotHalfBytes;
+                    const unsigned a_lo = smem_base + S::kLoOffset + lo_slot * tc::kSlotHalfBytes;
 #pragma unroll
                     for (int ks = 0; ks < tc::kSlotK / 8; ++ks) {
                         const int kg = q * (tc::kSlotK / 8) + ks;        // k-step within the tile: two core matrices each
@@ -250,6 +260,7 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
                         umma_tf32(tmem_d, da_hi, db_hi, S::kInstr, 1u);
                     }
                     umma_commit(empty_bar(slot));                        // slot free once these MMAs have read it
+                    umma_commit(lo_empty_bar(lo_slot));
                 }
                 umma_commit(tmem_full_bar(stage));                       // accumulator complete
             }

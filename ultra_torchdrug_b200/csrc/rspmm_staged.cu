@@ -326,21 +326,15 @@ __global__ void __launch_bounds__(kStagedThreads, 1) pairs_in_smem_kernel(const 
 
 // ---- destination-blocked grad_relation ------------------------------------------------------------------------------------
 // item = (slab, destination block b): the CTA stages grad_output rows [b * block_rows, (b + 1) * block_rows) of the slab,
-// then warp w reduces the (relation k, block b) runs for k = w, w + 24, ...:  acc += g[dst] (x) x[src]  with g from shared
+// then warp w reduces the (relation k, block b) runs for k = w, w + 32, ...:  acc += g[dst] (x) x[src]  with g from shared
 // memory and x gathered (half-warp per edge, LDG.128).  Every (k, b) run writes one partial row (zeros when empty); the
 // combine pass folds the n_block partial rows of a relation in block order - deterministic, no atomics on data.
-//
-// The pass is bound by HBM *latency* unless enough gathers are in flight (ncu, 16.8 M edges: DRAM 42 % busy at 4 rows
-// per half-warp and 1024 threads): 24 warps x 85 registers keep 8 rows per half-warp in flight (96 KB per SM), the
-// bounds of the next run and its first edge ids are fetched while the current run is reduced, so a run of ~35 edges
-// costs three dependent memory round trips instead of seven.
-template <int MSG, bool PACKED, int kBlockedWarps, int kBlockedDepth>   // warps per CTA; edges in flight per half-warp
-__global__ void __launch_bounds__(kBlockedWarps * 32, 1) dst_blocked_kernel(const BlockedRelArgs a) {
-    constexpr int kBlockedThreads = kBlockedWarps * 32;
+template <int MSG, bool PACKED>
+__global__ void __launch_bounds__(kStagedThreads, 1) dst_blocked_kernel(const BlockedRelArgs a) {
     using Ids = typename std::conditional<PACKED, unsigned, int2>::type;
     extern __shared__ __align__(16) float4 s_rows[];
-    __shared__ __align__(16) Ids s_edge[kBlockedWarps][32];
-    __shared__ __align__(16) float s_w[kBlockedWarps][32];
+    __shared__ __align__(16) Ids s_edge[kStagedWarps][32];
+    __shared__ __align__(16) float s_w[kStagedWarps][32];
     __shared__ int s_item;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int half = lane >> 4, l16 = lane & 15;
@@ -349,7 +343,6 @@ __global__ void __launch_bounds__(kBlockedWarps * 32, 1) dst_blocked_kernel(cons
     const unsigned row_bytes = (unsigned)(a.dim * sizeof(float));
     const int n_item = a.n_block * a.n_slab;
     const Ids *ids = reinterpret_cast<const Ids *>(PACKED ? (const void *)a.packed : (const void *)a.edge);
-    const bool weighted = a.w != nullptr;
     for (;;) {
         if (threadIdx.x == 0) s_item = (int)atomicAdd(a.counter, 1u);
         __syncthreads();
@@ -358,20 +351,7 @@ __global__ void __launch_bounds__(kBlockedWarps * 32, 1) dst_blocked_kernel(cons
         const int slab = item / a.n_block, b = item - slab * a.n_block;
         const int first_row = b * a.block_rows;
         const int rows = min(a.block_rows, a.n_out - first_row);
-        // this warp's first run: bounds and edge ids travel while the block is staged
-        int k = warp;
-        int begin = 0, end = 0;
-        if (k < a.n_rel) {
-            begin = __ldg(a.block_ptr + (long long)k * (a.n_block + 1) + b);
-            end = __ldg(a.block_ptr + (long long)k * (a.n_block + 1) + b + 1);
-        }
-        Ids ahead = Ids();
-        float ahead_w = 1.f;
-        if (begin + lane < end) {
-            ahead = __ldg(ids + begin + lane);
-            if (weighted) ahead_w = __ldg(a.w + begin + lane);
-        }
-        for (int i = threadIdx.x; i < rows * (kStagedSlab / 4); i += kBlockedThreads) {
+        for (int i = threadIdx.x; i < rows * (kStagedSlab / 4); i += kStagedThreads) {
             const long long c = (long long)slab * kStagedSlab + (i & 15) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < a.dim) v = __ldg(reinterpret_cast<const float4 *>(a.G + (long long)(first_row + (i >> 4)) * a.dim + c));
@@ -381,77 +361,66 @@ __global__ void __launch_bounds__(kBlockedWarps * 32, 1) dst_blocked_kernel(cons
         const long long col = (long long)slab * kStagedSlab + l16 * 4;
         const bool active = col < a.dim;
         const char *X = reinterpret_cast<const char *>(a.X + (active ? col : 0));
-        auto dst_of = [&](const Ids &e) { return PACKED ? (int)(id_bits_of(e) & low) : id_first(e); };
-        auto src_of = [&](const Ids &e) { return PACKED ? (int)(id_bits_of(e) >> shift) : id_second(e); };
-        while (k < a.n_rel) {
-            const int k_next = k + kBlockedWarps;
-            int next_begin = 0, next_end = 0;
-            if (k_next < a.n_rel) {     // used after this run: the loads overlap with it
-                next_begin = __ldg(a.block_ptr + (long long)k_next * (a.n_block + 1) + b);
-                next_end = __ldg(a.block_ptr + (long long)k_next * (a.n_block + 1) + b + 1);
-            }
+        for (int k = warp; k < a.n_rel; k += kStagedWarps) {
+            const int begin = __ldg(a.block_ptr + (long long)k * (a.n_block + 1) + b);
+            const int end = __ldg(a.block_ptr + (long long)k * (a.n_block + 1) + b + 1);
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            auto fetch_next_run = [&]() {
-                ahead = Ids();
-                ahead_w = 1.f;
-                if (next_begin + lane < next_end) {
-                    ahead = __ldg(ids + next_begin + lane);
-                    if (weighted) ahead_w = __ldg(a.w + next_begin + lane);
+            auto one = [&](const Ids &e, float w) {
+                const int dst = PACKED ? (int)(id_bits_of(e) & low) : id_first(e);
+                const int src = PACKED ? (int)(id_bits_of(e) >> shift) : id_second(e);
+                const float4 g = s_rows[(dst - first_row) * (kStagedSlab / 4) + l16];
+                float4 x = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (MSG == MSG_MUL) {
+                    Vec<float, 4> v;
+                    gather_load(reinterpret_cast<const float *>(X + (unsigned long long)(unsigned)src * row_bytes), v);
+                    x = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
                 }
+                const float gv[4] = {g.x, g.y, g.z, g.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[v] += MSG == MSG_MUL ? w * (gv[v] * xv[v]) : w * gv[v];
             };
-            if (begin >= end) fetch_next_run();
+            Ids ahead = Ids();
+            float ahead_w = 1.f;
+            if (begin + lane < end) {
+                ahead = __ldg(ids + begin + lane);
+                if (a.w) ahead_w = __ldg(a.w + begin + lane);
+            }
             for (int base = begin; base < end; base += 32) {
                 const int n = min(32, end - base);
                 __syncwarp();
                 s_edge[warp][lane] = ahead;
-                if (weighted) s_w[warp][lane] = ahead_w;
+                s_w[warp][lane] = ahead_w;
                 __syncwarp();
-                if (base + 32 < end) {      // next batch of this run, or the first batch of the next one
-                    if (base + 32 + lane < end) {
-                        ahead = __ldg(ids + base + 32 + lane);
-                        if (weighted) ahead_w = __ldg(a.w + base + 32 + lane);
-                    }
-                } else {
-                    fetch_next_run();
+                if (base + 32 + lane < end) {
+                    ahead = __ldg(ids + base + 32 + lane);
+                    if (a.w) ahead_w = __ldg(a.w + base + 32 + lane);
                 }
                 int u = 0;
-                for (; u + 2 * kBlockedDepth <= n; u += 2 * kBlockedDepth) {
-                    const int mine = u + half * kBlockedDepth;
-                    Vec<float, 4> x[kBlockedDepth];
-                    if (MSG == MSG_MUL) {
+                for (; u + 2 * kEdgesPerHalf <= n; u += 2 * kEdgesPerHalf) {
+                    const int mine = u + half * kEdgesPerHalf;
+                    Ids e[4];
+                    float w[4];
+                    float4 g[4];
+                    Vec<float, 4> x[4];
 #pragma unroll
-                        for (int q = 0; q < kBlockedDepth; ++q)
-                            gather_load(reinterpret_cast<const float *>(X + (unsigned long long)(unsigned)src_of(s_edge[warp][mine + q]) * row_bytes), x[q]);
+                    for (int q = 0; q < 4; ++q) {
+                        e[q] = s_edge[warp][mine + q];
+                        w[q] = s_w[warp][mine + q];
+                        const int dst = PACKED ? (int)(id_bits_of(e[q]) & low) : id_first(e[q]);
+                        const int src = PACKED ? (int)(id_bits_of(e[q]) >> shift) : id_second(e[q]);
+                        if (MSG == MSG_MUL) gather_load(reinterpret_cast<const float *>(X + (unsigned long long)(unsigned)src * row_bytes), x[q]);
+                        g[q] = s_rows[(dst - first_row) * (kStagedSlab / 4) + l16];
                     }
 #pragma unroll
-                    for (int q = 0; q < kBlockedDepth; ++q) {
-                        const float4 g = s_rows[(dst_of(s_edge[warp][mine + q]) - first_row) * (kStagedSlab / 4) + l16];
-                        const float w = weighted ? s_w[warp][mine + q] : 1.f;
-                        const float gv[4] = {g.x, g.y, g.z, g.w};
+                    for (int q = 0; q < 4; ++q) {
+                        const float gv[4] = {g[q].x, g[q].y, g[q].z, g[q].w};
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) acc[v] += MSG == MSG_MUL ? w * (gv[v] * x[q].v[v]) : w * gv[v];
+                        for (int v = 0; v < 4; ++v) acc[v] += MSG == MSG_MUL ? w[q] * (gv[v] * x[q].v[v]) : w[q] * gv[v];
                     }
                 }
-                // ragged tail (< 16 edges): the halves alternate; all of a half's loads are issued before the first use
-                {
-                    Vec<float, 4> x[kBlockedDepth];
-                    if (MSG == MSG_MUL) {
-#pragma unroll
-                        for (int q = 0; q < kBlockedDepth; ++q) {
-                            const int mine = u + 2 * q + half;
-                            if (mine < n) gather_load(reinterpret_cast<const float *>(X + (unsigned long long)(unsigned)src_of(s_edge[warp][mine]) * row_bytes), x[q]);
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < kBlockedDepth; ++q) {
-                        if (u + 2 * q + half < n) {
-                            const float4 g = s_rows[(dst_of(s_edge[warp][u + 2 * q + half]) - first_row) * (kStagedSlab / 4) + l16];
-                            const float w = weighted ? s_w[warp][u + 2 * q + half] : 1.f;
-                            const float gv[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-                            for (int v = 0; v < 4; ++v) acc[v] += MSG == MSG_MUL ? w * (gv[v] * x[q].v[v]) : w * gv[v];
-                        }
-                    }
+                for (; u < n; u += 2) {
+                    const int mine = u + half;
+                    if (mine < n) one(s_edge[warp][mine], s_w[warp][mine]);
                 }
             }
 #pragma unroll
@@ -460,9 +429,6 @@ __global__ void __launch_bounds__(kBlockedWarps * 32, 1) dst_blocked_kernel(cons
                 float *p = a.partial + ((long long)k * a.n_block + b) * a.dim + col;
                 *reinterpret_cast<float4 *>(p) = make_float4(acc[0], acc[1], acc[2], acc[3]);
             }
-            k = k_next;
-            begin = next_begin;
-            end = next_end;
         }
         __syncthreads();
     }
@@ -541,22 +507,14 @@ int launch_dst_blocked(BlockedRelArgs args, int msg, cudaStream_t stream) {
     const long long items = (long long)args.n_block * args.n_slab;
     const int blocks = (int)(items < sms ? items : sms);
     ULTRA_CUDA_OK(cudaMemsetAsync(args.counter, 0, sizeof(unsigned), stream));
-    // 32 warps x 4 rows per half-warp (64 registers) or 20 warps x 8 rows (96 registers): ULTRA_RSPMM_BLOCKED_DEPTH
-    static const int depth = getenv("ULTRA_RSPMM_BLOCKED_DEPTH") ? atoi(getenv("ULTRA_RSPMM_BLOCKED_DEPTH")) : 4;
-#define ULTRA_BLOCKED_LAUNCH(M, P, W, D)                                                                                       \
-    do {                                                                                                                       \
-        ULTRA_CUDA_OK(cudaFuncSetAttribute(dst_blocked_kernel<M, P, W, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        dst_blocked_kernel<M, P, W, D><<<blocks, W * 32, smem, stream>>>(args);                                               \
-    } while (0)
 #define ULTRA_BLOCKED(M, P)                                                                                                   \
     do {                                                                                                                       \
-        if (depth == 8) ULTRA_BLOCKED_LAUNCH(M, P, 20, 8);                                                                     \
-        else ULTRA_BLOCKED_LAUNCH(M, P, 32, 4);                                                                                \
+        ULTRA_CUDA_OK(cudaFuncSetAttribute(dst_blocked_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        dst_blocked_kernel<M, P><<<blocks, kStagedThreads, smem, stream>>>(args);                                             \
     } while (0)
     const bool packed = args.packed != nullptr && args.pack_shift > 0;
     if (msg == MSG_MUL) { if (packed) ULTRA_BLOCKED(MSG_MUL, true); else ULTRA_BLOCKED(MSG_MUL, false); }
     else { if (packed) ULTRA_BLOCKED(MSG_COPY, true); else ULTRA_BLOCKED(MSG_COPY, false); }
-#undef ULTRA_BLOCKED_LAUNCH
 #undef ULTRA_BLOCKED
     note_launch();
     return ULTRA_RSPMM_OK;
