@@ -138,7 +138,8 @@ enum {
     ULTRA_RSPMM_KERNEL_SEG_PNA = 3,       /* four PNA aggregates in one pass                                          */
     ULTRA_RSPMM_KERNEL_ROWS_IN_SMEM = 4,  /* few-row operands: the gathered slab is staged in shared memory           */
     ULTRA_RSPMM_KERNEL_DST_BLOCKED = 5,   /* grad_relation with grad_output rows of a destination block in shared memory */
-    ULTRA_RSPMM_KERNEL_PAIRS_IN_SMEM = 6  /* few-row operands with <= 4 relation types: one row read per (node, node) pair */
+    ULTRA_RSPMM_KERNEL_PAIRS_IN_SMEM = 6, /* few-row operands with <= 4 relation types: one row read per (node, node) pair */
+    ULTRA_RSPMM_KERNEL_SUBWARP_ROWS = 7   /* slabs beyond L2: 2 or 4 tasks per warp, 256- / 128-byte slabs (n_slab tells which) */
 };
 typedef struct ultra_rspmm_pass_info {
     int32_t kernel;    /* ULTRA_RSPMM_KERNEL_*                                        */
@@ -161,6 +162,10 @@ int ultra_rspmm_set_tuning(int32_t chunk, int32_t variant, int64_t l2_budget_byt
  * rel_model.py:253-257): 0 = never, 1 = automatic (default: when the slab refills are small against the edge work),
  * 2 = whenever the operand fits (tests). */
 int ultra_rspmm_set_staged(int32_t mode);
+/* Sub-warp rows kernel for graphs whose 512-byte column slab of the gathered operand exceeds `slab_bytes` (default 100 MiB;
+ * 0 = never): 2 or 4 tasks per warp over 256- or 128-byte slabs, so that the slab is L2-resident again.  sub: 0 = chosen by
+ * the slab size, 2 / 4 = forced (tests). */
+int ultra_rspmm_set_narrow(int64_t slab_bytes, int32_t sub);
 /* Index extensions built by ultra_rspmm_index_extend afterwards (0 = never, 1 = automatic, 2 = whenever the graph
  * qualifies structurally): pair lists; destination-block table. */
 int ultra_rspmm_set_extensions(int32_t pairs, int32_t blocked);

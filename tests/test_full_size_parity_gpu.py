@@ -43,6 +43,9 @@ CASES = {
     "c4": dict(graph="yago310", dim=4096, slabs=(0, 13, 31), grel_kernel="dst_blocked",
                expect={"fwd": dict(keep=1, grouped=1), "gin": dict(keep=1, grouped=1), "grel": dict(split=True)}),
     # a shape of the configs[4] sweep (E = 4 M, N = E / 32, R' = 474): HBM-resident slabs, 1.3 M (relation, block) runs
+    # E = 8.4 M, N = 262,144: the 512-byte slab (134 MB) exceeds L2 -> sub-warp rows kernel (2 tasks per warp, 256-byte slabs)
+    "c5_8m": dict(uniform=(1 << 23, 1 << 18, 474), dim=1024, slabs=(0, 6), grel_kernel="dst_blocked", fwd_kernel="subwarp_rows",
+                  ops=[("add", "mul"), ("add", "add"), ("min", "mul")], expect={"grel": dict(split=True)}),
     "c5_4m": dict(uniform=(1 << 22, 1 << 17, 474), dim=1024, slabs=(0, 5), grel_kernel="dst_blocked",
                   ops=[("add", "mul"), ("add", "add"), ("max", "mul")],
                   expect={"fwd": dict(keep=1, grouped=0), "grel": dict(split=True)}),
@@ -139,14 +142,17 @@ def test_full_size_matches_oracle(cuda, name, sum, mul):
     gin_info, grel_info = _lib.pass_info(_lib.PASS_GRAD_INPUT), _lib.pass_info(_lib.PASS_GRAD_RELATION)
 
     # ---- which kernels ran -----------------------------------------------------------------------------------------
-    assert forward_info["kernel_name"] == "seg_reduce" and forward_info["vec"] == 4 and forward_info["packed"] == 1
+    forward_kernel = case.spec.get("fwd_kernel", "seg_reduce") if sum == "add" else "seg_reduce"
+    assert forward_info["kernel_name"] == forward_kernel and forward_info["vec"] == 4 and forward_info["packed"] == 1, forward_info
+    if forward_kernel == "subwarp_rows":
+        assert forward_info["n_slab"] == case.dim // 64                     # 2 tasks per warp, 64-feature slabs
     want = dict(expect.get("fwd", {}))
     if sum != "add":
         want.pop("grouped", None)           # tasks that carry an arg-index are never grouped
         assert forward_info["grouped"] == 0
     _check_info(forward_info, want, "forward")
     backward_kernel = "seg_reduce" if sum == "add" else "seg_gated"
-    assert gin_info["kernel_name"] == backward_kernel
+    assert gin_info["kernel_name"] == (forward_kernel if sum == "add" else backward_kernel), gin_info
     assert grel_info["kernel_name"] == (case.spec.get("grel_kernel", "seg_reduce") if sum == "add" else "seg_gated"), grel_info
     if sum == "add":
         _check_info(gin_info, expect.get("gin", {}), "grad_input")

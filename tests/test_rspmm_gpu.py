@@ -899,3 +899,72 @@ def test_destination_blocked_grad_relation_parity(cuda, extensions_always, mul, 
     h_rel, _ = derived.backward(d_rel, d_in, None, d_grad, "add", mul)
     assert lib.pass_info(lib.PASS_GRAD_RELATION)["kernel_name"] == "dst_blocked"
     _assert_sum_close(h_rel.cpu().numpy(), 0.5 * e_rel, 0.5 * s_rel, "blocked grad_relation of a derived index")
+
+
+@pytest.mark.parametrize("sum", ["max", "min"])
+def test_minmax_gradient_all_ties_rule_ext_recall(cuda, sum):
+    """Hand-computed known answer for the min / max backward: EVERY edge whose message equals the extremum receives the
+    full upstream gradient (torchdrug `NaryMax::backward(out, y) = (out == y)`).  [ext-recall]: the rule follows this
+    repo's recollection of the un-vendored torchdrug source; the reference's own fallback path
+    cannot pin it (torch_scatter routes the gradient to one arg-index), and tests/test_torchdrug_probe.py compares with
+    the real operator whenever torchdrug is importable."""
+    from ultra_torchdrug_b200 import functional as F
+    # destination 0 receives three edges with equal messages (sources 0, 1, 2 hold the same value), destination 1 one edge
+    indices = torch.tensor([[0, 0, 0, 1], [0, 1, 2, 3], [0, 0, 1, 0]], device=cuda)
+    values = torch.ones(4, device=cuda)
+    index = F.GraphIndex(indices, values, (2, 4, 2))
+    relation = torch.tensor([[2.0, 2.0], [2.0, 2.0]], device=cuda)
+    input = torch.tensor([[3.0, -1.0], [3.0, -1.0], [3.0, -1.0], [5.0, 4.0]], device=cuda)
+    grad = torch.tensor([[1.0, 10.0], [100.0, 1000.0]], device=cuda)
+    out, arg = index.forward(relation, input, sum, "mul", return_argidx=True)
+    assert out.tolist() == [[6.0, -2.0], [10.0, 8.0]]
+    assert arg.tolist() == [[0, 0], [3, 3]]                     # the first tied edge in coalesce() order
+    g_rel, g_in = index.backward(relation, input, out, grad, sum, "mul")
+    # all three tied edges of destination 0 get g * rel = (2, 20); a single-winner rule would give (2, 20), 0, 0
+    assert g_in.tolist() == [[2.0, 20.0], [2.0, 20.0], [2.0, 20.0], [200.0, 2000.0]]
+    # relation 0: edges (0<-0), (0<-1), (1<-3); relation 1: edge (0<-2)
+    assert g_rel.tolist() == [[3.0 + 3.0 + 500.0, -10.0 - 10.0 + 4000.0], [3.0, -10.0]]
+
+
+@pytest.mark.parametrize("sub", [2, 4])
+@pytest.mark.parametrize("mul", ["mul", "add"])
+@pytest.mark.parametrize("weights,chunk,dim", [("unit", 0, 256), ("random", 0, 100), ("random", 16, 132), ("unit", 0, 36)])
+def test_subwarp_rows_kernel_parity(cuda, sub, mul, weights, chunk, dim):
+    """The sub-warp rows kernel (2 or 4 tasks per warp, 256- / 128-byte slabs; production use: slabs beyond L2), forced
+    on a small graph: forward, grad_input and grad_relation (two gathered operands) against the oracle, ragged widths,
+    merged duplicates with non-unit weights, split rows (chunk 16) and empty rows included."""
+    from ultra_torchdrug_b200 import functional as F, _lib
+    lib = _lib.lib()
+    _lib.check(lib.ultra_rspmm_set_narrow(1, sub), "ultra_rspmm_set_narrow")
+    if chunk:
+        lib.ultra_rspmm_set_tuning(chunk, 0, 0)
+    try:
+        n, n_rel, nnz = 1500, 9, 20000
+        indices, values = util.random_coo(n, n - 11, n_rel, nnz, seed=dim + sub, duplicates=300, weights=weights, skew=True)
+        shape = (n, n - 11, n_rel)
+        relation, input, grad = util.random_dense(n_rel, dim, 1), util.random_dense(n - 11, dim, 2), util.random_dense(n, dim, 3)
+        index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), shape)
+        d_rel, d_in, d_grad = (torch.from_numpy(x).to(cuda) for x in (relation, input, grad))
+        out = index.forward(d_rel, d_in, "add", mul)
+        info = _lib.pass_info(_lib.PASS_FORWARD)
+        assert info["kernel_name"] == "subwarp_rows" and info["n_slab"] == -(-dim // (128 // sub)), info
+        g_rel, g_in = index.backward(d_rel, d_in, out, d_grad, "add", mul)
+        assert _lib.pass_info(_lib.PASS_GRAD_INPUT)["kernel_name"] == "subwarp_rows"
+        assert _lib.pass_info(_lib.PASS_GRAD_RELATION)["kernel_name"] == "subwarp_rows"
+        exp, _ = util.oracle_forward(indices, values, shape, relation, input, "add", mul, dtype=np.float64)
+        scale, _ = util.oracle_forward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), "add", mul, dtype=np.float64)
+        _assert_sum_close(out.cpu().numpy(), exp, scale, "sub-warp forward")
+        e_rel, e_in = util.oracle_backward(indices, values, shape, relation, input, None, grad, "add", mul, dtype=np.float64)
+        s_rel, s_in = util.oracle_backward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), None, np.abs(grad),
+                                           "add", mul, dtype=np.float64)
+        _assert_sum_close(g_rel.cpu().numpy(), e_rel, s_rel, "sub-warp grad_relation")
+        _assert_sum_close(g_in.cpu().numpy(), e_in, s_in, "sub-warp grad_input")
+        assert torch.equal(out, index.forward(d_rel, d_in, "add", mul)), "two runs differ"
+        with_addend = index.forward(d_rel, d_in, "add", mul, addend=d_grad)
+        _assert_sum_close(with_addend.cpu().numpy(), exp + grad, scale + np.abs(grad), "sub-warp forward + addend")
+        index.forward(d_rel, d_in, "max", mul)                      # min / max keep the generic kernel
+        assert _lib.pass_info(_lib.PASS_FORWARD)["kernel_name"] == "seg_reduce"
+    finally:
+        _lib.check(lib.ultra_rspmm_set_narrow(100 << 20, 0), "ultra_rspmm_set_narrow")
+        if chunk:
+            lib.ultra_rspmm_set_tuning(256, 0, 0)

@@ -48,13 +48,14 @@ class PassInfo(ctypes.Structure):
 
 PASS_FORWARD, PASS_GRAD_INPUT, PASS_GRAD_RELATION = 0, 1, 2
 KERNEL_NAMES = {0: "none", 1: "seg_reduce", 2: "seg_gated", 3: "seg_pna", 4: "rows_in_smem", 5: "dst_blocked",
-                6: "pairs_in_smem"}
+                6: "pairs_in_smem", 7: "subwarp_rows"}
 
 #: every symbol `include/ultra_rspmm.h` declares: name -> (restype, argtypes)
 SYMBOLS = {
     "ultra_rspmm_last_pass_info": (ctypes.c_int, [c_int32, ctypes.POINTER(PassInfo)]),
     "ultra_rspmm_set_staged": (ctypes.c_int, [c_int32]),
     "ultra_rspmm_set_extensions": (ctypes.c_int, [c_int32, c_int32]),
+    "ultra_rspmm_set_narrow": (ctypes.c_int, [c_int64, c_int32]),
     "ultra_rspmm_index_extend_bytes": (ctypes.c_int, [ctypes.POINTER(Index), ctypes.POINTER(c_size_t)]),
     "ultra_rspmm_index_extend": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_size_t, c_void_p]),
     "ultra_probe_gather": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, ctypes.POINTER(c_int64),

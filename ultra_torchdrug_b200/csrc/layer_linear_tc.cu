@@ -21,6 +21,7 @@
 // hi / lo once per CTA (no-swizzle K-major layout; the two operands' layouts are independent).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "rspmm_common.cuh"
@@ -32,8 +33,6 @@ namespace {
 namespace tc {
 constexpr int kRows = 128;                             // UMMA M
 constexpr int kSlotK = 32;                             // K columns per ring slot = 4 k-steps of 8
-constexpr int kSlots = 5;                              // landing / hi slots: 80 KB of TMA loads in flight per SM
-constexpr int kLoSlots = 2;                            // lo tiles live only from the split to the end of their MMAs
 constexpr int kTmaWarp = 0;
 constexpr int kMmaWarp = 1;
 constexpr int kSplitWarp0 = 2;
@@ -42,9 +41,11 @@ constexpr int kEpilogueWarp0 = kSplitWarp0 + kSplitWarps;
 constexpr int kEpilogueWarps = 4;
 constexpr int kThreads = 32 * (kEpilogueWarp0 + kEpilogueWarps);
 constexpr int kSlotHalfBytes = kRows * kSlotK * 4;     // hi (or lo) part of a slot: 16 KB = one TMA box
-constexpr int kBarriers = 3 * kSlots + kLoSlots + 4;
 
-template <int N> struct Shape {
+// HI landing / hi slots (16 KB each, the TMA loads in flight), LO lo tiles (live from the split to the end of their MMAs)
+template <int N, int HI, int LO> struct Shape {
+    static constexpr int kSlots = HI, kLoSlots = LO;
+    static constexpr int kBarriers = 3 * HI + LO + 4;
     static constexpr int K = 2 * N;
     static constexpr int kSlotsPerTile = K / kSlotK;
     static constexpr int kWeightHalfBytes = N * K * 4;
@@ -55,6 +56,7 @@ template <int N> struct Shape {
     static constexpr int kStagingOffset = kLoOffset + kLoSlots * kSlotHalfBytes;
     static constexpr int kBarrierOffset = kStagingOffset + kEpilogueWarps * 32 * kStageStride * 4;
     static constexpr int kSmemBytes = kBarrierOffset + kBarriers * 8 + 16;
+    static_assert(kSmemBytes <= 227 * 1024, "ring does not fit the 227 KB of shared memory a CTA may use");
     static constexpr int kTmemColumns = 2 * N < 32 ? 32 : 2 * N;   // two accumulator stages; power of two >= 32
     // instruction descriptor: D = F32 (bits 4-5), A = B = TF32 (bits 7-9, 10-12), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     static constexpr unsigned kInstr = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(kRows >> 4) << 24);
@@ -123,35 +125,35 @@ __device__ __forceinline__ void tmem_load16(unsigned taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int N>
+template <int N, int HI, int LO>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, const float *__restrict__ A, long long lda,
                                     const float *__restrict__ W,
                                     const float *__restrict__ linear_bias, const float *__restrict__ gamma,
                                     const float *__restrict__ beta, float *__restrict__ out, long long ldo, long long rows,
                                     float eps, int relu, int shortcut) {
-    using S = tc::Shape<N>;
+    using S = tc::Shape<N, HI, LO>;
     constexpr int K = S::K, kSlotsPerTile = S::kSlotsPerTile;
     extern __shared__ __align__(1024) unsigned char smem[];
     const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
     const unsigned bar_base = smem_base + S::kBarrierOffset;
     auto full_bar = [&](int slot) { return bar_base + 8u * slot; };
-    auto empty_bar = [&](int slot) { return bar_base + 8u * (tc::kSlots + slot); };
-    auto landed_bar = [&](int slot) { return bar_base + 8u * (2 * tc::kSlots + slot); };
-    auto lo_empty_bar = [&](int slot) { return bar_base + 8u * (3 * tc::kSlots + slot); };
-    auto tmem_full_bar = [&](int stage) { return bar_base + 8u * (3 * tc::kSlots + tc::kLoSlots + stage); };
-    auto tmem_empty_bar = [&](int stage) { return bar_base + 8u * (3 * tc::kSlots + tc::kLoSlots + 2 + stage); };
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + S::kBarrierOffset + tc::kBarriers * 8);
+    auto empty_bar = [&](int slot) { return bar_base + 8u * (S::kSlots + slot); };
+    auto landed_bar = [&](int slot) { return bar_base + 8u * (2 * S::kSlots + slot); };
+    auto lo_empty_bar = [&](int slot) { return bar_base + 8u * (3 * S::kSlots + slot); };
+    auto tmem_full_bar = [&](int stage) { return bar_base + 8u * (3 * S::kSlots + S::kLoSlots + stage); };
+    auto tmem_empty_bar = [&](int stage) { return bar_base + 8u * (3 * S::kSlots + S::kLoSlots + 2 + stage); };
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + S::kBarrierOffset + S::kBarriers * 8);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- one-time setup: barriers, tensor memory, W split into hi / lo in UMMA layout ----------------------------------
     if (tid == 0) {
-        for (int s = 0; s < tc::kSlots; ++s) {
+        for (int s = 0; s < S::kSlots; ++s) {
             mbar_init(full_bar(s), tc::kSplitWarps);
             mbar_init(empty_bar(s), 1);
             mbar_init(landed_bar(s), 1);
         }
-        for (int s = 0; s < tc::kLoSlots; ++s) mbar_init(lo_empty_bar(s), 1);
+        for (int s = 0; s < S::kLoSlots; ++s) mbar_init(lo_empty_bar(s), 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(tmem_full_bar(s), 1);
             mbar_init(tmem_empty_bar(s), tc::kEpilogueWarps);
@@ -188,8 +190,8 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
             asm volatile("prefetch.tensormap [%0];" ::"l"(&a_map) : "memory");
             const long long total = my_tiles * kSlotsPerTile;
             for (long long it = 0; it < total; ++it) {
-                const int slot = (int)(it % tc::kSlots);
-                const unsigned phase = (unsigned)((it / tc::kSlots) & 1);
+                const int slot = (int)(it % S::kSlots);
+                const unsigned phase = (unsigned)((it / S::kSlots) & 1);
                 const long long tile = first + (it / kSlotsPerTile) * gridDim.x;
                 const int k0 = (int)(it % kSlotsPerTile) * tc::kSlotK;
                 mbar_wait(empty_bar(slot), phase ^ 1u);                  // the MMAs that read this slot have completed
@@ -203,10 +205,10 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
         const int t = tid - 32 * tc::kSplitWarp0;                        // 0 .. 127
         const long long total = my_tiles * kSlotsPerTile;
         for (long long it = 0; it < total; ++it) {
-            const int slot = (int)(it % tc::kSlots);
-            const unsigned phase = (unsigned)((it / tc::kSlots) & 1);
-            const int lo_slot = (int)(it % tc::kLoSlots);
-            const unsigned lo_phase = (unsigned)((it / tc::kLoSlots) & 1);
+            const int slot = (int)(it % S::kSlots);
+            const unsigned phase = (unsigned)((it / S::kSlots) & 1);
+            const int lo_slot = (int)(it % S::kLoSlots);
+            const unsigned lo_phase = (unsigned)((it / S::kLoSlots) & 1);
             mbar_wait(landed_bar(slot), phase);
             mbar_wait(lo_empty_bar(lo_slot), lo_phase ^ 1u);              // the MMAs that read this lo tile have completed
             unsigned char *hi_at = smem + S::kRingOffset + slot * tc::kSlotHalfBytes;
@@ -241,11 +243,11 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned tmem_d = tmem_base + (unsigned)(stage * N);
                 for (int q = 0; q < kSlotsPerTile; ++q, ++it) {
-                    const int slot = (int)(it % tc::kSlots);
-                    const unsigned phase = (unsigned)((it / tc::kSlots) & 1);
+                    const int slot = (int)(it % S::kSlots);
+                    const unsigned phase = (unsigned)((it / S::kSlots) & 1);
                     mbar_wait(full_bar(slot), phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const int lo_slot = (int)(it % tc::kLoSlots);
+                    const int lo_slot = (int)(it % S::kLoSlots);
                     const unsigned a_hi = smem_base + S::kRingOffset + slot * tc::kSlotHalfBytes;
                     const unsigned a_lo = smem_base + S::kLoOffset + lo_slot * tc::kSlotHalfBytes;
 #pragma unroll
@@ -372,12 +374,12 @@ int encode_tiled(EncodeTiled *out) {
     return ULTRA_RSPMM_OK;
 }
 
-template <int N>
+template <int N, int HI, int LO>
 int launch_linear_tc(const float *A, long long lda, const float *W, const float *linear_bias, const float *gamma,
                      const float *beta, float *out, long long ldo, long long rows, float eps, int relu, int shortcut,
                      cudaStream_t stream) {
-    using S = tc::Shape<N>;
-    auto kernel = linear_norm_relu_residual_tc_kernel<N>;
+    using S = tc::Shape<N, HI, LO>;
+    auto kernel = linear_norm_relu_residual_tc_kernel<N, HI, LO>;
     int device = 0, sm_count = 0;
     ULTRA_CUDA_OK(cudaGetDevice(&device));
     ULTRA_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -408,8 +410,20 @@ int launch_linear_tc(const float *A, long long lda, const float *W, const float 
 int layer_linear_tc(const float *A, long long lda, const float *W, const float *linear_bias, const float *gamma,
                     const float *beta, float *out, long long ldo, long long rows, int out_dim, float eps, int relu,
                     int shortcut, cudaStream_t stream) {
-    if (out_dim == 64) return launch_linear_tc<64>(A, lda, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu, shortcut, stream);
-    return launch_linear_tc<32>(A, lda, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu, shortcut, stream);
+    // ring shape: ULTRA_LINEAR_RING = "<hi slots><lo tiles>" (development knob; default 33)
+    static const int ring = getenv("ULTRA_LINEAR_RING") ? atoi(getenv("ULTRA_LINEAR_RING")) : 33;
+#define ULTRA_TC(N, HI, LO) launch_linear_tc<N, HI, LO>(A, lda, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu, shortcut, stream)
+    if (out_dim == 64) {
+        switch (ring) {
+            case 43: return ULTRA_TC(64, 4, 3);
+            case 44: return ULTRA_TC(64, 4, 4);
+            case 52: return ULTRA_TC(64, 5, 2);
+            case 53: return ULTRA_TC(64, 5, 3);
+            default: return ULTRA_TC(64, 3, 3);
+        }
+    }
+    return ULTRA_TC(32, 3, 3);
+#undef ULTRA_TC
 }
 
 }  // namespace ultra

@@ -13,6 +13,8 @@ static std::atomic<long long> g_launches{0};
 static thread_local int t_last_cuda_error = 0;
 int g_chunk = 256;
 int g_variant = 0;
+long long g_narrow_bytes = (getenv("ULTRA_RSPMM_NARROW_MB") ? atoll(getenv("ULTRA_RSPMM_NARROW_MB")) : 100) << 20;
+int g_narrow_sub = getenv("ULTRA_RSPMM_NARROW_SUB") ? atoi(getenv("ULTRA_RSPMM_NARROW_SUB")) : 0;
 int g_staged = getenv("ULTRA_RSPMM_STAGED") ? atoi(getenv("ULTRA_RSPMM_STAGED")) : 1;
 int g_group_edges = getenv("ULTRA_RSPMM_GROUP") ? atoi(getenv("ULTRA_RSPMM_GROUP")) : -1;
 long long g_l2_budget = 1ll << 40;   // slab narrowing off by default: it lost on every measured shape (profiles/)
@@ -68,6 +70,13 @@ extern "C" int ultra_rspmm_set_tuning(int32_t chunk, int32_t variant, int64_t l2
 extern "C" int ultra_rspmm_set_staged(int32_t mode) {
     if (mode < 0 || mode > 2) return ULTRA_RSPMM_ERR_ARG;
     g_staged = mode;
+    return ULTRA_RSPMM_OK;
+}
+
+extern "C" int ultra_rspmm_set_narrow(int64_t slab_bytes, int32_t sub) {
+    if (slab_bytes < 0 || (sub != 0 && sub != 2 && sub != 4)) return ULTRA_RSPMM_ERR_ARG;
+    g_narrow_bytes = slab_bytes;
+    g_narrow_sub = sub;
     return ULTRA_RSPMM_OK;
 }
 

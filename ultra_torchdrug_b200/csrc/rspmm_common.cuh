@@ -238,6 +238,25 @@ struct BlockedRelArgs {
 int launch_dst_blocked(BlockedRelArgs args, int msg, cudaStream_t stream);
 extern int g_pairs, g_blocked;
 
+// sub-warp rows kernel (rspmm_narrow.cu): graphs whose 512-byte slab exceeds L2 - SUB tasks per warp, 256 / 128-byte slabs
+struct NarrowArgs {
+    const int4 *task;         // plain task list of the order
+    const int2 *edge;
+    const unsigned *packed;   // or null
+    int pack_shift;
+    const float *w;           // null when all weights are 1
+    const float *A;           // gathered by edge.x
+    const float *B;           // table / gathered by edge.y (unused for MSG_COPY)
+    float *out;
+    const float *addend;
+    float *partial;
+    long long dim;
+    int n_task, n_slab;
+};
+int launch_narrow(const NarrowArgs &args, int msg, bool b_table, int sub, cudaStream_t stream);
+extern int g_narrow_sub;           // 0: by slab size, 2 / 4: forced
+extern long long g_narrow_bytes;   // a 512-byte slab of the gathered operand above this size takes the sub-warp kernel (0: never)
+
 // launch bookkeeping (claimed in bench.py as `gpu_launches`)
 void note_launch();
 // how the last pass of each kind was launched (ultra_rspmm_last_pass_info; read by the parity tests)

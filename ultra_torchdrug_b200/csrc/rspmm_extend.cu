@@ -9,6 +9,7 @@
 //    (rel, dst, src), so the edges of relation k whose destination lies in block b are one contiguous range, found by a
 //    binary search per (k, b).  The blocked grad_relation kernel (rspmm_staged.cu) stages the grad_output rows of a block
 //    in shared memory and gathers only the input rows.
+#include <cstdlib>
 #include <cstring>
 
 #include "rspmm_common.cuh"
@@ -22,7 +23,8 @@ namespace {
 
 constexpr int kPairThreads = 128;
 constexpr int kPairTable = 1024;          // >= kStagedMaxRows, one byte of relation mask per node
-constexpr int kBlockRows = 768;           // destination rows per block: 768 x 256 B = 192 KB of shared memory
+// destination rows per block: 768 x 256 B = 192 KB of shared memory (one CTA per SM); ULTRA_RSPMM_BLOCK_ROWS=384: two CTAs
+const int kBlockRows = getenv("ULTRA_RSPMM_BLOCK_ROWS") ? (atoi(getenv("ULTRA_RSPMM_BLOCK_ROWS")) > 0 && atoi(getenv("ULTRA_RSPMM_BLOCK_ROWS")) <= 768 ? atoi(getenv("ULTRA_RSPMM_BLOCK_ROWS")) : 768) : 768;
 
 // relation masks of one segment: table[other] |= 1 << rel (bytes packed four to a word, set with shared-memory atomics -
 // integer OR is order-independent)

@@ -758,6 +758,31 @@ int run_pass(int pass, const ultra_rspmm_index_t &ix, const ultra_rspmm_order_t 
         folded.n_split = ix.n_rel;
         return launch_combine<T, SUM, ARG>(folded, (const T *)workspace, nullptr, out, nullptr, dim, stream);
     }
+    // slab of the gathered operand far beyond L2: sub-warp rows kernel with a 256- or 128-byte slab that is L2-resident
+    // again (rspmm_narrow.cu).  grad_relation with two gathered operands only when the narrow slabs of both fit.
+    if (std::is_same<T, float>::value && SUM == ULTRA_RSPMM_SUM_ADD && !ARG && vec == 4 && !layout.block && g_narrow_bytes > 0 &&
+        rows_gathered * 512 > g_narrow_bytes && (B_TABLE || rows_gathered * 128 <= (96ll << 20)) &&
+        (order.n_slot == 0 || workspace)) {
+        const int sub = g_narrow_sub ? g_narrow_sub : (rows_gathered * 256 <= (72ll << 20) ? 2 : 4);
+        NarrowArgs na = {};
+        na.task = (const int4 *)order.task;
+        na.edge = (const int2 *)order.edge;
+        na.packed = order.pack_shift > 0 ? (const unsigned *)order.packed : nullptr;
+        na.pack_shift = order.pack_shift;
+        na.w = unit_weight ? nullptr : (const float *)order.w;
+        na.A = (const float *)A; na.B = (const float *)B; na.out = (float *)out; na.addend = (const float *)addend;
+        na.partial = (float *)workspace;
+        na.dim = dim;
+        na.n_task = order.n_task;
+        if (int status = launch_narrow(na, MSG, B_TABLE, sub, stream)) return status;
+        info.kernel = ULTRA_RSPMM_KERNEL_SUBWARP_ROWS;
+        info.vec = 4;
+        info.keep = 1;
+        info.n_task = order.n_task;
+        info.n_slab = (int)((dim + 128 / sub - 1) / (128 / sub));
+        note_pass(pass, info);
+        return launch_combine<T, SUM, ARG>(order, args.partial, args.partial_arg, out, arg_out, dim, stream, addend, layout);
+    }
     if (staged_applies<T, SUM, MSG, B_TABLE, ARG>(order, rows_gathered, dim, vec, ix.nnz, workspace, workspace_bytes, counter_at)) {
         StagedArgs staged = {};
         staged.task = (const int4 *)order.task;

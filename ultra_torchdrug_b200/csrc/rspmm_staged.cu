@@ -329,12 +329,13 @@ __global__ void __launch_bounds__(kStagedThreads, 1) pairs_in_smem_kernel(const 
 // then warp w reduces the (relation k, block b) runs for k = w, w + 32, ...:  acc += g[dst] (x) x[src]  with g from shared
 // memory and x gathered (half-warp per edge, LDG.128).  Every (k, b) run writes one partial row (zeros when empty); the
 // combine pass folds the n_block partial rows of a relation in block order - deterministic, no atomics on data.
-template <int MSG, bool PACKED>
-__global__ void __launch_bounds__(kStagedThreads, 1) dst_blocked_kernel(const BlockedRelArgs a) {
+template <int MSG, bool PACKED, int WARPS, int CTAS>   // WARPS x 32 threads per CTA, CTAS CTAs per SM (WARPS * CTAS = 32)
+__global__ void __launch_bounds__(WARPS * 32, CTAS) dst_blocked_kernel(const BlockedRelArgs a) {
     using Ids = typename std::conditional<PACKED, unsigned, int2>::type;
+    constexpr int kThreads = WARPS * 32;
     extern __shared__ __align__(16) float4 s_rows[];
-    __shared__ __align__(16) Ids s_edge[kStagedWarps][32];
-    __shared__ __align__(16) float s_w[kStagedWarps][32];
+    __shared__ __align__(16) Ids s_edge[WARPS][32];
+    __shared__ __align__(16) float s_w[WARPS][32];
     __shared__ int s_item;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int half = lane >> 4, l16 = lane & 15;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1) dst_blocked_kernel(const Bl
         const int slab = item / a.n_block, b = item - slab * a.n_block;
         const int first_row = b * a.block_rows;
         const int rows = min(a.block_rows, a.n_out - first_row);
-        for (int i = threadIdx.x; i < rows * (kStagedSlab / 4); i += kStagedThreads) {
+        for (int i = threadIdx.x; i < rows * (kStagedSlab / 4); i += kThreads) {
             const long long c = (long long)slab * kStagedSlab + (i & 15) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < a.dim) v = __ldg(reinterpret_cast<const float4 *>(a.G + (long long)(first_row + (i >> 4)) * a.dim + c));
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(kStagedThreads, 1) dst_blocked_kernel(const Bl
         const long long col = (long long)slab * kStagedSlab + l16 * 4;
         const bool active = col < a.dim;
         const char *X = reinterpret_cast<const char *>(a.X + (active ? col : 0));
-        for (int k = warp; k < a.n_rel; k += kStagedWarps) {
+        for (int k = warp; k < a.n_rel; k += WARPS) {
             const int begin = __ldg(a.block_ptr + (long long)k * (a.n_block + 1) + b);
             const int end = __ldg(a.block_ptr + (long long)k * (a.n_block + 1) + b + 1);
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -505,17 +506,25 @@ int launch_dst_blocked(BlockedRelArgs args, int msg, cudaStream_t stream) {
     int sms = 0;
     if (int status = sm_count(&sms)) return status;
     const long long items = (long long)args.n_block * args.n_slab;
-    const int blocks = (int)(items < sms ? items : sms);
     ULTRA_CUDA_OK(cudaMemsetAsync(args.counter, 0, sizeof(unsigned), stream));
+    // blocks of <= 400 rows (<= 100 KB of shared memory): two CTAs of 16 warps per SM, so that one CTA's block refill and
+    // end-of-item barrier overlap with the other's gathers; larger blocks: one CTA of 32 warps
+    const bool two = smem <= 100 * 1024;
+#define ULTRA_BLOCKED_LAUNCH(M, P, W, C)                                                                                       \
+    do {                                                                                                                       \
+        ULTRA_CUDA_OK(cudaFuncSetAttribute(dst_blocked_kernel<M, P, W, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        dst_blocked_kernel<M, P, W, C><<<(items < C * sms ? (int)items : C * sms), W * 32, smem, stream>>>(args);              \
+    } while (0)
 #define ULTRA_BLOCKED(M, P)                                                                                                   \
     do {                                                                                                                       \
-        ULTRA_CUDA_OK(cudaFuncSetAttribute(dst_blocked_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        dst_blocked_kernel<M, P><<<blocks, kStagedThreads, smem, stream>>>(args);                                             \
+        if (two) ULTRA_BLOCKED_LAUNCH(M, P, 16, 2);                                                                            \
+        else ULTRA_BLOCKED_LAUNCH(M, P, 32, 1);                                                                                \
     } while (0)
     const bool packed = args.packed != nullptr && args.pack_shift > 0;
     if (msg == MSG_MUL) { if (packed) ULTRA_BLOCKED(MSG_MUL, true); else ULTRA_BLOCKED(MSG_MUL, false); }
     else { if (packed) ULTRA_BLOCKED(MSG_COPY, true); else ULTRA_BLOCKED(MSG_COPY, false); }
 #undef ULTRA_BLOCKED
+#undef ULTRA_BLOCKED_LAUNCH
     note_launch();
     return ULTRA_RSPMM_OK;
 }
