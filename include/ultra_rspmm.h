@@ -162,9 +162,10 @@ int ultra_rspmm_set_tuning(int32_t chunk, int32_t variant, int64_t l2_budget_byt
  * rel_model.py:253-257): 0 = never, 1 = automatic (default: when the slab refills are small against the edge work),
  * 2 = whenever the operand fits (tests). */
 int ultra_rspmm_set_staged(int32_t mode);
-/* Sub-warp rows kernel for graphs whose 512-byte column slab of the gathered operand exceeds `slab_bytes` (default 100 MiB;
- * 0 = never): 2 or 4 tasks per warp over 256- or 128-byte slabs, so that the slab is L2-resident again.  sub: 0 = chosen by
- * the slab size, 2 / 4 = forced (tests). */
+/* Sub-warp rows kernel (experimental, off by default: slab_bytes = 0) for graphs whose 512-byte column slab of the gathered
+ * operand exceeds `slab_bytes`: 2 or 4 tasks per warp over 256- or 128-byte slabs, so that the slab is L2-resident again.
+ * Measured slower than the generic kernel at every shape of the configs[4] sweep.  sub: 0 = chosen by the slab
+ * size, 2 / 4 = forced (tests). */
 int ultra_rspmm_set_narrow(int64_t slab_bytes, int32_t sub);
 /* Index extensions built by ultra_rspmm_index_extend afterwards (0 = never, 1 = automatic, 2 = whenever the graph
  * qualifies structurally): pair lists; destination-block table. */

@@ -43,9 +43,9 @@ CASES = {
     "c4": dict(graph="yago310", dim=4096, slabs=(0, 13, 31), grel_kernel="dst_blocked",
                expect={"fwd": dict(keep=1, grouped=1), "gin": dict(keep=1, grouped=1), "grel": dict(split=True)}),
     # a shape of the configs[4] sweep (E = 4 M, N = E / 32, R' = 474): HBM-resident slabs, 1.3 M (relation, block) runs
-    # E = 8.4 M, N = 262,144: the 512-byte slab (134 MB) exceeds L2 -> sub-warp rows kernel (2 tasks per warp, 256-byte slabs)
-    "c5_8m": dict(uniform=(1 << 23, 1 << 18, 474), dim=1024, slabs=(0, 6), grel_kernel="dst_blocked", fwd_kernel="subwarp_rows",
-                  ops=[("add", "mul"), ("add", "add"), ("min", "mul")], expect={"grel": dict(split=True)}),
+    # E = 8.4 M, N = 262,144: the 512-byte slab (134 MB) exceeds L2: HBM-bound generic kernel with hints + blocked grad_relation
+    "c5_8m": dict(uniform=(1 << 23, 1 << 18, 474), dim=1024, slabs=(0, 6), grel_kernel="dst_blocked",
+                  ops=[("add", "mul"), ("add", "add"), ("min", "mul")], expect={"fwd": dict(keep=1), "grel": dict(split=True)}),
     "c5_4m": dict(uniform=(1 << 22, 1 << 17, 474), dim=1024, slabs=(0, 5), grel_kernel="dst_blocked",
                   ops=[("add", "mul"), ("add", "add"), ("max", "mul")],
                   expect={"fwd": dict(keep=1, grouped=0), "grel": dict(split=True)}),

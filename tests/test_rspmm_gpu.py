@@ -965,6 +965,6 @@ def test_subwarp_rows_kernel_parity(cuda, sub, mul, weights, chunk, dim):
         index.forward(d_rel, d_in, "max", mul)                      # min / max keep the generic kernel
         assert _lib.pass_info(_lib.PASS_FORWARD)["kernel_name"] == "seg_reduce"
     finally:
-        _lib.check(lib.ultra_rspmm_set_narrow(100 << 20, 0), "ultra_rspmm_set_narrow")
+        _lib.check(lib.ultra_rspmm_set_narrow(0, 0), "ultra_rspmm_set_narrow")
         if chunk:
             lib.ultra_rspmm_set_tuning(256, 0, 0)

@@ -1,4 +1,4 @@
-"""rspmm microbenchmark sweep (BASELINE.json configs[4]): E in 1M..16M directed edges, N = E / 32, R' in 64..2000,
+"""rspmm microbenchmark sweep (BASELINE.json configs[4]): E in {1, 2, 4, 8, 16} M directed edges, N = E / 32, R' in 64..2000,
 D in 256..8192, {add, max} x {mul (DistMult), add (TransE)}, forward and forward+backward vs the HBM roofline.
 
     python tools/sweep.py [--quick] > profiles/r01_sweep.csv
@@ -52,10 +52,10 @@ def main():
         peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    edges = [1 << 20, 1 << 22] if args.quick else [1 << 20, 1 << 22, 1 << 24]
+    edges = [1 << 20, 1 << 22] if args.quick else [1 << 20, 1 << 21, 1 << 22, 1 << 23, 1 << 24]
     relations = [64, 2000] if args.quick else [64, 474, 2000]
     dims = [256, 4096] if args.quick else [256, 1024, 4096, 8192]
-    ops = [("add", "mul"), ("max", "mul"), ("add", "add")]
+    ops = [("add", "mul"), ("max", "mul"), ("add", "add"), ("max", "add")]
     print("E_raw,E,N,R,D,sum,mul,index_ms,fwd_ms,fwd_bwd_ms,fwd_GBps,fwd_pct_hbm,fwd_bwd_GBps,fwd_bwd_pct_hbm,G_edge_msgs_per_s_fwd")
     generator = torch.Generator(device=device).manual_seed(1024)
     for e_raw in edges:

@@ -13,7 +13,8 @@ static std::atomic<long long> g_launches{0};
 static thread_local int t_last_cuda_error = 0;
 int g_chunk = 256;
 int g_variant = 0;
-long long g_narrow_bytes = (getenv("ULTRA_RSPMM_NARROW_MB") ? atoll(getenv("ULTRA_RSPMM_NARROW_MB")) : 100) << 20;
+// off by default: measured slower than the 512-byte generic kernel on every shape tried (DESIGN.md "Tried and rejected")
+long long g_narrow_bytes = (getenv("ULTRA_RSPMM_NARROW_MB") ? atoll(getenv("ULTRA_RSPMM_NARROW_MB")) : 0) << 20;
 int g_narrow_sub = getenv("ULTRA_RSPMM_NARROW_SUB") ? atoi(getenv("ULTRA_RSPMM_NARROW_SUB")) : 0;
 int g_staged = getenv("ULTRA_RSPMM_STAGED") ? atoi(getenv("ULTRA_RSPMM_STAGED")) : 1;
 int g_group_edges = getenv("ULTRA_RSPMM_GROUP") ? atoi(getenv("ULTRA_RSPMM_GROUP")) : -1;

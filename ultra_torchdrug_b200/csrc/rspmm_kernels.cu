@@ -16,6 +16,7 @@
 // any moment read one (rows x SLAB) column block of the gathered operand - it stays in the 126 MB
 // L2 - and one (n_rel x SLAB) block of the relation table, which stays in L1.  HBM traffic is then
 // the compulsory bytes; the gathers are L2 hits.  No atomics anywhere: results are bit-reproducible.
+#include <cstdlib>
 #include <initializer_list>
 #include <type_traits>
 
@@ -655,6 +656,12 @@ static size_t slot_bytes(const ultra_rspmm_order_t &order, long long dim, size_t
     return bytes;
 }
 
+// largest workspace the destination-blocked pass may ask for (partial rows: n_rel x n_block x dim floats)
+static size_t blocked_cap() {
+    static const size_t cap = (size_t)(getenv("ULTRA_RSPMM_BLOCKED_MAX_GB") ? atoll(getenv("ULTRA_RSPMM_BLOCKED_MAX_GB")) : 16) << 30;
+    return cap;
+}
+
 // workspace of the destination-blocked grad_relation pass: n_rel x n_block partial rows + its work counter
 static size_t blocked_bytes(const ultra_rspmm_index_t &ix, long long dim) {
     if (!ix.block_ptr || ix.dtype != ULTRA_RSPMM_F32) return 0;
@@ -734,7 +741,7 @@ int run_pass(int pass, const ultra_rspmm_index_t &ix, const ultra_rspmm_order_t 
     // grad_relation of graphs whose gathered slabs exceed L2: destination-blocked pass (3 row gathers per edge and step)
     if (std::is_same<T, float>::value && SUM == ULTRA_RSPMM_SUM_ADD && !ARG && pass == GREL && vec == 4 && g_blocked != 0 &&
         ix.block_ptr && !layout.block && !addend && workspace &&
-        workspace_bytes >= blocked_bytes(ix, dim) && blocked_bytes(ix, dim) <= (16ull << 30)) {
+        workspace_bytes >= blocked_bytes(ix, dim) && blocked_bytes(ix, dim) <= blocked_cap()) {
         BlockedRelArgs ba = {};
         ba.block_ptr = ix.block_ptr;
         ba.edge = (const int2 *)order.edge;
@@ -1033,7 +1040,7 @@ extern "C" int ultra_rspmm_workspace_bytes(const ultra_rspmm_index_t *index, int
     if (forward_bytes) *forward_bytes = pass_bytes(index->csr, dim, elem, true);
     if (backward_bytes) {
         const size_t a = pass_bytes(index->csc, dim, elem, false), b = pass_bytes(index->rel, dim, elem, false);
-        const size_t c = dtype == ULTRA_RSPMM_F32 && blocked_bytes(*index, dim) <= (16ull << 30) ? blocked_bytes(*index, dim) : 0;
+        const size_t c = dtype == ULTRA_RSPMM_F32 && blocked_bytes(*index, dim) <= blocked_cap() ? blocked_bytes(*index, dim) : 0;
         *backward_bytes = a > b ? (a > c ? a : c) : (b > c ? b : c);
     }
     return ULTRA_RSPMM_OK;
