@@ -153,12 +153,17 @@ def test_full_size_matches_oracle(cuda, name, sum, mul):
     _check_info(forward_info, want, "forward")
     backward_kernel = "seg_reduce" if sum == "add" else "seg_gated"
     assert gin_info["kernel_name"] == (forward_kernel if sum == "add" else backward_kernel), gin_info
-    assert grel_info["kernel_name"] == (case.spec.get("grel_kernel", "seg_reduce") if sum == "add" else "seg_gated"), grel_info
+    # the destination-blocked pass serves DistMult here; TransE (grad_output is the only gathered operand) keeps the generic
+    # kernel until that one slab is far beyond L2 (n_out * 512 B > 150 MB: none of these shapes)
+    want_grel = "seg_gated" if sum != "add" else (case.spec.get("grel_kernel", "seg_reduce") if mul == "mul" else "seg_reduce")
+    assert grel_info["kernel_name"] == want_grel, grel_info
     if sum == "add":
         _check_info(gin_info, expect.get("gin", {}), "grad_input")
         want = dict(expect.get("grel", {}))
         if mul == "add":
             want.pop("keep", None)          # TransE: grad_relation gathers grad_output only (half the slab bytes)
+            if "grel_kernel" in case.spec:
+                want["keep"] = 1            # ... through the generic kernel with L2 hints on these large shapes
         _check_info(grel_info, want, "grad_relation")
     else:
         _check_info(grel_info, {k: v for k, v in expect.get("grel", {}).items() if k == "split"}, "grad_relation")

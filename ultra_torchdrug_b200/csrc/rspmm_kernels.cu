@@ -658,7 +658,7 @@ static size_t slot_bytes(const ultra_rspmm_order_t &order, long long dim, size_t
 
 // largest workspace the destination-blocked pass may ask for (partial rows: n_rel x n_block x dim floats)
 static size_t blocked_cap() {
-    static const size_t cap = (size_t)(getenv("ULTRA_RSPMM_BLOCKED_MAX_GB") ? atoll(getenv("ULTRA_RSPMM_BLOCKED_MAX_GB")) : 16) << 30;
+    static const size_t cap = (size_t)(getenv("ULTRA_RSPMM_BLOCKED_MAX_GB") ? atoll(getenv("ULTRA_RSPMM_BLOCKED_MAX_GB")) : 24) << 30;
     return cap;
 }
 
@@ -666,6 +666,18 @@ static size_t blocked_cap() {
 static size_t blocked_bytes(const ultra_rspmm_index_t &ix, long long dim) {
     if (!ix.block_ptr || ix.dtype != ULTRA_RSPMM_F32) return 0;
     return align_up((size_t)ix.n_rel * ix.n_block * dim * sizeof(float)) + 256;
+}
+
+// When the blocked pass beats the generic one (configs[4] sweep, profiles/r02_sweep_c5.csv): it trades one row gather per
+// edge for a partial row per (relation, block) run, so the runs must be long enough; DistMult saves the grad_output gather
+// once the two slabs exceed L2 (slightly: runs >= 24 edges; far: runs >= 8); TransE gathers grad_output only, which the
+// staged blocks replace by streaming loads - that pays once that one slab is far beyond L2.
+static bool blocked_pays(const ultra_rspmm_index_t &ix, long long dim, int msg) {
+    if (g_blocked == 2) return true;
+    const double run = (double)ix.nnz / ((double)ix.n_rel * (ix.n_block > 0 ? ix.n_block : 1));
+    if (msg == MSG_COPY) return (long long)ix.n_out * 512 > (150ll << 20) && run >= 8;
+    const long long both = ((long long)ix.n_out + ix.n_in) * 512;
+    return dim >= 512 && ((both > (200ll << 20) && run >= 8) || run >= 24);
 }
 
 // Few-row operands (the graph of relations): the gathered operand's 64-feature slab fits shared memory and every edge
@@ -740,7 +752,7 @@ int run_pass(int pass, const ultra_rspmm_index_t &ix, const ultra_rspmm_order_t 
     }
     // grad_relation of graphs whose gathered slabs exceed L2: destination-blocked pass (3 row gathers per edge and step)
     if (std::is_same<T, float>::value && SUM == ULTRA_RSPMM_SUM_ADD && !ARG && pass == GREL && vec == 4 && g_blocked != 0 &&
-        ix.block_ptr && !layout.block && !addend && workspace &&
+        ix.block_ptr && !layout.block && !addend && workspace && blocked_pays(ix, dim, MSG) &&
         workspace_bytes >= blocked_bytes(ix, dim) && blocked_bytes(ix, dim) <= blocked_cap()) {
         BlockedRelArgs ba = {};
         ba.block_ptr = ix.block_ptr;
