@@ -316,6 +316,25 @@ int ultra_layer_linear_norm_relu_residual(const float *dev_input, int64_t input_
                                           float *dev_out, int64_t out_stride, int64_t rows, int32_t out_dim, float eps,
                                           int32_t relu, int32_t shortcut, void *stream);
 
+/* ---- the Linear of `combine` under autograd (fine-tuning; reference layer.py:386-392) on the tensor cores -------------------
+ * fp32 accuracy through the 3xTF32 split, no cuBLAS SIMT SGEMM, no `cat([input, update])`.
+ * ultra_layer_rows_gemm:  out[r, 0:n_out] = [a0[r, :] | a1[r, :]] @ weight^T  for `rows` rows (tcgen05 + TMA).
+ *     (n_out, k_in) = (64, 128): the forward Linear; a0 = layer input, a1 = update (64 columns each, a1 may be NULL when a0
+ *                     already holds all 128 columns), weight (64, 128) row-major, out0 (rows, 64).
+ *     (n_out, k_in) = (128, 64): gradient w.r.t. [input | update] = dx @ W; a0 = dx (64 columns), a1 = NULL, weight = W^T
+ *                     (128, 64) row-major; columns [0, 64) go to out0 (+ addend0 when given: the short-cut's gradient),
+ *                     columns [64, 128) to out1 (or to out0 + 64 when out1 is NULL).
+ *     Row strides (ld*) in floats, multiples of 4; all pointers 16-byte aligned.
+ * ultra_layer_rows_gemm_weight:  weight_grad[n, k] = sum_r dx[r, n] * [a0[r, :] | a1[r, :]][k]  -> (64, 128); mma.sync over
+ *     row tiles with per-CTA partial results folded in fixed order (deterministic).  workspace: *_weight_bytes. */
+int ultra_layer_rows_gemm(const float *dev_a0, int64_t lda0, const float *dev_a1, int64_t lda1, const float *dev_weight,
+                          float *dev_out0, int64_t ld_out0, float *dev_out1, int64_t ld_out1, const float *dev_addend0,
+                          int64_t ld_addend0, int64_t rows, int32_t n_out, int32_t k_in, void *stream);
+int ultra_layer_rows_gemm_weight_bytes(size_t *workspace_bytes);
+int ultra_layer_rows_gemm_weight(const float *dev_dx, int64_t ld_dx, const float *dev_a0, int64_t lda0, const float *dev_a1,
+                                 int64_t lda1, int64_t rows, float *dev_weight_grad, void *workspace, size_t workspace_bytes,
+                                 void *stream);
+
 /* which implementation serves ultra_layer_linear_norm_relu_residual: 0 = library default, 1 = mma.sync, 2 = tcgen05 */
 int ultra_layer_linear_set_kernel(int32_t kind);
 

@@ -968,3 +968,50 @@ def test_subwarp_rows_kernel_parity(cuda, sub, mul, weights, chunk, dim):
         _lib.check(lib.ultra_rspmm_set_narrow(0, 0), "ultra_rspmm_set_narrow")
         if chunk:
             lib.ultra_rspmm_set_tuning(256, 0, 0)
+
+
+@pytest.mark.parametrize("rows", [1, 127, 128, 1000, 40000])
+def test_combine_linear_forward_and_backward_have_fp32_accuracy(cuda, rows):
+    """`combine_linear` (tcgen05 + TMA product, mma.sync weight gradient; no cat, no cuBLAS SIMT SGEMM) against a float64
+    evaluation of `cat([input, update]) @ W^T` (reference layer.py:386-388) and its three gradients: errors at the level of
+    the fp32 cuBLAS path, far below what TF32 operands give; deterministic."""
+    from ultra_torchdrug_b200 import functional as F
+    torch.backends.cuda.matmul.allow_tf32 = False
+    generator = torch.Generator(device=cuda).manual_seed(rows)
+    input = (torch.randn(rows, 64, device=cuda, generator=generator) * 2 + 0.3).requires_grad_()
+    update = (torch.randn(rows, 64, device=cuda, generator=generator) * 3 - 0.1).requires_grad_()
+    weight = (torch.randn(64, 128, device=cuda, generator=generator) / 8).requires_grad_()
+    grad = torch.randn(rows, 64, device=cuda, generator=generator)
+
+    def evaluate(dtype, tf32=False):
+        a, b, w = (t.detach().to(dtype).requires_grad_() for t in (input, update, weight))
+        joined = torch.cat([a, b], dim=-1)
+        if tf32:
+            cut = lambda t: (t.detach().view(torch.int32) & ~0x1fff).view(torch.float32)
+            out = cut(joined) @ cut(w).t()
+            return out, None
+        out = joined @ w.t()
+        out.backward(grad.to(dtype))
+        return out.detach(), (a.grad, b.grad, w.grad)
+
+    exact, exact_grads = evaluate(torch.float64)
+    plain, plain_grads = evaluate(torch.float32)
+    tf32_out, _ = evaluate(torch.float32, tf32=True)
+    out = F.combine_linear(input, update, weight)
+    out.backward(grad)
+    got_grads = (input.grad, update.grad, weight.grad)
+    error = lambda value, reference: float((value.double() - reference).abs().max())
+    assert error(out.detach(), exact) <= 4 * error(plain, exact) + 1e-6
+    assert error(out.detach(), exact) < max(error(tf32_out, exact) / 20, 1e-6)
+    for got, want32, want64, name in zip(got_grads, plain_grads, exact_grads, ("input", "update", "weight")):
+        scale = float(want64.abs().max()) + 1e-6
+        assert error(got, want64) <= 4 * error(want32, want64) + 1e-6 * scale, (name, error(got, want64), error(want32, want64))
+    first = [g.clone() for g in got_grads]
+    input.grad = update.grad = weight.grad = None
+    F.combine_linear(input, update, weight).backward(grad)
+    assert all(torch.equal(a, b) for a, b in zip(first, (input.grad, update.grad, weight.grad))), "two runs differ"
+    # (N, B, 64) operands, as the layers pass them
+    shaped = F.combine_linear(input.detach().view(rows, 1, 64), update.detach().view(rows, 1, 64), weight.detach())
+    assert shaped.shape == (rows, 1, 64) and torch.equal(shaped.view(rows, 64), out.detach())
+    with pytest.raises(RuntimeError):
+        F.combine_linear(input[:, :32], update[:, :32], weight)

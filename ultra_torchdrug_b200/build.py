@@ -17,8 +17,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libultra_rspmm.so")
 HASH_PATH = LIB_PATH + ".sha256"
-SOURCES = ["rspmm_api.cu", "rspmm_index.cu", "rspmm_kernels.cu", "rspmm_staged.cu", "rspmm_narrow.cu", "rspmm_extend.cu", "probe.cu", "layer_epilogue.cu", "layer_linear.cu", "layer_linear_tc.cu"]
-HEADERS = [os.path.join(CSRC, "rspmm_common.cuh"), os.path.join(ROOT, "include", "ultra_rspmm.h")]
+SOURCES = ["rspmm_api.cu", "rspmm_index.cu", "rspmm_kernels.cu", "rspmm_staged.cu", "rspmm_narrow.cu", "rspmm_extend.cu", "probe.cu", "layer_epilogue.cu", "layer_linear.cu", "layer_linear_tc.cu", "layer_gemm_tc.cu"]
+HEADERS = [os.path.join(CSRC, "rspmm_common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(ROOT, "include", "ultra_rspmm.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -677,7 +677,7 @@ static bool blocked_pays(const ultra_rspmm_index_t &ix, long long dim, int msg) 
     const double run = (double)ix.nnz / ((double)ix.n_rel * (ix.n_block > 0 ? ix.n_block : 1));
     if (msg == MSG_COPY) return (long long)ix.n_out * 512 > (150ll << 20) && run >= 8;
     const long long both = ((long long)ix.n_out + ix.n_in) * 512;
-    return dim >= 512 && ((both > (200ll << 20) && run >= 8) || run >= 24);
+    return (both > (200ll << 20) && run >= 8) || (dim >= 512 && run >= 24);
 }
 
 // Few-row operands (the graph of relations): the gathered operand's 64-feature slab fits shared memory and every edge

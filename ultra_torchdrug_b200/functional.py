@@ -21,7 +21,8 @@ from . import _lib
 __all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
            "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "RSPMMAddBoundaryFunction", "rspmm_add_one_hot", "RSPMMAddOneHotFunction", "rspmm_pna", "LayerEpilogueFunction",
            "layer_norm_relu_residual_into", "score_head", "fused_linear_supported",
-           "linear_norm_relu_residual_into", "score_head_linear", "attach_index"]
+           "linear_norm_relu_residual_into", "score_head_linear", "attach_index", "combine_linear", "combine_linear_supported",
+           "CombineLinearFunction"]
 
 _SUM_OPS = ("add", "min", "max")
 _MUL_OPS = ("mul", "add")
@@ -382,6 +383,68 @@ def linear_norm_relu_residual_into(buffer, linear_weight, out, linear_bias=None,
             ctypes.c_void_p(out.data_ptr()), out.stride(-2), rows, out_dim, float(eps), int(bool(relu)),
             int(bool(shortcut)), _stream_handle()), "ultra_layer_linear_norm_relu_residual")
     return out
+
+
+def combine_linear_supported(input, update, weight):
+    """Whether `combine_linear` serves this layer: fp32 CUDA, 64 features per half, a (64, 128) weight
+    (ULTRA_FUSED_LINEAR=0 keeps `cat` + the cuBLAS Linear)."""
+    return (input.is_cuda and input.dtype == torch.float32 and update.dtype == torch.float32 and input.shape == update.shape
+            and input.shape[-1] == 64 and tuple(weight.shape) == (64, 128) and weight.dtype == torch.float32
+            and os.environ.get("ULTRA_FUSED_LINEAR", "1") != "0")
+
+
+class CombineLinearFunction(torch.autograd.Function):
+    """`cat([input, update], -1) @ weight^T` of the layer's `combine` (reference layer.py:386-388) without the cat and on the
+    tensor cores at fp32 accuracy (3xTF32), forward and backward: `ultra_layer_rows_gemm` (tcgen05 + TMA) for the product
+    and for the gradient w.r.t. [input | update], `ultra_layer_rows_gemm_weight` (mma.sync, deterministic fold) for the
+    weight gradient.  The bias, LayerNorm, ReLU and the short-cut stay in `layer_norm_relu_residual` (fused forward and
+    backward)."""
+
+    @staticmethod
+    def forward(ctx, input, update, weight):
+        a0 = input.detach().contiguous()
+        a1 = update.detach().contiguous()
+        w = weight.detach().contiguous()
+        rows = a0.numel() // 64
+        out = torch.empty(a0.shape[:-1] + (64,), dtype=torch.float32, device=a0.device)
+        with torch.cuda.device(a0.device):
+            _lib.check(_lib.lib().ultra_layer_rows_gemm(_ptr(a0), 64, _ptr(a1), 64, _ptr(w), _ptr(out), 64, None, 0, None, 0, rows,
+                                                        64, 128, _stream_handle()), "ultra_layer_rows_gemm")
+        ctx.save_for_backward(a0, a1, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        a0, a1, w = ctx.saved_tensors
+        dx = grad_output.contiguous()
+        rows = dx.numel() // 64
+        lib = _lib.lib()
+        grad_input = grad_update = grad_weight = None
+        with torch.cuda.device(dx.device):
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+                grad_input, grad_update = torch.empty_like(a0), torch.empty_like(a1)
+                transposed = w.t().contiguous()                                  # (128, 64): [d input | d update] = dx @ W
+                _lib.check(lib.ultra_layer_rows_gemm(_ptr(dx), 64, None, 0, _ptr(transposed), _ptr(grad_input), 64, _ptr(grad_update),
+                                                     64, None, 0, rows, 128, 64, _stream_handle()), "ultra_layer_rows_gemm")
+            if ctx.needs_input_grad[2]:
+                need = ctypes.c_size_t()
+                _lib.check(lib.ultra_layer_rows_gemm_weight_bytes(ctypes.byref(need)), "ultra_layer_rows_gemm_weight_bytes")
+                workspace = torch.empty(need.value, dtype=torch.uint8, device=dx.device)
+                grad_weight = torch.empty_like(w)
+                _lib.check(lib.ultra_layer_rows_gemm_weight(_ptr(dx), 64, _ptr(a0), 64, _ptr(a1), 64, rows, _ptr(grad_weight),
+                                                            _ptr(workspace), need.value, _stream_handle()),
+                           "ultra_layer_rows_gemm_weight")
+        return grad_input, grad_update, grad_weight
+
+
+def combine_linear(input, update, weight):
+    """`torch.cat([input, update], dim=-1) @ weight^T` for (..., 64) halves and a (64, 128) weight - the Linear of
+    `combine` (reference layer.py:386-388) without its bias - differentiable w.r.t. all three operands."""
+    if not combine_linear_supported(input, update, weight):
+        raise RuntimeError("combine_linear needs float32 CUDA (..., 64) halves of equal shape and a (64, 128) weight")
+    if input.numel() == 0:
+        return input.new_zeros(input.shape)
+    return CombineLinearFunction.apply(input, update, weight)
 
 
 def score_head(z, query_bias, weight, bias=None):

@@ -111,8 +111,15 @@ class _RelationalConvBase(nn.Module):
         """relu(layer_norm(linear(cat[input, update]))) (+ residual: the caller's short-cut, model.py:126-127).
         On CUDA the Linear's bias, the normalisation, the activation and the short-cut run as one fused pass with a
         fused backward; elsewhere they are the reference's separate PyTorch ops."""
-        joined = torch.cat([input, update], dim=-1)
         fusable = self.layer_norm is not None and self.activation in (F.relu, None)
+        if fusable and rspmm.combine_linear_supported(input, update, self.linear.weight) and \
+                rspmm.layer_epilogue_supported(input, self.output_dim):
+            # no cat, tensor-core Linear at fp32 accuracy forward and backward (SURVEY 8 row f1 under autograd)
+            output = rspmm.combine_linear(input, update, self.linear.weight)
+            return rspmm.layer_norm_relu_residual(output, self.layer_norm.weight, self.layer_norm.bias, residual,
+                                                  self.layer_norm.eps, relu=self.activation is not None,
+                                                  linear_bias=self.linear.bias)
+        joined = torch.cat([input, update], dim=-1)
         if fusable and rspmm.layer_epilogue_supported(joined, self.output_dim):
             output = F.linear(joined, self.linear.weight)      # bias, normalisation, activation, short-cut: one pass
             return rspmm.layer_norm_relu_residual(output, self.layer_norm.weight, self.layer_norm.bias, residual,
