@@ -441,6 +441,14 @@ def c3_finetune(device, rank, world, steps, warmup=2):
     generator = torch.Generator().manual_seed(7)                # the same global batches on every rank
     batches = [triples[torch.randint(num_triple, (BATCH,), generator=generator)].to(device) for _ in range(warmup + steps)]
     torch.manual_seed(4096 + rank)                              # negatives differ per rank
+    mode = "eager"
+    if os.environ.get("ULTRA_BENCH_FINETUNE_GRAPH", "1") != "0":
+        try:
+            step.capture(BATCH)                                 # the whole step (incl. the NCCL all-reduce) as one CUDA graph
+            mode = "CUDA graph replay"
+        except Exception as error:                              # noqa: BLE001 - fall back to eager launches
+            step._graph = None
+            mode = "eager (capture failed: %s)" % type(error).__name__
     for batch in batches[:warmup]:
         step(batch)
     torch.cuda.synchronize()
@@ -452,7 +460,7 @@ def c3_finetune(device, rank, world, steps, warmup=2):
     stop.record()
     torch.cuda.synchronize()
     result = {"ms_per_step": start.elapsed_time(stop) / steps, "global_batch": BATCH, "negatives": step.num_negative,
-              "rspmm_launches_per_step": (F.launch_count() - launches) / steps, "loss_share_last_step": float(loss),
+              "rspmm_launches_per_step": (F.launch_count() - launches) / steps, "loss_share_last_step": float(loss), "mode": mode,
               "gradient_bytes": 4 * sum(p.numel() for p in step.parameters)}
     del step, graph
     torch.cuda.empty_cache()

@@ -79,9 +79,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _setup(seed=3):
+def _setup(seed=3, patch=True):
     from oracle.rspmm_oracle import generalized_rspmm_oracle
-    nbf.generalized_rspmm = generalized_rspmm_oracle            # CPU: the layers call the oracle operator
+    if patch:
+        nbf.generalized_rspmm = generalized_rspmm_oracle        # CPU worker processes: the layers call the oracle operator
     num_node, num_relation = 40, 3
     triples = synthetic.triples(num_node, num_relation, 260, seed=seed)
     graph = data.Graph(triples, num_node=num_node, num_relation=num_relation)
@@ -110,12 +111,14 @@ def _worker(rank, world, port, results):
         dist.destroy_process_group()
 
 
-def test_sharded_evaluation_and_finetune_step_gloo():
+def test_sharded_evaluation_and_finetune_step_gloo(monkeypatch):
+    from oracle.rspmm_oracle import generalized_rspmm_oracle
+    monkeypatch.setattr(nbf, "generalized_rspmm", generalized_rspmm_oracle)     # this process: restored after the test
     world = 2
     manager = mp.get_context("spawn").Manager()
     results = manager.dict()
     mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
-    triples, graph, model, rel_model = _setup()
+    triples, graph, model, rel_model = _setup(patch=False)
     batch = triples[:6]
     single = task.ShardedEvaluator(nbf.UltraRanker(model.eval(), rel_model.eval(), graph))(batch)
     assert single.shape == (6, 2) and (single >= 1).all()
@@ -127,3 +130,33 @@ def test_sharded_evaluation_and_finetune_step_gloo():
     for a, b in zip(results[0]["weights"], results[1]["weights"]):
         assert torch.equal(a, b)
     assert any(g is not None and g.abs().sum() > 0 for g in results[0]["grads"])
+
+
+@pytest.mark.gpu
+def test_captured_finetune_step_equals_eager(cuda, monkeypatch):
+    """`FinetuneStep.capture()`: the whole step (strict negatives, forward, backward, AdamW) replayed as one CUDA graph gives
+    the weights of the eager step, bit for bit - every kernel on the path is deterministic - when both draw the same
+    uniform numbers (torch.rand is pinned to a constant here; the graph-safe generator would otherwise differ)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    monkeypatch.setattr(torch, "rand", lambda *shape, device=None, **unused: torch.full(shape, 0.37, device=device))
+    num_node, num_relation = 300, 5
+    triples = synthetic.triples(num_node, num_relation, 2500, seed=9)
+    graph = data.Graph(triples, num_node=num_node, num_relation=num_relation).to(cuda)
+    batches = [triples[16 * i:16 * i + 16].to(cuda) for i in range(4)]
+
+    def build():
+        torch.manual_seed(5)
+        model, rel_model = nbf.ultra_models(num_relation, hidden=64, num_layers=2)
+        return task.FinetuneStep(model.to(cuda).train(), rel_model.to(cuda).train(), graph, num_negative=8)
+
+    eager, captured = build(), build().capture(16)
+    assert captured._graph is not None
+    for a, b in zip(eager.parameters, captured.parameters):
+        assert torch.equal(a, b), "capture() must leave the weights as they were"
+    for batch in batches:
+        loss_eager = eager(batch)
+        loss_captured = captured(batch).clone()
+        torch.testing.assert_close(loss_captured, loss_eager, rtol=1e-6, atol=1e-7)
+    for a, b in zip(eager.parameters, captured.parameters):
+        torch.testing.assert_close(b, a, rtol=1e-6, atol=1e-7)
+    assert torch.isfinite(loss_captured)
