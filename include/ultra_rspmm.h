@@ -316,6 +316,15 @@ int ultra_layer_linear_norm_relu_residual(const float *dev_input, int64_t input_
                                           float *dev_out, int64_t out_stride, int64_t rows, int32_t out_dim, float eps,
                                           int32_t relu, int32_t shortcut, void *stream);
 
+/* The same with the two halves of the Linear's input in two tensors: input[r, 0:out_dim] = layer input (also the short-cut),
+ * update[r, 0:out_dim] = update + boundary - the operator then reads and writes plain (N, B * d) matrices and neither a
+ * `cat` nor an interleaved (N, B, 2d) buffer exists.  tcgen05 + TMA only (two tensor maps); 16-byte aligned pointers. */
+int ultra_layer_linear_norm_relu_residual_two(const float *dev_input, int64_t input_stride, const float *dev_update,
+                                              int64_t update_stride, const float *dev_weight, const float *dev_linear_bias,
+                                              const float *dev_gamma, const float *dev_beta, float *dev_out,
+                                              int64_t out_stride, int64_t rows, int32_t out_dim, float eps, int32_t relu,
+                                              int32_t shortcut, void *stream);
+
 /* ---- the Linear of `combine` under autograd (fine-tuning; reference layer.py:386-392) on the tensor cores -------------------
  * fp32 accuracy through the 3xTF32 split, no cuBLAS SIMT SGEMM, no `cat([input, update])`.
  * ultra_layer_rows_gemm:  out[r, 0:n_out] = [a0[r, :] | a1[r, :]] @ weight^T  for `rows` rows (tcgen05 + TMA).
@@ -337,6 +346,7 @@ int ultra_layer_rows_gemm_weight(const float *dev_dx, int64_t ld_dx, const float
 
 /* which implementation serves ultra_layer_linear_norm_relu_residual: 0 = library default, 1 = mma.sync, 2 = tcgen05 */
 int ultra_layer_linear_set_kernel(int32_t kind);
+int ultra_layer_linear_get_kernel(void);   /* the implementation in effect: 1 or 2 */
 
 /* ---- scoring head (reference model.py:177-193, the 2-layer MLP over [hidden | query]) ---- */
 /* score[r] = bias[0] + sum_c weight[c] * relu(z[r, c] + query_bias[r % batch, c]) over `rows` rows of `dim` fp32 features

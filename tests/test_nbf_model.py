@@ -146,10 +146,11 @@ def test_cuda_graph_predict_equals_eager(cuda):
 
 
 @pytest.mark.gpu
-def test_buffered_layer_loop_equals_generic_loop(cuda, monkeypatch):
-    """The cat-free inference loop (`_run_layers_buffered`) gives the scores of the generic loop (cat + Linear +
-    epilogue): same kernels, same GEMM operands — only where the bytes live differs."""
-    from ultra_torchdrug_b200 import synthetic
+def test_copy_free_layer_loops_equal_generic_loop(cuda, monkeypatch):
+    """The two cat-free inference loops - plain (N, B, d) planes read through two TMA tensor maps (`_run_layers_planes`, the
+    default) and the interleaved (N, B, 2d) buffers (`_run_layers_buffered`) - give the scores of the generic loop (cat +
+    Linear + epilogue): same arithmetic, only where the bytes live differs."""
+    from ultra_torchdrug_b200 import functional as F, synthetic
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(11)
     num_node, num_relation = 400, 7
@@ -158,20 +159,27 @@ def test_buffered_layer_loop_equals_generic_loop(cuda, monkeypatch):
     model, rel_model = nbf.ultra_models(num_relation, hidden=64, num_layers=3)
     ranker = nbf.UltraRanker(model.to(cuda).eval(), rel_model.to(cuda).eval(), graph)
     batch = triples[:6].to(cuda)
-    taken = []
-    original = nbf._run_layers_buffered
-    monkeypatch.setattr(nbf, "_run_layers_buffered", lambda *a, **k: taken.append(1) or original(*a, **k))
+    taken = {"planes": 0, "buffered": 0}
+    planes, buffered = nbf._run_layers_planes, nbf._run_layers_buffered
+    monkeypatch.setattr(nbf, "_run_layers_planes", lambda *a, **k: taken.__setitem__("planes", taken["planes"] + 1) or planes(*a, **k))
+    monkeypatch.setattr(nbf, "_run_layers_buffered", lambda *a, **k: taken.__setitem__("buffered", taken["buffered"] + 1) or buffered(*a, **k))
     with torch.no_grad():
-        buffered = ranker.predict(batch)
-    assert len(taken) == 3, "the buffered loop must serve the relation pass and both entity passes"
+        from_planes = ranker.predict(batch)
+    assert taken == {"planes": 3, "buffered": 0}, "the plane loop must serve the relation pass and both entity passes"
+    monkeypatch.setattr(F, "linear_planes_supported", lambda hidden, out_dim: False)
+    with torch.no_grad():
+        from_buffers = ranker.predict(batch)
+    assert taken == {"planes": 3, "buffered": 3}
     monkeypatch.setattr(nbf, "_buffered_layers_supported", lambda layers, boundary: False)
     with torch.no_grad():
         generic = ranker.predict(batch)
-    assert len(taken) == 3
-    torch.testing.assert_close(buffered, generic, rtol=1e-5, atol=1e-6)
+    assert taken == {"planes": 3, "buffered": 3}
+    torch.testing.assert_close(from_planes, generic, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(from_buffers, generic, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(from_planes, from_buffers, rtol=1e-6, atol=1e-6)
     with torch.enable_grad():                        # training keeps the autograd path
         ranker.predict(batch).sum().backward()
-    assert len(taken) == 3
+    assert taken == {"planes": 3, "buffered": 3}
 
 
 @pytest.mark.gpu

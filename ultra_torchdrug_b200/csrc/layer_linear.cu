@@ -346,7 +346,7 @@ int launch_linear(const float *A, long long lda, const float *W, const float *li
 
 namespace ultra {
 // layer_linear_tc.cu
-int layer_linear_tc(const float *A, long long lda, const float *W, const float *linear_bias, const float *gamma,
+int layer_linear_tc(const float *A, long long lda, const float *A1, long long lda1, const float *W, const float *linear_bias, const float *gamma,
                     const float *beta, float *out, long long ldo, long long rows, int out_dim, float eps, int relu,
                     int shortcut, cudaStream_t stream);
 int g_linear_kernel = 0;   // 0 = default, 1 = mma.sync, 2 = tcgen05
@@ -359,6 +359,8 @@ extern "C" int ultra_layer_linear_set_kernel(int32_t kind) {
     g_linear_kernel = kind;
     return ULTRA_RSPMM_OK;
 }
+
+extern "C" int ultra_layer_linear_get_kernel(void) { return g_linear_kernel ? g_linear_kernel : kDefaultLinearKernel; }
 
 extern "C" int ultra_layer_linear_norm_relu_residual(const float *dev_input, int64_t input_stride, const float *dev_weight,
                                                      const float *dev_linear_bias, const float *dev_gamma,
@@ -378,13 +380,32 @@ extern "C" int ultra_layer_linear_norm_relu_residual(const float *dev_input, int
                               out_stride % 4 == 0;
     const int kind = g_linear_kernel ? g_linear_kernel : kDefaultLinearKernel;
     if (kind == 2 && wide_aligned)
-        return layer_linear_tc(dev_input, input_stride, dev_weight, dev_linear_bias, dev_gamma, dev_beta, dev_out, out_stride,
+        return layer_linear_tc(dev_input, input_stride, nullptr, 0, dev_weight, dev_linear_bias, dev_gamma, dev_beta, dev_out, out_stride,
                                rows, out_dim, eps, relu, shortcut, s);
     if (out_dim == 64)
         return launch_linear<64>(dev_input, input_stride, dev_weight, dev_linear_bias, dev_gamma, dev_beta, dev_out,
                                  out_stride, rows, eps, relu, shortcut, s);
     return launch_linear<32>(dev_input, input_stride, dev_weight, dev_linear_bias, dev_gamma, dev_beta, dev_out, out_stride,
                              rows, eps, relu, shortcut, s);
+}
+
+extern "C" int ultra_layer_linear_norm_relu_residual_two(const float *dev_input, int64_t input_stride, const float *dev_update,
+                                                         int64_t update_stride, const float *dev_weight,
+                                                         const float *dev_linear_bias, const float *dev_gamma,
+                                                         const float *dev_beta, float *dev_out, int64_t out_stride, int64_t rows,
+                                                         int32_t out_dim, float eps, int32_t relu, int32_t shortcut, void *stream) {
+    if (rows < 0 || (rows > 0 && (!dev_input || !dev_update || !dev_weight || !dev_out))) return ULTRA_RSPMM_ERR_ARG;
+    if ((dev_gamma == nullptr) != (dev_beta == nullptr)) return ULTRA_RSPMM_ERR_ARG;
+    if (out_dim != 32 && out_dim != 64) return ULTRA_RSPMM_ERR_RANGE;
+    if (input_stride < out_dim || input_stride % 4 || update_stride < out_dim || update_stride % 4 || out_stride < out_dim ||
+        out_stride % 4)
+        return ULTRA_RSPMM_ERR_ARG;
+    if (((uintptr_t)dev_input | (uintptr_t)dev_update | (uintptr_t)dev_out | (uintptr_t)dev_linear_bias | (uintptr_t)dev_gamma |
+         (uintptr_t)dev_beta | (uintptr_t)dev_weight) & 15)
+        return ULTRA_RSPMM_ERR_ARG;
+    if (rows == 0) return ULTRA_RSPMM_OK;
+    return layer_linear_tc(dev_input, input_stride, dev_update, update_stride, dev_weight, dev_linear_bias, dev_gamma, dev_beta,
+                           dev_out, out_stride, rows, out_dim, eps, relu, shortcut, (cudaStream_t)stream);
 }
 
 extern "C" int ultra_score_head_linear(const float *dev_input, int64_t input_stride, const float *dev_weight,

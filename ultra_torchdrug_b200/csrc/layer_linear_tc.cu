@@ -64,7 +64,8 @@ template <int N, int HI, int LO> struct Shape {
 
 template <int N, int HI, int LO>
 __global__ void __launch_bounds__(tc::kThreads, 1)
-linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, const float *__restrict__ A, long long lda,
+linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap a_map2,
+                                    int two_sources, const float *__restrict__ A, long long lda,
                                     const float *__restrict__ W,
                                     const float *__restrict__ linear_bias, const float *__restrict__ gamma,
                                     const float *__restrict__ beta, float *__restrict__ out, long long ldo, long long rows,
@@ -125,15 +126,19 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
         // ===== TMA producer (one thread) ================================================================================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&a_map) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&a_map2) : "memory");
             const long long total = my_tiles * kSlotsPerTile;
             for (long long it = 0; it < total; ++it) {
                 const int slot = (int)(it % S::kSlots);
                 const unsigned phase = (unsigned)((it / S::kSlots) & 1);
                 const long long tile = first + (it / kSlotsPerTile) * gridDim.x;
-                const int k0 = (int)(it % kSlotsPerTile) * tc::kSlotK;
+                // two sources: the K slots of the first half come from the layer input, those of the second from the update
+                const int q = (int)(it % kSlotsPerTile);
+                const bool second = two_sources && q >= kSlotsPerTile / 2;
+                const int k0 = (second ? q - kSlotsPerTile / 2 : q) * tc::kSlotK;
                 mbar_wait(empty_bar(slot), phase ^ 1u);                  // the MMAs that read this slot have completed
                 mbar_expect_tx(landed_bar(slot), tc::kSlotHalfBytes);
-                tma_load_2d(smem_base + S::kRingOffset + slot * tc::kSlotHalfBytes, &a_map, k0, (int)(tile * tc::kRows),
+                tma_load_2d(smem_base + S::kRingOffset + slot * tc::kSlotHalfBytes, second ? &a_map2 : &a_map, k0, (int)(tile * tc::kRows),
                             landed_bar(slot));                           // rows past the end are filled with zeros
             }
         }
@@ -292,7 +297,7 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
 }
 
 template <int N, int HI, int LO>
-int launch_linear_tc(const float *A, long long lda, const float *W, const float *linear_bias, const float *gamma,
+int launch_linear_tc(const float *A, long long lda, const float *A1, long long lda1, const float *W, const float *linear_bias, const float *gamma,
                      const float *beta, float *out, long long ldo, long long rows, float eps, int relu, int shortcut,
                      cudaStream_t stream) {
     using S = tc::Shape<N, HI, LO>;
@@ -302,11 +307,13 @@ int launch_linear_tc(const float *A, long long lda, const float *W, const float 
     ULTRA_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     ULTRA_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmemBytes));
     // the (rows, 2N) operand as a 2-D tensor: inner dimension = the 2N columns the Linear reads, rows lda floats apart
-    CUtensorMap map;
-    if (int status = encode_rows_map(&map, A, rows, S::K, lda)) return status;
+    CUtensorMap map, map2;
+    const bool two = A1 != nullptr;
+    if (int status = encode_rows_map(&map, A, rows, two ? S::K / 2 : S::K, lda)) return status;
+    if (int status = encode_rows_map(&map2, two ? A1 : A, rows, two ? S::K / 2 : S::K, two ? lda1 : lda)) return status;
     const long long n_tiles = (rows + tc::kRows - 1) / tc::kRows;
     const unsigned grid = (unsigned)(n_tiles < sm_count ? n_tiles : sm_count);
-    kernel<<<grid, tc::kThreads, S::kSmemBytes, stream>>>(map, A, lda, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu,
+    kernel<<<grid, tc::kThreads, S::kSmemBytes, stream>>>(map, map2, two ? 1 : 0, A, lda, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu,
                                                          shortcut);
     note_launch();
     ULTRA_CUDA_OK(cudaGetLastError());
@@ -316,12 +323,12 @@ int launch_linear_tc(const float *A, long long lda, const float *W, const float 
 }  // namespace
 
 // called by ultra_layer_linear_norm_relu_residual (layer_linear.cu) after its argument checks
-int layer_linear_tc(const float *A, long long lda, const float *W, const float *linear_bias, const float *gamma,
+int layer_linear_tc(const float *A, long long lda, const float *A1, long long lda1, const float *W, const float *linear_bias, const float *gamma,
                     const float *beta, float *out, long long ldo, long long rows, int out_dim, float eps, int relu,
                     int shortcut, cudaStream_t stream) {
     // ring shape: ULTRA_LINEAR_RING = "<hi slots><lo tiles>" (development knob; default 33)
     static const int ring = getenv("ULTRA_LINEAR_RING") ? atoi(getenv("ULTRA_LINEAR_RING")) : 33;
-#define ULTRA_TC(N, HI, LO) launch_linear_tc<N, HI, LO>(A, lda, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu, shortcut, stream)
+#define ULTRA_TC(N, HI, LO) launch_linear_tc<N, HI, LO>(A, lda, A1, lda1, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu, shortcut, stream)
     if (out_dim == 64) {
         switch (ring) {
             case 43: return ULTRA_TC(64, 4, 3);

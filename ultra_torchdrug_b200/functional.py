@@ -21,7 +21,7 @@ from . import _lib
 __all__ = ["generalized_rspmm", "GraphIndex", "graph_index", "clear_index_cache", "launch_count",
            "layer_norm_relu_residual", "layer_epilogue_supported", "rspmm_add_boundary", "RSPMMAddBoundaryFunction", "rspmm_add_one_hot", "RSPMMAddOneHotFunction", "rspmm_pna", "LayerEpilogueFunction",
            "layer_norm_relu_residual_into", "score_head", "fused_linear_supported",
-           "linear_norm_relu_residual_into", "score_head_linear", "attach_index", "combine_linear", "combine_linear_supported",
+           "linear_norm_relu_residual_into", "score_head_linear", "attach_index", "combine_linear", "combine_linear_supported", "linear_norm_relu_residual_two", "linear_planes_supported",
            "CombineLinearFunction"]
 
 _SUM_OPS = ("add", "min", "max")
@@ -154,7 +154,7 @@ class GraphIndex(object):
                 raise RuntimeError("Expect `%s` to be contiguous" % name)
         return dim
 
-    def forward(self, relation, input, sum="add", mul="mul", return_argidx=False, addend=None):
+    def forward(self, relation, input, sum="add", mul="mul", return_argidx=False, addend=None, out=None):
         self._check_dense(relation=relation, input=input)
         if sum not in _SUM_OPS or mul not in _MUL_OPS:
             raise ValueError("No generalized rspmm implementation found for summation `%s` and multiplication `%s`" % (sum, mul))
@@ -162,7 +162,12 @@ class GraphIndex(object):
         if addend is not None and (sum != "add" or addend.shape != (self.shape[0], dim) or addend.dtype != input.dtype
                                    or addend.device != input.device or not addend.is_contiguous()):
             raise RuntimeError("`addend` needs sum='add' and the shape / dtype / device of the output, contiguous")
-        output = torch.empty((self.shape[0], dim), dtype=input.dtype, device=input.device)
+        if out is not None:
+            if out.shape != (self.shape[0], dim) or out.dtype != input.dtype or out.device != input.device or not out.is_contiguous():
+                raise RuntimeError("`out` must be a contiguous (%d, %d) tensor of the operands' dtype and device" % (self.shape[0], dim))
+            output = out
+        else:
+            output = torch.empty((self.shape[0], dim), dtype=input.dtype, device=input.device)
         argidx = None
         if return_argidx and sum != "add":
             argidx = torch.empty((self.shape[0], dim), dtype=torch.int32, device=input.device)
@@ -445,6 +450,34 @@ def combine_linear(input, update, weight):
     if input.numel() == 0:
         return input.new_zeros(input.shape)
     return CombineLinearFunction.apply(input, update, weight)
+
+
+def linear_planes_supported(hidden, out_dim):
+    """Whether `linear_norm_relu_residual_two` serves this layer: float32 CUDA, 32 or 64 features, the tcgen05 + TMA kernel
+    in effect (`ultra_layer_linear_set_kernel(1)` or ULTRA_LAYER_PLANES=0 keep the interleaved (N, B, 2d) buffers)."""
+    return (fused_linear_supported(hidden, out_dim) and os.environ.get("ULTRA_LAYER_PLANES", "1") != "0"
+            and _lib.lib().ultra_layer_linear_get_kernel() == 2)
+
+
+def linear_norm_relu_residual_two(input, update, linear_weight, out, linear_bias=None, weight=None, bias=None, eps=1e-5,
+                                  relu=True, shortcut=True):
+    """`out = relu(layer_norm(cat([input, update], -1) @ linear_weight^T + linear_bias) * weight + bias) + input` with the two
+    halves of the Linear's input in two contiguous (..., d) tensors (inference; `ultra_layer_linear_norm_relu_residual_two`):
+    no `cat`, no interleaved buffer - the operator reads and writes plain matrices."""
+    out_dim = linear_weight.shape[0]
+    if not fused_linear_supported(input, out_dim) or input.shape != update.shape or input.shape[-1] != out_dim or \
+            not input.is_contiguous() or not update.is_contiguous() or linear_weight.shape != (out_dim, 2 * out_dim) or \
+            update.dtype != torch.float32 or update.device != input.device:
+        raise RuntimeError("linear_norm_relu_residual_two needs contiguous float32 CUDA (..., d) halves, d in {32, 64}")
+    if not _is_row_view(out, input.shape, input.device):
+        raise RuntimeError("`out` must be a float32 (..., %d) view whose rows are evenly spaced" % out_dim)
+    rows = input.numel() // max(out_dim, 1)
+    with torch.cuda.device(input.device):
+        _lib.check(_lib.lib().ultra_layer_linear_norm_relu_residual_two(
+            _ptr(input), out_dim, _ptr(update), out_dim, _ptr(linear_weight.contiguous()), _ptr(linear_bias), _ptr(weight),
+            _ptr(bias), ctypes.c_void_p(out.data_ptr()), out.stride(-2), rows, out_dim, float(eps), int(bool(relu)),
+            int(bool(shortcut)), _stream_handle()), "ultra_layer_linear_norm_relu_residual_two")
+    return out
 
 
 def score_head(z, query_bias, weight, bias=None):

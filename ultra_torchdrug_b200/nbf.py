@@ -234,6 +234,32 @@ def _run_layers_buffered(layers, graph, boundary, short_cut, one_hot=None):
     return buffers[len(layers) % 2]
 
 
+def _run_layers_planes(layers, graph, short_cut, one_hot):
+    """The inference layer loop on plain matrices: the hidden state ping-pongs between two (N, B, d) tensors, the operator
+    writes `update` into a third one (plain forward: no blocked layout, which costs 10-20 % on large graphs), the one-hot
+    boundary (reference model.py:106-109) is B row updates, and the fused Linear + LayerNorm + ReLU + short-cut kernel reads
+    its two K-halves from the two tensors through two TMA tensor maps.  Same arithmetic as `_run_layers_buffered`.
+    Returns the final hidden state (N, B, d)."""
+    node, query = one_hot
+    num_node, batch, width = graph.num_node, query.shape[-2], query.shape[-1]
+    column = torch.arange(batch, device=query.device)
+    hidden = [torch.empty(num_node, batch, width, dtype=query.dtype, device=query.device) for _ in range(2)]
+    update = torch.empty(num_node, batch, width, dtype=query.dtype, device=query.device)
+    hidden[0].zero_()
+    hidden[0][node, column] = query
+    index = rspmm.graph_index(graph.adjacency.transpose(0, 1))
+    for number, layer in enumerate(layers):
+        current, following = hidden[number % 2], hidden[(number + 1) % 2]
+        relation_input = layer.relation_input(graph, batch).contiguous()
+        index.forward(relation_input, current.view(num_node, -1), "add", MESSAGE_TO_MUL[layer.message_func],
+                      out=update.view(num_node, -1))
+        update[node, column] += query
+        rspmm.linear_norm_relu_residual_two(current, update, layer.linear.weight, following, layer.linear.bias,
+                                            layer.layer_norm.weight, layer.layer_norm.bias, layer.layer_norm.eps,
+                                            relu=layer.activation is not None, shortcut=short_cut)
+    return hidden[len(layers) % 2]
+
+
 def _run_layers(layers, graph, boundary, short_cut, one_hot=None):
     """`one_hot = (node_index, query)` must describe `boundary` (the caller derived both from the same query batch)."""
     if _buffered_layers_supported(layers, boundary):
@@ -304,20 +330,21 @@ class TransferNBFNet(nn.Module):
         keep[edge_index] = False
         return graph.edge_mask(keep)
 
-    def _split_head_supported(self, feature):
-        """2-layer ReLU scoring MLP over [hidden | query] on the inference fast path (see `_split_head`)."""
+    def _split_head_supported(self, feature, query):
+        """2-layer ReLU scoring MLP over [hidden | query] on the inference fast path (see `_split_head`); `feature` is the
+        (N, B, 2d) layer buffer or the (N, B, d) hidden state."""
         layers = self.mlp.layers
         return (len(layers) == 2 and layers[1].out_features == 1 and self.mlp.activation is F.relu
                 and not self.mlp.short_cut and self.mlp.batch_norms is None and self.mlp.dropout is None
-                and layers[0].in_features == feature.shape[-1] and layers[0].bias is not None
-                and rspmm.layer_epilogue_supported(feature, layers[0].out_features))
+                and layers[0].in_features == 2 * query.shape[-1] and feature.shape[-1] in (query.shape[-1], 2 * query.shape[-1])
+                and layers[0].bias is not None and rspmm.layer_epilogue_supported(feature, layers[0].out_features))
 
     def _split_head(self, feature, query):
         """Scores of every (node, query) pair from the (N, B, 2d) layer buffer without materialising cat([hidden, query])
         (reference model.py:141-143, 177-193): W1 [hidden | query] = W1h hidden + W1q query, the second term being one row
         per query.  The GEMM over all pairs halves to K = d; bias, ReLU and the 1-row second Linear are one fused pass."""
         num_node, batch, width = feature.shape
-        hidden_dim = width - query.shape[-1]
+        hidden_dim = query.shape[-1]                       # the first `hidden_dim` columns of `feature` are the hidden state
         first, second = self.mlp.layers
         query_bias = F.linear(query, first.weight[:, hidden_dim:], first.bias)
         if rspmm.fused_linear_supported(feature, hidden_dim) and first.out_features == 2 * hidden_dim:
@@ -331,9 +358,14 @@ class TransferNBFNet(nn.Module):
         with graph.graph():
             graph.query = query
         if not self.concat_hidden and _buffered_layers_supported(self.layers, query):
+            if rspmm.linear_planes_supported(query, query.shape[-1]):
+                hidden = _run_layers_planes(self.layers, graph, self.short_cut, (h_index, query))      # (N, B, d)
+                if self._split_head_supported(hidden, query):
+                    return hidden, query
+                return torch.cat([hidden, query.expand(graph.num_node, -1, -1)], dim=-1)
             # (N, B, 2d): hidden | free; the one-hot boundary (model.py:106-109) is applied in its sparse form
             feature = _run_layers_buffered(self.layers, graph, None, self.short_cut, one_hot=(h_index, query))
-            if self._split_head_supported(feature):
+            if self._split_head_supported(feature, query):
                 return feature, query                                                      # head reads the halves apart
             feature[..., query.shape[-1]:] = query                                         # cat([hidden, query]) in place
             return feature
@@ -425,6 +457,8 @@ class CustomNBFNetFull(nn.Module):
         with graph.graph():
             graph.query = query
         if _buffered_layers_supported(self.layers, query):
+            if rspmm.linear_planes_supported(query, query.shape[-1]):
+                return _run_layers_planes(self.layers, graph, self.short_cut, (h_index, query)).transpose(1, 0)
             hidden = _run_layers_buffered(self.layers, graph, None, self.short_cut, one_hot=(h_index, query))
             return hidden[..., :query.shape[-1]].transpose(1, 0)
         boundary = _one_hot_boundary(graph.num_node, h_index, query)
