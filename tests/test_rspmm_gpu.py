@@ -1015,3 +1015,59 @@ def test_combine_linear_forward_and_backward_have_fp32_accuracy(cuda, rows):
     assert shaped.shape == (rows, 1, 64) and torch.equal(shaped.view(rows, 64), out.detach())
     with pytest.raises(RuntimeError):
         F.combine_linear(input[:, :32], update[:, :32], weight)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("ULTRA_TEST_SEEDS", "24"))))
+def test_parity_randomized_specialised_kernels(cuda, seed):
+    """Seeded random shapes through the kernels that production selects only on particular graphs, all forced on here:
+    rows-in-shared-memory / pair kernels (few rows; pairs need <= 4 relation types and unit weights), the
+    destination-blocked grad_relation, the sub-warp rows kernel.  Sum aggregation (the only one they serve), both
+    message functions, ragged widths, duplicates, split rows."""
+    from ultra_torchdrug_b200 import functional as F, _lib
+    rng = np.random.default_rng(5000 + seed)
+    family = ("pairs", "staged", "blocked", "subwarp")[seed % 4]
+    n = int(rng.integers(2, 300)) if family in ("pairs", "staged") else int(rng.integers(2, 2500))
+    n_in = n if family == "pairs" else max(1, n - int(rng.integers(0, min(n, 20))))
+    n_rel = int(rng.integers(1, 5)) if family == "pairs" else int(rng.choice([1, 3, 4, 17, 60]))
+    nnz = int(rng.integers(0, 12 * n))
+    dim = int(rng.choice([4, 8, 36, 64, 100, 128, 192, 260]))
+    mul = ("mul", "add")[(seed // 4) % 2]
+    weights = "unit" if family == "pairs" or seed % 3 else "random"
+    duplicates = 0 if family == "pairs" else int(rng.integers(0, 30)) if nnz else 0
+    chunk = int(rng.choice([8, 64, 256]))
+    lib = _lib.lib()
+    lib.ultra_rspmm_set_tuning(chunk, 0, 0)
+    _lib.check(lib.ultra_rspmm_set_extensions(2 if family == "pairs" else 0, 2 if family == "blocked" else 0), "set_extensions")
+    _lib.check(lib.ultra_rspmm_set_staged(2 if family in ("pairs", "staged") else 0), "set_staged")
+    _lib.check(lib.ultra_rspmm_set_narrow(1 if family == "subwarp" else 0, int(rng.choice([2, 4]))), "set_narrow")
+    try:
+        indices, values = util.random_coo(n, n_in, n_rel, nnz, seed, duplicates, weights, bool(seed % 2))
+        if family == "pairs" and indices.shape[1]:          # pair lists need coalesced unit weights: drop duplicate triples
+            indices = np.unique(indices, axis=1)
+            values = np.ones(indices.shape[1], dtype=np.float32)
+        shape = (n, n_in, n_rel)
+        relation, input, grad = util.random_dense(n_rel, dim, seed + 1), util.random_dense(n_in, dim, seed + 2), util.random_dense(n, dim, seed + 3)
+        index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), shape)
+        d_rel, d_in, d_grad = (torch.from_numpy(x).to(cuda) for x in (relation, input, grad))
+        out = index.forward(d_rel, d_in, "add", mul)
+        served = _lib.pass_info(_lib.PASS_FORWARD)["kernel_name"] if indices.shape[1] and dim else None
+        g_rel, g_in = index.backward(d_rel, d_in, out, d_grad, "add", mul)
+        if indices.shape[1]:
+            expected = {"pairs": ("pairs_in_smem",), "staged": ("rows_in_smem",), "blocked": ("seg_reduce",), "subwarp": ("subwarp_rows",)}
+            if dim % 4 == 0:
+                assert served in expected[family], (family, served)
+                if family == "blocked":
+                    assert _lib.pass_info(_lib.PASS_GRAD_RELATION)["kernel_name"] == "dst_blocked"
+        exp, _ = util.oracle_forward(indices, values, shape, relation, input, "add", mul, dtype=np.float64)
+        scale, _ = util.oracle_forward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), "add", mul, dtype=np.float64)
+        _assert_sum_close(out.cpu().numpy(), exp, scale, "%s forward" % family)
+        e_rel, e_in = util.oracle_backward(indices, values, shape, relation, input, None, grad, "add", mul, dtype=np.float64)
+        s_rel, s_in = util.oracle_backward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), None, np.abs(grad),
+                                           "add", mul, dtype=np.float64)
+        _assert_sum_close(g_rel.cpu().numpy(), e_rel, s_rel, "%s grad_relation" % family)
+        _assert_sum_close(g_in.cpu().numpy(), e_in, s_in, "%s grad_input" % family)
+    finally:
+        lib.ultra_rspmm_set_tuning(256, 0, 0)
+        _lib.check(lib.ultra_rspmm_set_extensions(1, 1), "set_extensions")
+        _lib.check(lib.ultra_rspmm_set_staged(1), "set_staged")
+        _lib.check(lib.ultra_rspmm_set_narrow(0, 0), "set_narrow")
