@@ -441,17 +441,16 @@ def c3_finetune(device, rank, world, steps, warmup=2):
     generator = torch.Generator().manual_seed(7)                # the same global batches on every rank
     batches = [triples[torch.randint(num_triple, (BATCH,), generator=generator)].to(device) for _ in range(warmup + steps)]
     torch.manual_seed(4096 + rank)                              # negatives differ per rank
-    launches = F.launch_count()
-    step(batches[0])                                            # one eager step: counts the library's launches per step
-    launches_per_step = F.launch_count() - launches
-    mode = "eager"
+    # No eager backward may run on the default stream before the capture: autograd would bind the parameters' AccumulateGrad
+    # nodes to that stream and the capture (which warms up on a side stream) would be invalidated.
+    mode, launches = "eager", F.launch_count()
     if os.environ.get("ULTRA_BENCH_FINETUNE_GRAPH", "1") != "0":
-        try:
-            step.capture(BATCH)                                 # the whole step (incl. the NCCL all-reduce) as one CUDA graph
-            mode = "CUDA graph replay"
-        except Exception as error:                              # noqa: BLE001 - fall back to eager launches
-            step._graph = None
-            mode = "eager (capture failed: %s)" % type(error).__name__
+        step.capture(BATCH)                                     # the whole step (incl. the NCCL all-reduce) as one CUDA graph
+        mode = "CUDA graph replay"
+        launches_per_step = (F.launch_count() - launches) / 4   # 3 warm-up steps + the captured one
+    else:
+        step(batches[0])
+        launches_per_step = F.launch_count() - launches
     for batch in batches[:warmup]:
         step(batch)
     torch.cuda.synchronize()
@@ -572,7 +571,13 @@ def run_gpu_arm(args):
     barrier()
     c4 = c4_predict(device, rank, world, extra_steps)
     barrier()
-    c3 = c3_finetune(device, rank, world, extra_steps)
+    try:
+        c3 = c3_finetune(device, rank, world, extra_steps)
+    except Exception as error:                                  # noqa: BLE001 - never lose the headline line to an extra leg
+        if world > 1:
+            raise                                               # ranks must not diverge around a collective
+        sys.stderr.write("c3_finetune leg failed: %r\n" % (error,))
+        c3 = {"ms_per_step": float("nan"), "gradient_bytes": 0, "error": repr(error)}
 
     if world > 1:
         both = torch.tensor([elapsed_ms, e2e_ms, queries["ms_per_batch"], copy_ms, c4["ms_per_global_batch"], c3["ms_per_step"]],
