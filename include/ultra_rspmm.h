@@ -347,6 +347,10 @@ int ultra_layer_rows_gemm_weight(const float *dev_dx, int64_t ld_dx, const float
 /* which implementation serves ultra_layer_linear_norm_relu_residual: 0 = library default, 1 = mma.sync, 2 = tcgen05 */
 int ultra_layer_linear_set_kernel(int32_t kind);
 int ultra_layer_linear_get_kernel(void);   /* the implementation in effect: 1 or 2 */
+/* development: when set (8 int64 per CTA, >= 8 * SM count), the tcgen05 kernel records the cycles each warp role spent
+ * waiting on its barriers: [tma/empty, split/landed, split/lo_empty, mma/tmem_empty, mma/full, epilogue/tmem_full, total
+ * cycles, tiles].  NULL switches it off (default). */
+int ultra_layer_linear_set_debug(long long *dev_buffer);
 
 /* ---- scoring head (reference model.py:177-193, the 2-layer MLP over [hidden | query]) ---- */
 /* score[r] = bias[0] + sum_c weight[c] * relu(z[r, c] + query_bias[r % batch, c]) over `rows` rows of `dim` fp32 features

@@ -112,6 +112,7 @@ SYMBOLS = {
                                                                  c_int32, c_int32, c_void_p]),
     "ultra_layer_linear_set_kernel": (ctypes.c_int, [c_int32]),
     "ultra_layer_linear_get_kernel": (ctypes.c_int, []),
+    "ultra_layer_linear_set_debug": (ctypes.c_int, [c_void_p]),
     "ultra_layer_rows_gemm": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                              c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p]),
     "ultra_layer_rows_gemm_weight_bytes": (ctypes.c_int, [ctypes.POINTER(c_size_t)]),

@@ -25,6 +25,8 @@
 
 namespace ultra {
 
+long long *g_linear_debug = nullptr;   // development: per-CTA barrier wait cycles (ultra_layer_linear_set_debug)
+
 namespace {
 
 using namespace tcx;
@@ -69,8 +71,22 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
                                     const float *__restrict__ W,
                                     const float *__restrict__ linear_bias, const float *__restrict__ gamma,
                                     const float *__restrict__ beta, float *__restrict__ out, long long ldo, long long rows,
-                                    float eps, int relu, int shortcut) {
+                                    float eps, int relu, int shortcut, long long *debug) {
     using S = tc::Shape<N, HI, LO>;
+    // debug (development): cycles each role spent waiting on its barriers, per CTA: [tma/empty, split/landed, split/lo_empty,
+    // mma/tmem_empty, mma/full, epilogue/tmem_full, total]
+    long long waited = 0, waited2 = 0;
+    const long long kernel_start = debug ? clock64() : 0;
+#define ULTRA_TIMED_WAIT(counter, ...)                 \
+    do {                                               \
+        if (debug) {                                   \
+            const long long t0_ = clock64();           \
+            __VA_ARGS__;                               \
+            counter += clock64() - t0_;                \
+        } else {                                       \
+            __VA_ARGS__;                               \
+        }                                              \
+    } while (0)
     constexpr int K = S::K, kSlotsPerTile = S::kSlotsPerTile;
     extern __shared__ __align__(1024) unsigned char smem[];
     const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
@@ -136,7 +152,7 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
                 const int q = (int)(it % kSlotsPerTile);
                 const bool second = two_sources && q >= kSlotsPerTile / 2;
                 const int k0 = (second ? q - kSlotsPerTile / 2 : q) * tc::kSlotK;
-                mbar_wait(empty_bar(slot), phase ^ 1u);                  // the MMAs that read this slot have completed
+                ULTRA_TIMED_WAIT(waited, mbar_wait(empty_bar(slot), phase ^ 1u));   // the MMAs that read this slot have completed
                 mbar_expect_tx(landed_bar(slot), tc::kSlotHalfBytes);
                 tma_load_2d(smem_base + S::kRingOffset + slot * tc::kSlotHalfBytes, second ? &a_map2 : &a_map, k0, (int)(tile * tc::kRows),
                             landed_bar(slot));                           // rows past the end are filled with zeros
@@ -151,8 +167,8 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
             const unsigned phase = (unsigned)((it / S::kSlots) & 1);
             const int lo_slot = (int)(it % S::kLoSlots);
             const unsigned lo_phase = (unsigned)((it / S::kLoSlots) & 1);
-            mbar_wait(landed_bar(slot), phase);
-            mbar_wait(lo_empty_bar(lo_slot), lo_phase ^ 1u);              // the MMAs that read this lo tile have completed
+            ULTRA_TIMED_WAIT(waited, mbar_wait(landed_bar(slot), phase));
+            ULTRA_TIMED_WAIT(waited2, mbar_wait(lo_empty_bar(lo_slot), lo_phase ^ 1u));   // the MMAs that read this lo tile have completed
             unsigned char *hi_at = smem + S::kRingOffset + slot * tc::kSlotHalfBytes;
             unsigned char *lo_at = smem + S::kLoOffset + lo_slot * tc::kSlotHalfBytes;
             constexpr int kChunksPerThread = tc::kSlotHalfBytes / 16 / (32 * tc::kSplitWarps);
@@ -181,13 +197,13 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
             for (long long t = 0; t < my_tiles; ++t) {
                 const int stage = (int)(t & 1);
                 const unsigned accum_phase = (unsigned)((t >> 1) & 1);
-                mbar_wait(tmem_empty_bar(stage), accum_phase ^ 1u);
+                ULTRA_TIMED_WAIT(waited, mbar_wait(tmem_empty_bar(stage), accum_phase ^ 1u));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned tmem_d = tmem_base + (unsigned)(stage * N);
                 for (int q = 0; q < kSlotsPerTile; ++q, ++it) {
                     const int slot = (int)(it % S::kSlots);
                     const unsigned phase = (unsigned)((it / S::kSlots) & 1);
-                    mbar_wait(full_bar(slot), phase);
+                    ULTRA_TIMED_WAIT(waited2, mbar_wait(full_bar(slot), phase));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const int lo_slot = (int)(it % S::kLoSlots);
                     const unsigned a_hi = smem_base + S::kRingOffset + slot * tc::kSlotHalfBytes;
@@ -229,7 +245,7 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
             const int stage = (int)(t & 1);
             const unsigned accum_phase = (unsigned)((t >> 1) & 1);
             const long long row0 = (first + t * gridDim.x) * tc::kRows + 32 * quadrant;
-            mbar_wait(tmem_full_bar(stage), accum_phase);
+            ULTRA_TIMED_WAIT(waited, mbar_wait(tmem_full_bar(stage), accum_phase));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float v[N];
 #pragma unroll
@@ -287,6 +303,14 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
         }
     }
 
+    if (debug) {
+        long long *mine = debug + 8 * (long long)blockIdx.x;
+        if (warp == tc::kTmaWarp && lane == 0) mine[0] = waited;
+        if (warp == tc::kSplitWarp0 && lane == 0) { mine[1] = waited; mine[2] = waited2; }
+        if (warp == tc::kMmaWarp && lane == 0) { mine[3] = waited; mine[4] = waited2; }
+        if (warp == tc::kEpilogueWarp0 && lane == 0) { mine[5] = waited; mine[6] = clock64() - kernel_start; mine[7] = my_tiles; }
+    }
+#undef ULTRA_TIMED_WAIT
     // ---- teardown -------------------------------------------------------------------------------------------------------
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -314,7 +338,7 @@ int launch_linear_tc(const float *A, long long lda, const float *A1, long long l
     const long long n_tiles = (rows + tc::kRows - 1) / tc::kRows;
     const unsigned grid = (unsigned)(n_tiles < sm_count ? n_tiles : sm_count);
     kernel<<<grid, tc::kThreads, S::kSmemBytes, stream>>>(map, map2, two ? 1 : 0, A, lda, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu,
-                                                         shortcut);
+                                                         shortcut, g_linear_debug);
     note_launch();
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;
@@ -343,3 +367,8 @@ int layer_linear_tc(const float *A, long long lda, const float *A1, long long ld
 }
 
 }  // namespace ultra
+
+extern "C" int ultra_layer_linear_set_debug(long long *dev_buffer) {
+    ultra::g_linear_debug = dev_buffer;    // 8 int64 per CTA (at least 8 * SM count), or NULL to switch the instrumentation off
+    return ULTRA_RSPMM_OK;
+}
