@@ -63,6 +63,7 @@ def main():
     parser.add_argument("--variant", type=int, default=0, help="0 auto, 1 no L2 eviction hints, 2 hints always")
     parser.add_argument("--relgraph", action="store_true", help="dense 4-relation graph over R' nodes instead")
     parser.add_argument("--staged", type=int, default=-1, help="rows-in-shared-memory kernel: 0 off, 1 auto, 2 always")
+    parser.add_argument("--blocked", type=int, default=-1, help="destination-blocked grad_relation: 0 never, 1 auto, 2 always")
     parser.add_argument("--uniform", default=None, help="E:N:R - uniform random graph (BASELINE configs[4] sweep shapes)")
     parser.add_argument("--dim", type=int, default=0, help="feature width (overrides --batch * 64)")
     args = parser.parse_args()
@@ -78,6 +79,9 @@ def main():
     if args.staged >= 0:
         from ultra_torchdrug_b200 import _lib
         _lib.lib().ultra_rspmm_set_staged(args.staged)
+    if args.blocked >= 0:
+        from ultra_torchdrug_b200 import _lib
+        _lib.lib().ultra_rspmm_set_extensions(1, args.blocked)
     if args.uniform:
         e_raw, n, r = (int(v) for v in args.uniform.split(":"))
         generator = torch.Generator().manual_seed(1024)

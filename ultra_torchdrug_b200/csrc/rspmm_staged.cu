@@ -344,6 +344,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) dst_blocked_kernel(const Blo
     const unsigned row_bytes = (unsigned)(a.dim * sizeof(float));
     const int n_item = a.n_block * a.n_slab;
     const Ids *ids = reinterpret_cast<const Ids *>(PACKED ? (const void *)a.packed : (const void *)a.edge);
+    // the gathered slab of X (n_in x 256 B, re-read once per edge) should stay in L2; grad_output rows, edge ids and partial
+    // rows pass through once (16.8 M edges: 47.6 -> 45.0 ms; C4: 4.36 -> 4.02 ms)
+    const unsigned long long keep_policy = policy_evict_last(), once_policy = policy_evict_first();
     for (;;) {
         if (threadIdx.x == 0) s_item = (int)atomicAdd(a.counter, 1u);
         __syncthreads();
@@ -355,7 +358,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) dst_blocked_kernel(const Blo
         for (int i = threadIdx.x; i < rows * (kStagedSlab / 4); i += kThreads) {
             const long long c = (long long)slab * kStagedSlab + (i & 15) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < a.dim) v = __ldg(reinterpret_cast<const float4 *>(a.G + (long long)(first_row + (i >> 4)) * a.dim + c));
+            if (c < a.dim) {
+                Vec<float, 4> g;
+                gather_load_keep(a.G + (long long)(first_row + (i >> 4)) * a.dim + c, g, once_policy);
+                v = make_float4(g.v[0], g.v[1], g.v[2], g.v[3]);
+            }
             s_rows[i] = v;
         }
         __syncthreads();
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) dst_blocked_kernel(const Blo
                 float4 x = make_float4(1.f, 1.f, 1.f, 1.f);
                 if (MSG == MSG_MUL) {
                     Vec<float, 4> v;
-                    gather_load(reinterpret_cast<const float *>(X + (unsigned long long)(unsigned)src * row_bytes), v);
+                    gather_load_keep(reinterpret_cast<const float *>(X + (unsigned long long)(unsigned)src * row_bytes), v, keep_policy);
                     x = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
                 }
                 const float gv[4] = {g.x, g.y, g.z, g.w}, xv[4] = {x.x, x.y, x.z, x.w};
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) dst_blocked_kernel(const Blo
             Ids ahead = Ids();
             float ahead_w = 1.f;
             if (begin + lane < end) {
-                ahead = __ldg(ids + begin + lane);
+                ahead = edge_load_once(ids + begin + lane, once_policy);
                 if (a.w) ahead_w = __ldg(a.w + begin + lane);
             }
             for (int base = begin; base < end; base += 32) {
@@ -393,7 +400,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) dst_blocked_kernel(const Blo
                 s_w[warp][lane] = ahead_w;
                 __syncwarp();
                 if (base + 32 + lane < end) {
-                    ahead = __ldg(ids + base + 32 + lane);
+                    ahead = edge_load_once(ids + base + 32 + lane, once_policy);
                     if (a.w) ahead_w = __ldg(a.w + base + 32 + lane);
                 }
                 int u = 0;
@@ -409,7 +416,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) dst_blocked_kernel(const Blo
                         w[q] = s_w[warp][mine + q];
                         const int dst = PACKED ? (int)(id_bits_of(e[q]) & low) : id_first(e[q]);
                         const int src = PACKED ? (int)(id_bits_of(e[q]) >> shift) : id_second(e[q]);
-                        if (MSG == MSG_MUL) gather_load(reinterpret_cast<const float *>(X + (unsigned long long)(unsigned)src * row_bytes), x[q]);
+                        if (MSG == MSG_MUL) gather_load_keep(reinterpret_cast<const float *>(X + (unsigned long long)(unsigned)src * row_bytes), x[q], keep_policy);
                         g[q] = s_rows[(dst - first_row) * (kStagedSlab / 4) + l16];
                     }
 #pragma unroll
@@ -428,7 +435,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) dst_blocked_kernel(const Blo
             for (int v = 0; v < 4; ++v) acc[v] += __shfl_xor_sync(kFullMask, acc[v], 16);
             if (half == 0 && active) {
                 float *p = a.partial + ((long long)k * a.n_block + b) * a.dim + col;
-                *reinterpret_cast<float4 *>(p) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                __stcs(reinterpret_cast<float4 *>(p), make_float4(acc[0], acc[1], acc[2], acc[3]));
             }
         }
         __syncthreads();
