@@ -9,8 +9,8 @@
 //
 // rows_gemm_tc_kernel is the fused-Linear kernel of layer_linear_tc.cu with a plain epilogue: persistent CTAs, one per SM;
 // warp 0 = TMA producer (16 KB SWIZZLE_128B boxes of 32 columns x 128 rows into a ring of 3 slots, from one or two tensor
-// maps), warps 2-5 = in-place hi / lo split, warp 1 = MMA issuer (tcgen05.mma.kind::tf32, M 128, N 64 or 128, two
-// accumulator stages in TMEM), warps 6-9 = epilogue (tcgen05.ld 64 columns at a time, staged through warp-private shared
+// maps), warps 2-5 = hi / lo split into A slots in tensor memory (tcgen05.st), warp 1 = MMA issuer (tcgen05.mma.kind::tf32,
+// A from tensor memory, M 128, N 64 or 128, two accumulator stages in TMEM), warps 6-9 = epilogue (tcgen05.ld 64 columns at a time, staged through warp-private shared
 // memory, coalesced 16-byte stores).
 //
 // weight_grad_kernel reduces over millions of rows into a 64 x 128 result: persistent CTAs walk 64-row tiles (cp.async
@@ -28,11 +28,12 @@ using namespace tcx;
 namespace gm {
 constexpr int kRows = 128;
 constexpr int kSlotK = 32;
-constexpr int kSlots = 3;
+constexpr int kSlots = 3;                               // landing slots of the TMA ring (16 KB each)
+constexpr int kASlots = 2;                              // A slots in tensor memory (64 columns each: hi | lo), see layer_linear_tc.cu
 constexpr int kTmaWarp = 0, kMmaWarp = 1, kSplitWarp0 = 2, kSplitWarps = 4, kEpilogueWarp0 = 6, kEpilogueWarps = 4;
 constexpr int kThreads = 32 * (kEpilogueWarp0 + kEpilogueWarps);
 constexpr int kSlotHalfBytes = kRows * kSlotK * 4;
-constexpr int kBarriers = 3 * kSlots + 4;
+constexpr int kBarriers = 2 * kSlots + 2 * kASlots + 4;
 constexpr int kHalf = 64;                               // epilogue works on 64 output columns at a time
 constexpr int kStageStride = kHalf + 4;
 
@@ -41,10 +42,12 @@ template <int N, int K> struct Shape {
     static constexpr int kWeightHalfBytes = N * K * 4;
     static constexpr int kCoreBytesW = N * 16;
     static constexpr int kRingOffset = (2 * kWeightHalfBytes + 1023) / 1024 * 1024;
-    static constexpr int kStagingOffset = kRingOffset + kSlots * 2 * kSlotHalfBytes;
+    static constexpr int kStagingOffset = kRingOffset + kSlots * kSlotHalfBytes;
     static constexpr int kBarrierOffset = kStagingOffset + kEpilogueWarps * 32 * kStageStride * 4;
     static constexpr int kSmemBytes = kBarrierOffset + kBarriers * 8 + 16;
-    static constexpr int kTmemColumns = 2 * N;          // two accumulator stages: 128 or 256 columns
+    static constexpr int kOperandColumn0 = 2 * N;       // two accumulator stages (128 or 256 columns), then the A slots
+    static constexpr int kTmemColumns = 512;
+    static_assert(2 * N + 64 * kASlots <= 512, "accumulators and A slots exceed tensor memory");
     static constexpr unsigned kInstr = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(kRows >> 4) << 24);
     static_assert(kSmemBytes <= 227 * 1024, "does not fit shared memory");
 };
@@ -66,19 +69,24 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
     extern __shared__ __align__(1024) unsigned char smem[];
     const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
     const unsigned bar_base = smem_base + S::kBarrierOffset;
-    auto full_bar = [&](int slot) { return bar_base + 8u * slot; };
+    // landed / empty per landing slot (empty = the split warps have read it); full / a_free per tensor-memory A slot
+    auto landed_bar = [&](int slot) { return bar_base + 8u * slot; };
     auto empty_bar = [&](int slot) { return bar_base + 8u * (gm::kSlots + slot); };
-    auto landed_bar = [&](int slot) { return bar_base + 8u * (2 * gm::kSlots + slot); };
-    auto tmem_full_bar = [&](int stage) { return bar_base + 8u * (3 * gm::kSlots + stage); };
-    auto tmem_empty_bar = [&](int stage) { return bar_base + 8u * (3 * gm::kSlots + 2 + stage); };
+    auto full_bar = [&](int slot) { return bar_base + 8u * (2 * gm::kSlots + slot); };
+    auto a_free_bar = [&](int slot) { return bar_base + 8u * (2 * gm::kSlots + gm::kASlots + slot); };
+    auto tmem_full_bar = [&](int stage) { return bar_base + 8u * (2 * gm::kSlots + 2 * gm::kASlots + stage); };
+    auto tmem_empty_bar = [&](int stage) { return bar_base + 8u * (2 * gm::kSlots + 2 * gm::kASlots + 2 + stage); };
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + S::kBarrierOffset + gm::kBarriers * 8);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
         for (int s = 0; s < gm::kSlots; ++s) {
-            mbar_init(full_bar(s), gm::kSplitWarps);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), gm::kSplitWarps);
             mbar_init(landed_bar(s), 1);
+        }
+        for (int s = 0; s < gm::kASlots; ++s) {
+            mbar_init(full_bar(s), gm::kSplitWarps);
+            mbar_init(a_free_bar(s), 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tmem_full_bar(s), 1);
@@ -125,34 +133,43 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
                 const int k0 = (second ? q - kSlotsPerTile / 2 : q) * gm::kSlotK;
                 mbar_wait(empty_bar(slot), phase ^ 1u);
                 mbar_expect_tx(landed_bar(slot), gm::kSlotHalfBytes);
-                tma_load_2d(smem_base + S::kRingOffset + slot * 2 * gm::kSlotHalfBytes, second ? &map1 : &map0, k0,
+                tma_load_2d(smem_base + S::kRingOffset + slot * gm::kSlotHalfBytes, second ? &map1 : &map0, k0,
                             (int)(tile * gm::kRows), landed_bar(slot));
             }
         }
     } else if (warp >= gm::kSplitWarp0 && warp < gm::kEpilogueWarp0) {
-        const int t = tid - 32 * gm::kSplitWarp0;
+        // one thread = one row of a landed slot (the tensor-memory lane its warp may write): 8 conflict-free 16-byte reads
+        // of the swizzled row, hi = tf32(x) and lo = tf32(x - hi) to the A slot's columns with tcgen05.st
+        const int quadrant = warp & 3, r = 32 * quadrant + lane;
         for (long long it = 0; it < total; ++it) {
-            const int slot = (int)(it % gm::kSlots);
-            const unsigned phase = (unsigned)((it / gm::kSlots) & 1);
-            mbar_wait(landed_bar(slot), phase);
-            unsigned char *hi_at = smem + S::kRingOffset + slot * 2 * gm::kSlotHalfBytes;
-            constexpr int kChunksPerThread = gm::kSlotHalfBytes / 16 / (32 * gm::kSplitWarps);
-            float4 x[kChunksPerThread];
+            const int slot = (int)(it % gm::kSlots), a_slot = (int)(it % gm::kASlots);
+            mbar_wait(landed_bar(slot), (unsigned)((it / gm::kSlots) & 1));
+            mbar_wait(a_free_bar(a_slot), (unsigned)((it / gm::kASlots) & 1) ^ 1u);   // the MMAs that read this A slot have completed
+            const unsigned char *at = smem + S::kRingOffset + slot * gm::kSlotHalfBytes + r * 128;
+            float4 x[8];
 #pragma unroll
-            for (int q = 0; q < kChunksPerThread; ++q)
-                x[q] = *reinterpret_cast<const float4 *>(hi_at + 16 * (t + q * 32 * gm::kSplitWarps));
+            for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4 *>(at + ((c ^ (r & 7)) << 4));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned taddr = tmem_base + ((unsigned)(32 * quadrant) << 16) + (unsigned)(S::kOperandColumn0 + 64 * a_slot);
 #pragma unroll
-            for (int q = 0; q < kChunksPerThread; ++q) {
-                const float4 hi = make_float4(tc_tf32(x[q].x), tc_tf32(x[q].y), tc_tf32(x[q].z), tc_tf32(x[q].w));
-                const float4 lo = make_float4(tc_tf32(x[q].x - hi.x), tc_tf32(x[q].y - hi.y), tc_tf32(x[q].z - hi.z),
-                                              tc_tf32(x[q].w - hi.w));
-                unsigned char *at = hi_at + 16 * (t + q * 32 * gm::kSplitWarps);
-                *reinterpret_cast<float4 *>(at) = hi;
-                *reinterpret_cast<float4 *>(at + gm::kSlotHalfBytes) = lo;
+            for (int h = 0; h < 2; ++h) {
+                float hi[16], lo[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 v = x[4 * h + c];
+                    hi[4 * c] = tc_tf32(v.x); hi[4 * c + 1] = tc_tf32(v.y); hi[4 * c + 2] = tc_tf32(v.z); hi[4 * c + 3] = tc_tf32(v.w);
+                    lo[4 * c] = tc_tf32(v.x - hi[4 * c]); lo[4 * c + 1] = tc_tf32(v.y - hi[4 * c + 1]);
+                    lo[4 * c + 2] = tc_tf32(v.z - hi[4 * c + 2]); lo[4 * c + 3] = tc_tf32(v.w - hi[4 * c + 3]);
+                }
+                tmem_store16(taddr + 16 * h, hi);
+                tmem_store16(taddr + 32 + 16 * h, lo);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(slot));
+            if (lane == 0) mbar_arrive(empty_bar(slot));                 // the slot's bytes are in registers: TMA may refill it
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(a_slot));
         }
     } else if (warp == gm::kMmaWarp) {
         if (lane == 0) {
@@ -165,23 +182,20 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned tmem_d = tmem_base + (unsigned)(stage * N);
                 for (int q = 0; q < kSlotsPerTile; ++q, ++it) {
-                    const int slot = (int)(it % gm::kSlots);
-                    const unsigned phase = (unsigned)((it / gm::kSlots) & 1);
-                    mbar_wait(full_bar(slot), phase);
+                    const int a_slot = (int)(it % gm::kASlots);
+                    mbar_wait(full_bar(a_slot), (unsigned)((it / gm::kASlots) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const unsigned a_hi = smem_base + S::kRingOffset + slot * 2 * gm::kSlotHalfBytes;
-                    const unsigned a_lo = a_hi + gm::kSlotHalfBytes;
+                    const unsigned a_hi = tmem_base + (unsigned)(S::kOperandColumn0 + 64 * a_slot), a_lo = a_hi + 32u;
 #pragma unroll
                     for (int ks = 0; ks < gm::kSlotK / 8; ++ks) {
                         const int kg = q * (gm::kSlotK / 8) + ks;
-                        const unsigned long long da_hi = umma_desc_sw128(a_hi + ks * 32), da_lo = umma_desc_sw128(a_lo + ks * 32);
                         const unsigned long long db_hi = umma_desc(w_hi + kg * 2 * S::kCoreBytesW, S::kCoreBytesW, 128);
                         const unsigned long long db_lo = umma_desc(w_lo + kg * 2 * S::kCoreBytesW, S::kCoreBytesW, 128);
-                        umma_tf32(tmem_d, da_lo, db_hi, S::kInstr, kg > 0 ? 1u : 0u);
-                        umma_tf32(tmem_d, da_hi, db_lo, S::kInstr, 1u);
-                        umma_tf32(tmem_d, da_hi, db_hi, S::kInstr, 1u);
+                        umma_tf32_ts(tmem_d, a_lo + 8u * ks, db_hi, S::kInstr, kg > 0 ? 1u : 0u);
+                        umma_tf32_ts(tmem_d, a_hi + 8u * ks, db_lo, S::kInstr, 1u);
+                        umma_tf32_ts(tmem_d, a_hi + 8u * ks, db_hi, S::kInstr, 1u);
                     }
-                    umma_commit(empty_bar(slot));
+                    umma_commit(a_free_bar(a_slot));                     // the A slot may be overwritten once these MMAs have read it
                 }
                 umma_commit(tmem_full_bar(stage));
             }
