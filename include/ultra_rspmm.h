@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ULTRA_RSPMM_ABI_VERSION 5
+#define ULTRA_RSPMM_ABI_VERSION 6
 
 /* status codes (0 = ok).  For ULTRA_RSPMM_ERR_CUDA the cudaError_t is kept per thread, see
  * ultra_rspmm_last_cuda_error(). */
@@ -254,6 +254,14 @@ int ultra_rspmm_backward(const ultra_rspmm_index_t *index, const void *dev_relat
                          const void *dev_output, const void *dev_grad_output, void *dev_grad_relation,
                          void *dev_grad_input, int64_t dim, int32_t dtype, int32_t sum_op, int32_t mul_op,
                          void *workspace, size_t workspace_bytes, void *stream);
+/* The same for sum_op = add with  grad_input = (operator's gradient) + dev_grad_input_addend  ((n_in, dim), not aliasing
+ * dev_grad_input; NULL = plain backward): the layer input of an NBFNet layer also feeds the Linear of `combine` and the
+ * short-cut (reference layer.py:386-392, model.py:126-127), and their gradients arrive here instead of in two more passes
+ * over (N, D) tensors (the framework's gradient accumulation). */
+int ultra_rspmm_backward_addend(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
+                                const void *dev_grad_output, void *dev_grad_relation, void *dev_grad_input,
+                                const void *dev_grad_input_addend, int64_t dim, int32_t dtype, int32_t mul_op,
+                                void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- host-buffer convenience layer (what a non-torch host binds; used for end-to-end timing) --- */
 /* Owns device copies of one graph's index and of the dense operands; every call below takes HOST

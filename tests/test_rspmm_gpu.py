@@ -1017,6 +1017,60 @@ def test_combine_linear_forward_and_backward_have_fp32_accuracy(cuda, rows):
         F.combine_linear(input[:, :32], update[:, :32], weight)
 
 
+@pytest.mark.parametrize("nodes,batch,relations,mul,shortcut", [(300, 3, 7, "mul", True), (1500, 2, 40, "add", True),
+                                                                  (90, 5, 4, "mul", False)])
+def test_single_node_layer_equals_three_node_layer(cuda, nodes, batch, relations, mul, shortcut):
+    """`nbf_layer` (operator + Linear + LayerNorm/ReLU/short-cut as ONE autograd node whose backward folds the three
+    gradients of the layer input into the kernels) against the composition of the three separate nodes
+    (`rspmm_add_one_hot`, `combine_linear`, `layer_norm_relu_residual`): the forward runs the same kernels (bit-equal), the
+    gradients differ only in the order the three contributions to d input are added; and `backward(input_addend=...)`
+    against backward + add."""
+    from ultra_torchdrug_b200 import functional as F, synthetic
+    generator = torch.Generator().manual_seed(nodes)
+    edges = torch.stack([torch.randint(nodes, (nodes * 6,), generator=generator), torch.randint(nodes, (nodes * 6,), generator=generator),
+                         torch.randint(relations, (nodes * 6,), generator=generator)], dim=1)
+    sparse = synthetic.operator_operand(edges, nodes, relations, cuda)
+    device_generator = torch.Generator(device=cuda).manual_seed(batch)
+    leaf = lambda *shape, scale=1.0: (torch.randn(*shape, device=cuda, generator=device_generator) * scale).requires_grad_()
+    x, relation, query = leaf(nodes, batch, 64), leaf(relations, batch * 64), leaf(batch, 64)
+    weight, linear_bias, gamma, beta = leaf(64, 128, scale=0.125), leaf(64), leaf(64), leaf(64)
+    node_index = torch.randint(nodes, (batch,), device=cuda, generator=device_generator)
+    grad = torch.randn(nodes, batch, 64, device=cuda, generator=device_generator)
+    leaves = (x, relation, query, weight, linear_bias, gamma, beta)
+
+    def three_nodes():
+        update = F.rspmm_add_one_hot(sparse, relation, x.flatten(1), node_index, query, mul).view(nodes, batch, 64)
+        return F.layer_norm_relu_residual(F.combine_linear(x, update, weight), gamma, beta, x if shortcut else None, 1e-5,
+                                          relu=True, linear_bias=linear_bias)
+
+    def grads(fn):
+        for t in leaves:
+            t.grad = None
+        out = fn()
+        out.backward(grad)
+        return out.detach(), [t.grad.clone() for t in leaves]
+
+    want, want_grads = grads(three_nodes)
+    got, got_grads = grads(lambda: F.nbf_layer(sparse, relation, x, node_index, query, weight, linear_bias, gamma, beta, mul, 1e-5,
+                                               True, shortcut))
+    assert torch.equal(got, want)
+    for name, a, b in zip(("x", "relation", "query", "weight", "linear_bias", "gamma", "beta"), got_grads, want_grads):
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5 * float(b.abs().max()), msg=lambda m, name=name: name + ": " + m)
+    again, again_grads = grads(lambda: F.nbf_layer(sparse, relation, x, node_index, query, weight, linear_bias, gamma, beta, mul,
+                                                   1e-5, True, shortcut))
+    assert torch.equal(again, got) and all(torch.equal(a, b) for a, b in zip(again_grads, got_grads)), "two runs differ"
+    # the operator's backward with an addend
+    index = F.graph_index(sparse)
+    flat_x, flat_grad = x.detach().flatten(1), grad.flatten(1)
+    addend = torch.randn_like(flat_x)
+    g_rel, g_in = index.backward(relation.detach(), flat_x, None, flat_grad, "add", mul)
+    a_rel, a_in = index.backward(relation.detach(), flat_x, None, flat_grad, "add", mul, input_addend=addend)
+    assert torch.equal(a_rel, g_rel)
+    torch.testing.assert_close(a_in, g_in + addend, rtol=1e-6, atol=1e-6 * float(g_in.abs().max()))
+    with pytest.raises(RuntimeError):
+        index.backward(relation.detach(), flat_x, None, flat_grad, "add", mul, need_input=False, input_addend=addend)
+
+
 @pytest.mark.parametrize("seed", range(int(os.environ.get("ULTRA_TEST_SEEDS", "24"))))
 def test_parity_randomized_specialised_kernels(cuda, seed):
     """Seeded random shapes through the kernels that production selects only on particular graphs, all forced on here:

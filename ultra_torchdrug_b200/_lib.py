@@ -8,7 +8,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 OK, ERR_ARG, ERR_WORKSPACE, ERR_CUDA, ERR_INDEX, ERR_DTYPE, ERR_RANGE = range(7)
 SUM_CODE = {"add": 0, "min": 1, "max": 2}
@@ -85,6 +85,8 @@ SYMBOLS = {
                                                c_void_p, c_int64, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "ultra_rspmm_backward": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
+    "ultra_rspmm_backward_addend": (ctypes.c_int, [ctypes.POINTER(Index), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_int64, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "ultra_rspmm_ctx_create": (ctypes.c_int, [ctypes.POINTER(c_void_p), c_int32]),
     "ultra_rspmm_ctx_destroy": (ctypes.c_int, [c_void_p]),
     "ultra_rspmm_ctx_set_graph": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32]),

@@ -236,17 +236,23 @@ rows_gemm_tc_kernel(const __grid_constant__ CUtensorMap map0, const __grid_const
                 float *out = h == 0 ? a.out0 : (a.out1 ? a.out1 : a.out0 + gm::kHalf);
                 const long long ld = h == 0 || !a.out1 ? a.ld0 : a.ld1;
                 const float *addend = h == 0 ? a.addend0 : nullptr;
+                constexpr int kBatch = 8;                                // addend loads in flight before their first use
 #pragma unroll
-                for (int pass = 0; pass < kPasses; ++pass) {
-                    const int r = pass * kRowsPerPass + sub_row;
-                    const long long row = row0 + r;
-                    float4 y = *reinterpret_cast<const float4 *>(staged + r * kStride + 4 * my_chunk);
-                    if (row < a.rows) {
-                        if (addend) {
-                            const float4 e = __ldg(reinterpret_cast<const float4 *>(addend + row * a.ld_addend + 4 * my_chunk));
-                            y = make_float4(y.x + e.x, y.y + e.y, y.z + e.z, y.w + e.w);
-                        }
-                        *reinterpret_cast<float4 *>(out + row * ld + 4 * my_chunk) = y;
+                for (int first_pass = 0; first_pass < kPasses; first_pass += kBatch) {
+                    float4 extra[kBatch];
+#pragma unroll
+                    for (int j = 0; j < kBatch; ++j) {
+                        const long long row = row0 + (first_pass + j) * kRowsPerPass + sub_row;
+                        extra[j] = addend && row < a.rows ? __ldg(reinterpret_cast<const float4 *>(addend + row * a.ld_addend + 4 * my_chunk))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kBatch; ++j) {
+                        const int r = (first_pass + j) * kRowsPerPass + sub_row;
+                        const long long row = row0 + r;
+                        float4 y = *reinterpret_cast<const float4 *>(staged + r * kStride + 4 * my_chunk);
+                        y = make_float4(y.x + extra[j].x, y.y + extra[j].y, y.z + extra[j].z, y.w + extra[j].w);
+                        if (row < a.rows) *reinterpret_cast<float4 *>(out + row * ld + 4 * my_chunk) = y;
                     }
                 }
                 __syncwarp();

@@ -935,7 +935,7 @@ int forward_typed(const ultra_rspmm_index_t &ix, const void *relation, const voi
 template <typename T>
 int backward_typed(const ultra_rspmm_index_t &ix, const void *relation, const void *input, const void *output,
                    const void *grad_output, void *grad_relation, void *grad_input, long long dim, int sum_op,
-                   int mul_op, void *ws, size_t ws_bytes, cudaStream_t stream) {
+                   int mul_op, void *ws, size_t ws_bytes, cudaStream_t stream, const void *grad_input_addend = nullptr) {
     const T *r = (const T *)relation, *x = (const T *)input, *o = (const T *)output, *g = (const T *)grad_output;
     T *gr = (T *)grad_relation, *gx = (T *)grad_input;
     const bool unit = ix.unit_weight != 0;
@@ -944,8 +944,8 @@ int backward_typed(const ultra_rspmm_index_t &ix, const void *relation, const vo
     if (sum_op == ULTRA_RSPMM_SUM_ADD) {
         if (gx) {
             status = mul_op == ULTRA_RSPMM_MUL_MUL
-                         ? run_pass<T, ADD, MSG_MUL, true, false>(GIN, ix, ix.csc, unit, g, r, ix.n_out, gx, nullptr, dim, ws, ws_bytes, stream)
-                         : run_pass<T, ADD, MSG_COPY, true, false>(GIN, ix, ix.csc, unit, g, r, ix.n_out, gx, nullptr, dim, ws, ws_bytes, stream);
+                         ? run_pass<T, ADD, MSG_MUL, true, false>(GIN, ix, ix.csc, unit, g, r, ix.n_out, gx, nullptr, dim, ws, ws_bytes, stream, (const T *)grad_input_addend)
+                         : run_pass<T, ADD, MSG_COPY, true, false>(GIN, ix, ix.csc, unit, g, r, ix.n_out, gx, nullptr, dim, ws, ws_bytes, stream, (const T *)grad_input_addend);
             if (status) return status;
         }
         if (gr) {
@@ -1080,16 +1080,18 @@ extern "C" int ultra_rspmm_forward(const ultra_rspmm_index_t *index, const void 
     return ULTRA_RSPMM_OK;
 }
 
-extern "C" int ultra_rspmm_backward(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
-                                    const void *dev_output, const void *dev_grad_output, void *dev_grad_relation,
-                                    void *dev_grad_input, int64_t dim, int32_t dtype, int32_t sum_op, int32_t mul_op,
-                                    void *workspace, size_t workspace_bytes, void *stream) {
+static int backward_call(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
+                         const void *dev_output, const void *dev_grad_output, void *dev_grad_relation, void *dev_grad_input,
+                         const void *dev_grad_input_addend, int64_t dim, int32_t dtype, int32_t sum_op, int32_t mul_op,
+                         void *workspace, size_t workspace_bytes, void *stream) {
     int status = check_call(index, dim, dtype, sum_op, mul_op);
     if (status) return status;
     if (dim == 0 || (!dev_grad_relation && !dev_grad_input)) return ULTRA_RSPMM_OK;
     if (index->n_out > 0 && !dev_grad_output) return ULTRA_RSPMM_ERR_ARG;
     if (sum_op != ULTRA_RSPMM_SUM_ADD && index->n_out > 0 && !dev_output) return ULTRA_RSPMM_ERR_ARG;
     if ((index->n_rel > 0 && !dev_relation) || (index->n_in > 0 && !dev_input)) return ULTRA_RSPMM_ERR_ARG;
+    if (dev_grad_input_addend && (sum_op != ULTRA_RSPMM_SUM_ADD || !dev_grad_input || dev_grad_input_addend == dev_grad_input))
+        return ULTRA_RSPMM_ERR_ARG;
     const size_t elem = dtype == ULTRA_RSPMM_F32 ? 4 : 8;
     size_t need = 0;
     if (dev_grad_input) need = pass_bytes(index->csc, dim, elem, false);
@@ -1102,12 +1104,28 @@ extern "C" int ultra_rspmm_backward(const ultra_rspmm_index_t *index, const void
     cudaStream_t s = (cudaStream_t)stream;
     status = dtype == ULTRA_RSPMM_F32
                  ? backward_typed<float>(*index, dev_relation, dev_input, dev_output, dev_grad_output, dev_grad_relation,
-                                         dev_grad_input, dim, sum_op, mul_op, workspace, workspace_bytes, s)
+                                         dev_grad_input, dim, sum_op, mul_op, workspace, workspace_bytes, s, dev_grad_input_addend)
                  : backward_typed<double>(*index, dev_relation, dev_input, dev_output, dev_grad_output, dev_grad_relation,
-                                          dev_grad_input, dim, sum_op, mul_op, workspace, workspace_bytes, s);
+                                          dev_grad_input, dim, sum_op, mul_op, workspace, workspace_bytes, s, dev_grad_input_addend);
     if (status) return status;
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;
+}
+
+extern "C" int ultra_rspmm_backward(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
+                                    const void *dev_output, const void *dev_grad_output, void *dev_grad_relation,
+                                    void *dev_grad_input, int64_t dim, int32_t dtype, int32_t sum_op, int32_t mul_op,
+                                    void *workspace, size_t workspace_bytes, void *stream) {
+    return backward_call(index, dev_relation, dev_input, dev_output, dev_grad_output, dev_grad_relation, dev_grad_input, nullptr,
+                         dim, dtype, sum_op, mul_op, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ultra_rspmm_backward_addend(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,
+                                           const void *dev_grad_output, void *dev_grad_relation, void *dev_grad_input,
+                                           const void *dev_grad_input_addend, int64_t dim, int32_t dtype, int32_t mul_op,
+                                           void *workspace, size_t workspace_bytes, void *stream) {
+    return backward_call(index, dev_relation, dev_input, nullptr, dev_grad_output, dev_grad_relation, dev_grad_input,
+                         dev_grad_input_addend, dim, dtype, ULTRA_RSPMM_SUM_ADD, mul_op, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ultra_rspmm_forward_pna(const ultra_rspmm_index_t *index, const void *dev_relation, const void *dev_input,

@@ -238,22 +238,36 @@ class GraphIndex(object):
         return tuple(outputs)
 
     def backward(self, relation, input, output, grad_output, sum="add", mul="mul", need_relation=True,
-                 need_input=True):
+                 need_input=True, input_addend=None):
+        """(grad_relation, grad_input).  `input_addend` (sum="add" only): an (n_in, dim) tensor added to grad_input in
+        the kernel that writes it (`ultra_rspmm_backward_addend`)."""
         self._check_dense(relation=relation, input=input, grad_output=grad_output, output=output if sum != "add" else None)
         if sum not in _SUM_OPS or mul not in _MUL_OPS:
             raise ValueError("No generalized rspmm implementation found for summation `%s` and multiplication `%s`" % (sum, mul))
         if sum != "add" and output is None:
             raise RuntimeError("min / max backward needs the saved `output`")
+        if input_addend is not None:
+            if sum != "add" or not need_input:
+                raise RuntimeError("`input_addend` belongs to grad_input of the sum aggregation")
+            if input_addend.shape != input.shape or input_addend.dtype != input.dtype or input_addend.device != input.device \
+                    or not input_addend.is_contiguous():
+                raise RuntimeError("`input_addend` must be a contiguous tensor with the shape, dtype and device of `input`")
         dim = input.shape[1]
         grad_relation = torch.empty_like(relation) if need_relation else None
         grad_input = torch.empty_like(input) if need_input else None
         need = self.workspace_bytes(dim)[1]
         with torch.cuda.device(input.device):
             workspace = torch.empty(need, dtype=torch.uint8, device=input.device) if need else None
-            _lib.check(_lib.lib().ultra_rspmm_backward(
-                ctypes.byref(self.c), _ptr(relation), _ptr(input), _ptr(output), _ptr(grad_output),
-                _ptr(grad_relation), _ptr(grad_input), dim, _DTYPE_CODE[self.dtype], _lib.SUM_CODE[sum],
-                _lib.MUL_CODE[mul], _ptr(workspace), need, _stream_handle()), "ultra_rspmm_backward")
+            if input_addend is not None:
+                _lib.check(_lib.lib().ultra_rspmm_backward_addend(
+                    ctypes.byref(self.c), _ptr(relation), _ptr(input), _ptr(grad_output), _ptr(grad_relation), _ptr(grad_input),
+                    _ptr(input_addend), dim, _DTYPE_CODE[self.dtype], _lib.MUL_CODE[mul], _ptr(workspace), need,
+                    _stream_handle()), "ultra_rspmm_backward_addend")
+            else:
+                _lib.check(_lib.lib().ultra_rspmm_backward(
+                    ctypes.byref(self.c), _ptr(relation), _ptr(input), _ptr(output), _ptr(grad_output),
+                    _ptr(grad_relation), _ptr(grad_input), dim, _DTYPE_CODE[self.dtype], _lib.SUM_CODE[sum],
+                    _lib.MUL_CODE[mul], _ptr(workspace), need, _stream_handle()), "ultra_rspmm_backward")
         return grad_relation, grad_input
 
 
@@ -644,6 +658,112 @@ def rspmm_add_one_hot(sparse, relation, input, node_index, query, mul="mul"):
             or query.dtype != input.dtype or sparse.size(0) != sparse.size(1):
         raise RuntimeError("`query` must be (B, d) with B * d == input.size(1), `node_index` (B,), and `sparse` square")
     return RSPMMAddOneHotFunction.apply(sparse, relation, input, node_index, query, mul)
+
+
+class NBFLayerFunction(torch.autograd.Function):
+    """One NBFNet layer with sum aggregation as ONE autograd node (reference layer.py:336-392 + model.py:126-127):
+
+        update = rspmm(adjacency, relation, x) + one_hot_boundary(node_index, query)
+        y = relu(layer_norm(cat([x, update]) @ W^T + b) * gamma + beta)  (+ x: the short-cut)
+
+    Forward: the operator, `ultra_layer_rows_gemm` and the fused epilogue, exactly the kernels the three separate nodes
+    (`RSPMMAddOneHotFunction`, `CombineLinearFunction`, `LayerEpilogueFunction`) run.  Backward: the layer input x has
+    three consumers - the operator, the Linear, the short-cut - and autograd would sum their gradients in two extra passes
+    over (N, B, d) tensors per layer (8 % of a C3 fine-tuning step); here the short-cut's gradient enters the `dX` GEMM's
+    epilogue and their sum enters the operator's grad_input pass (`ultra_rspmm_backward_addend`)."""
+
+    @staticmethod
+    def forward(ctx, sparse, relation, x, node_index, query, weight, linear_bias, gamma, beta, mul, eps, relu, shortcut):
+        index = graph_index(sparse)
+        x = x.detach().contiguous()
+        relation = relation.detach().contiguous()
+        num_node, batch, width = x.shape
+        update = index.forward(relation, x.view(num_node, batch * width), "add", mul).view(num_node, batch, width)
+        columns = torch.arange(batch, device=x.device)
+        update[node_index, columns] += query.detach()
+        w = weight.detach().contiguous()
+        rows = num_node * batch
+        lin = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().ultra_layer_rows_gemm(_ptr(x), 64, _ptr(update), 64, _ptr(w), _ptr(lin), 64, None, 0, None, 0, rows,
+                                                        64, 128, _stream_handle()), "ultra_layer_rows_gemm")
+        small = [None if t is None else t.detach().contiguous() for t in (linear_bias, gamma, beta)]
+        out = _epilogue_forward(lin, small[0], small[1], small[2], x if shortcut else None, eps, relu)
+        ctx.index, ctx.mul, ctx.eps, ctx.relu, ctx.shortcut = index, mul, eps, relu, shortcut
+        ctx.present = [t is not None for t in small]
+        ctx.save_for_backward(relation, x, update, lin, w, node_index, *[t if t is not None else x.new_empty(0) for t in small])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        relation, x, update, lin, w, node_index, linear_bias, gamma, beta = ctx.saved_tensors
+        linear_bias, gamma, beta = (t if present else None for t, present in zip((linear_bias, gamma, beta), ctx.present))
+        grad_out = grad_out.contiguous()
+        num_node, batch, width = x.shape
+        rows = num_node * batch
+        lib = _lib.lib()
+        need = ctypes.c_size_t()
+        grad_lin = torch.empty_like(lin)
+        sums = torch.empty(3, width, dtype=x.dtype, device=x.device)
+        grad_weight = None
+        with torch.cuda.device(x.device):
+            _lib.check(lib.ultra_layer_norm_relu_residual_backward_bytes(width, ctypes.byref(need)), "backward_bytes")
+            workspace = torch.empty(need.value, dtype=torch.uint8, device=x.device)
+            _lib.check(lib.ultra_layer_norm_relu_residual_backward(
+                _ptr(lin), _ptr(linear_bias), _ptr(gamma), _ptr(beta), _ptr(grad_out), _ptr(grad_lin), _ptr(sums[0]),
+                _ptr(sums[1]), _ptr(sums[2]), rows, width, float(ctx.eps), int(bool(ctx.relu)), _ptr(workspace), need.value,
+                _stream_handle()), "ultra_layer_norm_relu_residual_backward")
+            # [d x (Linear) + d x (short-cut) | d update] = grad_lin @ W  (+ grad_out on the first half)
+            grad_x_partial, grad_update = torch.empty_like(x), torch.empty_like(update)
+            transposed = w.t().contiguous()
+            _lib.check(lib.ultra_layer_rows_gemm(_ptr(grad_lin), 64, None, 0, _ptr(transposed), _ptr(grad_x_partial), 64,
+                                                 _ptr(grad_update), 64, _ptr(grad_out) if ctx.shortcut else None, 64, rows, 128, 64,
+                                                 _stream_handle()), "ultra_layer_rows_gemm")
+            if ctx.needs_input_grad[5]:
+                _lib.check(lib.ultra_layer_rows_gemm_weight_bytes(ctypes.byref(need)), "ultra_layer_rows_gemm_weight_bytes")
+                workspace = torch.empty(need.value, dtype=torch.uint8, device=x.device)
+                grad_weight = torch.empty_like(w)
+                _lib.check(lib.ultra_layer_rows_gemm_weight(_ptr(grad_lin), 64, _ptr(x), 64, _ptr(update), 64, rows, _ptr(grad_weight),
+                                                            _ptr(workspace), need.value, _stream_handle()),
+                           "ultra_layer_rows_gemm_weight")
+        flat = (num_node, batch * width)
+        if ctx.needs_input_grad[2]:
+            grad_relation, grad_x = ctx.index.backward(relation, x.view(flat), None, grad_update.view(flat), "add", ctx.mul,
+                                                       need_relation=ctx.needs_input_grad[1], input_addend=grad_x_partial.view(flat))
+            grad_x = grad_x.view(x.shape)
+        else:
+            grad_relation, _ = ctx.index.backward(relation, x.view(flat), None, grad_update.view(flat), "add", ctx.mul,
+                                                  need_relation=ctx.needs_input_grad[1], need_input=False)
+            grad_x = None
+        grad_query = None
+        if ctx.needs_input_grad[4]:
+            grad_query = grad_update[node_index, torch.arange(batch, device=x.device)]
+        return (None, grad_relation, grad_x, None, grad_query, grad_weight, sums[0] if linear_bias is not None else None,
+                sums[1] if gamma is not None else None, sums[2] if beta is not None else None, None, None, None, None)
+
+
+def nbf_layer_supported(relation, x, query, weight):
+    """Whether `nbf_layer` serves this layer: float32 CUDA, (N, B, 64) hidden state, (64, 128) Linear."""
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[-1] == 64 and tuple(weight.shape) == (64, 128)
+            and weight.dtype == torch.float32 and weight.device == x.device and relation.dtype == torch.float32
+            and relation.device == x.device and query.dim() == 2 and query.shape == (x.shape[1], 64) and x.numel() > 0)
+
+
+def nbf_layer(sparse, relation, x, node_index, query, weight, linear_bias=None, gamma=None, beta=None, mul="mul", eps=1e-5,
+              relu=True, shortcut=True):
+    """relu(layer_norm(cat([x, rspmm(sparse, relation, x) + boundary]) @ weight^T + linear_bias) * gamma + beta) (+ x), boundary
+    = `query[b]` at node `node_index[b]` - one NBFNet layer with sum aggregation (reference layer.py:336-392,
+    model.py:106-109, 126-127) as a single differentiable node; x: (N, B, 64), relation: (R, B * 64)."""
+    if not nbf_layer_supported(relation, x, query, weight):
+        raise RuntimeError("nbf_layer needs float32 CUDA operands: x (N, B, 64), query (B, 64), weight (64, 128)")
+    if mul not in _MUL_OPS:
+        raise ValueError("Unknown multiplication `%s`" % mul)
+    if sparse.requires_grad:
+        raise RuntimeError("gradient w.r.t. the sparse values is outside the rspmm hot path")
+    _check_operands(sparse, relation, x.view(x.shape[0], -1))
+    if node_index.shape != (query.shape[0],) or sparse.size(0) != sparse.size(1):
+        raise RuntimeError("`node_index` must be (B,) and `sparse` square")
+    return NBFLayerFunction.apply(sparse, relation, x, node_index, query, weight, linear_bias, gamma, beta, mul, eps, relu, shortcut)
 
 
 def rspmm_add_boundary(sparse, relation, input, boundary, mul="mul"):

@@ -132,7 +132,25 @@ class _RelationalConvBase(nn.Module):
             output = self.activation(output)
         return output if residual is None else output + residual
 
+    def _single_node_supported(self, graph, input, residual, one_hot):
+        """Training fast path of `forward`: the whole layer as one autograd node (`functional.nbf_layer`)."""
+        if one_hot is None or not torch.is_grad_enabled() or not (residual is None or residual is input):
+            return False
+        if self.aggregate_func != "sum" or self.message_func not in MESSAGE_TO_MUL or self.layer_norm is None:
+            return False
+        if self.activation not in (F.relu, None) or generalized_rspmm is not rspmm.generalized_rspmm:
+            return False
+        if os.environ.get("ULTRA_NBF_SINGLE_NODE", "1") == "0" or graph.adjacency.requires_grad:
+            return False
+        return input.dim() == 3 and rspmm.nbf_layer_supported(input, input, one_hot[1], self.linear.weight)
+
     def forward(self, graph, input, residual=None, one_hot=None):
+        if self._single_node_supported(graph, input, residual, one_hot):
+            relation_input = self.relation_input(graph, len(graph.query))
+            return rspmm.nbf_layer(graph.adjacency.transpose(0, 1), relation_input, input, one_hot[0], one_hot[1],
+                                   self.linear.weight, self.linear.bias, self.layer_norm.weight, self.layer_norm.bias,
+                                   MESSAGE_TO_MUL[self.message_func], self.layer_norm.eps, self.activation is not None,
+                                   residual is not None)
         return self.combine(input, self.message_and_aggregate(graph, input, one_hot), residual)
 
 
@@ -380,7 +398,7 @@ class TransferNBFNet(nn.Module):
                 hiddens.append(hidden)
             return torch.cat(hiddens + [query.expand(graph.num_node, -1, -1)], dim=-1)
         hidden = _run_layers(self.layers, graph, boundary, self.short_cut, one_hot=(h_index, query))
-        return torch.cat([hidden, query.expand(graph.num_node, -1, -1)], dim=-1)
+        return hidden, query                                # the caller concatenates - after picking candidates, if it can
 
     def mask_easy_edges(self, graph, h_index, t_index, r_index):
         """`remove_easy_edges` + `undirected(add_inverse=True)` without changing the edge structure: the edges that match
@@ -420,15 +438,21 @@ class TransferNBFNet(nn.Module):
             assert (h_index[:, :1] == h_index).all() and (r_index[:, :1] == r_index).all()
         elif _DEVICE_ASSERTS:
             torch._assert_async(((h_index[:, :1] == h_index) & (r_index[:, :1] == r_index)).all())
-        feature = self.bellmanford(graph, h_index[:, 0], r_index[:, 0])           # (N, B, 2d)
+        feature = self.bellmanford(graph, h_index[:, 0], r_index[:, 0])           # (N, B, 2d) or ((N, B, d), (B, d))
         if isinstance(feature, tuple):
-            score = self._split_head(*feature).transpose(0, 1)                    # (B, N)
-            return score.gather(1, t_index).view(shape)
-        if 2 * t_index.shape[1] >= graph.num_node:
-            # ranking against (almost) all entities: score every node once, then pick - the MLP is row-wise, so this
-            # equals the reference's gather-then-score (model.py:177-193) without copying the (B, N, 2d) feature tensor
-            score = self.mlp(feature).squeeze(-1).transpose(0, 1)                 # (B, N)
-            return score.gather(1, t_index).view(shape)
+            hidden, query = feature
+            if not torch.is_grad_enabled() and hidden.is_cuda and self._split_head_supported(hidden, query):
+                score = self._split_head(hidden, query).transpose(0, 1)           # (B, N)
+                return score.gather(1, t_index).view(shape)
+            if 2 * t_index.shape[1] < graph.num_node:
+                # a few candidates per query (training: 1 + num_negative): pick their hidden rows first, then append the
+                # query - row for row the reference's cat-then-gather (model.py:141-143, 177-193) without the
+                # (N, B, 2d) copy and its (N, B, 2d) gradient
+                rows = torch.arange(t_index.shape[0], device=t_index.device).unsqueeze(-1)
+                picked = hidden[t_index, rows]                                    # (B, T, d); its gradient: B * T row updates
+                feature = torch.cat([picked, query.unsqueeze(1).expand(-1, picked.shape[1], -1)], dim=-1)
+                return self.mlp(feature).squeeze(-1).view(shape)
+            feature = torch.cat([hidden, query.expand(graph.num_node, -1, -1)], dim=-1)
         feature = feature.transpose(0, 1)
         feature = feature.gather(1, t_index.unsqueeze(-1).expand(-1, -1, feature.shape[-1]))
         return self.mlp(feature).squeeze(-1).view(shape)
