@@ -112,9 +112,9 @@ typedef struct ultra_rspmm_index {
     const int32_t *merge_start; /* nnz + 1: csr edge m is the sum of merge_perm[merge_start[m] .. merge_start[m + 1])  */
     /* ---- optional extensions, filled by ultra_rspmm_index_extend (all zero / null when absent) ---- */
     ultra_rspmm_pairs_t pairs[2];   /* [0] csr order (forward), [1] csc order (gradient w.r.t. input)                 */
-    const int32_t *block_ptr;   /* n_rel x (n_block + 1): position in the rel order where the edges of relation k with
-                                   destination >= b * block_rows start - a (relation, destination block) run is a
-                                   contiguous range of the rel order (it is sorted by (rel, dst, src))                 */
+    const int32_t *block_ptr;   /* n_rel x (2 n_block + 1): position in the rel order where the edges of relation k with
+                                   destination >= h * block_rows / 2 start - a (relation, destination block) run is the
+                                   contiguous range between entries 2 b and 2 b + 2, its two half blocks split at 2 b + 1 */
     const int32_t *block_split; /* n_rel x int4 {rel, rel * n_block, n_block, 0}: combine list of the blocked pass     */
     int32_t block_rows;         /* destination rows per block (their grad_output slab is staged in shared memory)      */
     int32_t n_block;
@@ -139,7 +139,8 @@ enum {
     ULTRA_RSPMM_KERNEL_ROWS_IN_SMEM = 4,  /* few-row operands: the gathered slab is staged in shared memory           */
     ULTRA_RSPMM_KERNEL_DST_BLOCKED = 5,   /* grad_relation with grad_output rows of a destination block in shared memory */
     ULTRA_RSPMM_KERNEL_PAIRS_IN_SMEM = 6, /* few-row operands with <= 4 relation types: one row read per (node, node) pair */
-    ULTRA_RSPMM_KERNEL_SUBWARP_ROWS = 7   /* slabs beyond L2: 2 or 4 tasks per warp, 256- / 128-byte slabs (n_slab tells which) */
+    ULTRA_RSPMM_KERNEL_SUBWARP_ROWS = 7,  /* slabs beyond L2: 2 or 4 tasks per warp, 256- / 128-byte slabs (n_slab tells which) */
+    ULTRA_RSPMM_KERNEL_DST_BLOCKED_GATED = 8 /* min / max grad_relation with grad_output and output rows of half a block staged */
 };
 typedef struct ultra_rspmm_pass_info {
     int32_t kernel;    /* ULTRA_RSPMM_KERNEL_*                                        */

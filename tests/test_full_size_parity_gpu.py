@@ -155,7 +155,9 @@ def test_full_size_matches_oracle(cuda, name, sum, mul):
     assert gin_info["kernel_name"] == (forward_kernel if sum == "add" else backward_kernel), gin_info
     # the destination-blocked pass serves DistMult here; TransE (grad_output is the only gathered operand) keeps the generic
     # kernel until that one slab is far beyond L2 (n_out * 512 B > 150 MB: none of these shapes)
-    want_grel = "seg_gated" if sum != "add" else (case.spec.get("grel_kernel", "seg_reduce") if mul == "mul" else "seg_reduce")
+    # min / max: the gated destination-blocked pass wherever the block table exists and the two slabs exceed L2
+    gated = "dst_blocked_gated" if "grel_kernel" in case.spec else "seg_gated"
+    want_grel = gated if sum != "add" else (case.spec.get("grel_kernel", "seg_reduce") if mul == "mul" else "seg_reduce")
     assert grel_info["kernel_name"] == want_grel, grel_info
     if sum == "add":
         _check_info(gin_info, expect.get("gin", {}), "grad_input")

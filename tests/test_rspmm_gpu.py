@@ -902,6 +902,43 @@ def test_destination_blocked_grad_relation_parity(cuda, extensions_always, mul, 
 
 
 @pytest.mark.parametrize("sum", ["max", "min"])
+@pytest.mark.parametrize("mul", ["mul", "add"])
+@pytest.mark.parametrize("weights,ties", [("unit", True), ("random", False)])
+@pytest.mark.parametrize("n,n_rel,nnz,dim", [(2000, 7, 30000, 192), (1700, 40, 9000, 64), (500, 3, 5000, 100)])
+def test_destination_blocked_gated_grad_relation_parity(cuda, extensions_always, sum, mul, weights, ties, n, n_rel, nnz, dim):
+    """grad_relation of min / max through the destination-blocked gated kernel (forced on): grad_output AND output rows of
+    half a block staged in shared memory, input rows gathered, the all-ties gate `output[dst] == w (x (x) relation)` in the
+    same expressions as the generic gated kernel - so the sums agree with the oracle, and with integer-valued operands
+    (every extremum has exact ties, every sum is exact) bit for bit with the generic kernel."""
+    from ultra_torchdrug_b200 import functional as F
+    lib = extensions_always
+    indices, values = util.random_coo(n, n - 50, n_rel, nnz, seed=nnz + 1, duplicates=100, weights=weights, skew=True)
+    shape = (n, n - 50, n_rel)
+    index = F.GraphIndex(torch.from_numpy(indices).to(cuda), torch.from_numpy(values).to(cuda), shape)
+    relation, input = util.random_dense(n_rel, dim, 1, np.float32, ties), util.random_dense(n - 50, dim, 2, np.float32, ties)
+    grad = util.random_dense(n, dim, 3, np.float32, ties)
+    d_rel, d_in, d_grad = (torch.from_numpy(x).to(cuda) for x in (relation, input, grad))
+    out = index.forward(d_rel, d_in, sum, mul)
+    g_rel, g_in = index.backward(d_rel, d_in, out, d_grad, sum, mul)
+    assert lib.pass_info(lib.PASS_GRAD_RELATION)["kernel_name"] == "dst_blocked_gated"
+    out_np = out.cpu().numpy()
+    e_rel, e_in = util.oracle_backward(indices, values, shape, relation, input, out_np, grad, sum, mul, dtype=np.float64)
+    s_rel, s_in = util.oracle_backward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), out_np, np.abs(grad),
+                                       "add", mul, dtype=np.float64)
+    _assert_sum_close(g_rel.cpu().numpy(), e_rel, s_rel, "blocked gated grad_relation %s/%s" % (sum, mul))
+    _assert_sum_close(g_in.cpu().numpy(), e_in, s_in, "grad_input %s/%s" % (sum, mul))
+    again, _ = index.backward(d_rel, d_in, out, d_grad, sum, mul)
+    assert torch.equal(g_rel, again), "two runs differ"
+    lib.check(lib.lib().ultra_rspmm_set_extensions(2, 0), "ultra_rspmm_set_extensions")       # the generic gated kernel
+    generic, _ = index.backward(d_rel, d_in, out, d_grad, sum, mul)
+    assert lib.pass_info(lib.PASS_GRAD_RELATION)["kernel_name"] == "seg_gated"
+    if ties:
+        assert torch.equal(g_rel, generic), "integer-valued operands: the two kernels must agree exactly"
+    else:
+        _assert_sum_close(g_rel.cpu().numpy(), generic.cpu().numpy().astype(np.float64), s_rel, "blocked vs generic")
+
+
+@pytest.mark.parametrize("sum", ["max", "min"])
 def test_minmax_gradient_all_ties_rule_ext_recall(cuda, sum):
     """Hand-computed known answer for the min / max backward: EVERY edge whose message equals the extremum receives the
     full upstream gradient (torchdrug `NaryMax::backward(out, y) = (out == y)`).  [ext-recall]: the rule follows this

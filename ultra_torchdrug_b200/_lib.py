@@ -48,7 +48,7 @@ class PassInfo(ctypes.Structure):
 
 PASS_FORWARD, PASS_GRAD_INPUT, PASS_GRAD_RELATION = 0, 1, 2
 KERNEL_NAMES = {0: "none", 1: "seg_reduce", 2: "seg_gated", 3: "seg_pna", 4: "rows_in_smem", 5: "dst_blocked",
-                6: "pairs_in_smem", 7: "subwarp_rows"}
+                6: "pairs_in_smem", 7: "subwarp_rows", 8: "dst_blocked_gated"}
 
 #: every symbol `include/ultra_rspmm.h` declares: name -> (restype, argtypes)
 SYMBOLS = {

@@ -230,12 +230,15 @@ struct BlockedRelArgs {
     const float *w;           // rel-order weights, null when all 1
     const float *G;           // grad_output (n_out, dim): staged
     const float *X;           // input (n_in, dim): gathered (unused for MSG_COPY)
+    const float *O;           // gated pass (min / max): output (n_out, dim), staged beside G
+    const float *R;           // gated pass: relation (n_rel, dim), the run's own row
     float *partial;           // (n_rel * n_block, dim)
     unsigned *counter;
     long long dim;
     int n_rel, n_block, block_rows, n_out, n_slab;
 };
 int launch_dst_blocked(BlockedRelArgs args, int msg, cudaStream_t stream);
+int launch_dst_blocked_gated(BlockedRelArgs args, int msg, cudaStream_t stream);   // msg: MSG_MUL or MSG_ADD
 extern int g_pairs, g_blocked;
 
 // sub-warp rows kernel (rspmm_narrow.cu): graphs whose 512-byte slab exceeds L2 - SUB tasks per warp, 256 / 128-byte slabs

@@ -24,7 +24,7 @@ namespace {
 constexpr int kPairThreads = 128;
 constexpr int kPairTable = 1024;          // >= kStagedMaxRows, one byte of relation mask per node
 // destination rows per block: 768 x 256 B = 192 KB of shared memory (one CTA per SM); ULTRA_RSPMM_BLOCK_ROWS=384: two CTAs
-const int kBlockRows = getenv("ULTRA_RSPMM_BLOCK_ROWS") ? (atoi(getenv("ULTRA_RSPMM_BLOCK_ROWS")) > 0 && atoi(getenv("ULTRA_RSPMM_BLOCK_ROWS")) <= 768 ? atoi(getenv("ULTRA_RSPMM_BLOCK_ROWS")) : 768) : 768;
+const int kBlockRows = getenv("ULTRA_RSPMM_BLOCK_ROWS") ? (atoi(getenv("ULTRA_RSPMM_BLOCK_ROWS")) > 1 && atoi(getenv("ULTRA_RSPMM_BLOCK_ROWS")) <= 768 ? atoi(getenv("ULTRA_RSPMM_BLOCK_ROWS")) & ~1 : 768) : 768;   // even: half blocks
 
 // relation masks of one segment: table[other] |= 1 << rel (bytes packed four to a word, set with shared-memory atomics -
 // integer OR is order-independent)
@@ -98,21 +98,24 @@ __global__ void __launch_bounds__(kPairThreads) pair_emit_kernel(const int32_t *
     }
 }
 
-// block_ptr[k * (n_block + 1) + b] = first position in [ptr[k], ptr[k + 1]) of the rel order whose destination >= b * rows
+// block_ptr[k * (2 n_block + 1) + h] = first position in [ptr[k], ptr[k + 1]) of the rel order whose destination >= h * rows / 2:
+// half-block granularity - the sum pass takes blocks (entries 2 b and 2 b + 2), the gated pass, which stages two rows per
+// destination, half blocks
 __global__ void block_ptr_kernel(const int32_t *__restrict__ ptr, const int2 *__restrict__ edge, int n_rel, int n_block,
                                  int block_rows, int32_t *__restrict__ block_ptr, int4 *__restrict__ split) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)n_rel * (n_block + 1)) return;
-    const int k = (int)(i / (n_block + 1)), b = (int)(i - (long long)k * (n_block + 1));
+    const int per_rel = 2 * n_block + 1;
+    if (i >= (long long)n_rel * per_rel) return;
+    const int k = (int)(i / per_rel), h = (int)(i - (long long)k * per_rel);
     int lo = ptr[k], hi = ptr[k + 1];
-    const long long bound = (long long)b * block_rows;
+    const long long bound = (long long)h * (block_rows / 2);
     while (lo < hi) {
         const int mid = lo + ((hi - lo) >> 1);
         if (edge[mid].x < bound) lo = mid + 1;
         else hi = mid;
     }
     block_ptr[i] = lo;
-    if (b == 0) split[k] = make_int4(k, k * n_block, n_block, 0);
+    if (h == 0) split[k] = make_int4(k, k * n_block, n_block, 0);
 }
 
 struct ExtendLayout {
@@ -141,7 +144,7 @@ ExtendLayout extend_layout(const ultra_rspmm_index_t &ix) {
         }
     }
     if (L.blocks) {
-        L.block_ptr = at; at = align_up(at + 4 * (size_t)ix.n_rel * ((size_t)L.n_block + 1));
+        L.block_ptr = at; at = align_up(at + 4 * (size_t)ix.n_rel * (2 * (size_t)L.n_block + 1));
         L.block_split = at; at = align_up(at + sizeof(int4) * (size_t)ix.n_rel);
     }
     L.total = at;
@@ -204,7 +207,7 @@ extern "C" int ultra_rspmm_index_extend(ultra_rspmm_index_t *index, void *buffer
     if (L.blocks) {
         int32_t *block_ptr = (int32_t *)(base + L.block_ptr);
         int4 *split = (int4 *)(base + L.block_split);
-        const long long n = (long long)index->n_rel * (L.n_block + 1);
+        const long long n = (long long)index->n_rel * (2 * L.n_block + 1);
         block_ptr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(index->rel.ptr, (const int2 *)index->rel.edge, index->n_rel,
                                                                         L.n_block, kBlockRows, block_ptr, split);
         note_launch();

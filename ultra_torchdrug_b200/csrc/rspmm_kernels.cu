@@ -905,6 +905,46 @@ int run_gated(int pass, const ultra_rspmm_order_t &order, bool unit_weight, cons
     return launch_combine<T, ULTRA_RSPMM_SUM_ADD, false>(order, args.partial, nullptr, out, nullptr, dim, stream);
 }
 
+// grad_relation of min / max on graphs whose slabs exceed L2: destination-blocked gated pass (one gathered row per edge
+// instead of three).  Returns true when it ran (status in *status).
+template <typename T, int MSG>
+bool run_gated_blocked(const ultra_rspmm_index_t &ix, bool unit_weight, const T *G, const T *O, const T *X, const T *R, T *out,
+                       long long dim, void *workspace, size_t workspace_bytes, cudaStream_t stream, int *status) {
+    if (!std::is_same<T, float>::value || g_blocked == 0 || !ix.block_ptr || !workspace || ix.block_rows % 2) return false;
+    if (workspace_bytes < blocked_bytes(ix, dim) || blocked_bytes(ix, dim) > blocked_cap()) return false;
+    if (pick_vec<T>(dim, (long long)ix.n_out + ix.n_in, {G, O, X, R, out, workspace}) != 4) return false;
+    const double run = (double)ix.nnz / ((double)ix.n_rel * (ix.n_block > 0 ? ix.n_block : 1));
+    const long long both = ((long long)ix.n_out + ix.n_in) * 512;
+    // a run is walked in two halves: below ~24 edges per run the per-run overhead eats the saved gathers (R' = 2,000 at
+    // 8.4 M edges, 12 edges per run: 62-68 % of the HBM peak fwd+bwd generic, 58-60 % blocked)
+    if (g_blocked != 2 && !(both > (96ll << 20) && run >= 24)) return false;
+    BlockedRelArgs ba = {};
+    ba.block_ptr = ix.block_ptr;
+    ba.edge = (const int2 *)ix.rel.edge;
+    ba.packed = ix.rel.pack_shift > 0 ? (const unsigned *)ix.rel.packed : nullptr;
+    ba.pack_shift = ix.rel.pack_shift;
+    ba.w = unit_weight ? nullptr : (const float *)ix.rel.w;
+    ba.G = (const float *)G; ba.O = (const float *)O; ba.X = (const float *)X; ba.R = (const float *)R;
+    ba.partial = (float *)workspace;
+    ba.counter = (unsigned *)((char *)workspace + blocked_bytes(ix, dim) - 256);
+    ba.dim = dim; ba.n_rel = ix.n_rel; ba.n_block = ix.n_block; ba.block_rows = ix.block_rows; ba.n_out = ix.n_out;
+    *status = launch_dst_blocked_gated(ba, MSG, stream);
+    if (*status) return true;
+    ultra_rspmm_pass_info_t info = {};
+    info.kernel = ULTRA_RSPMM_KERNEL_DST_BLOCKED_GATED;
+    info.vec = 4;
+    info.packed = ix.rel.pack_shift > 0;
+    info.n_task = ix.n_rel * ix.n_block;
+    info.n_slab = (int)((dim + kStagedSlab - 1) / kStagedSlab);
+    info.n_split = ix.n_rel;
+    note_pass(GREL, info);
+    ultra_rspmm_order_t folded = ix.rel;         // combine list: relation k <- its n_block partial rows, in block order
+    folded.split = ix.block_split;
+    folded.n_split = ix.n_rel;
+    *status = launch_combine<T, ULTRA_RSPMM_SUM_ADD, false>(folded, (const T *)workspace, nullptr, out, nullptr, dim, stream);
+    return true;
+}
+
 template <typename T, int SUM>
 int forward_sum(const ultra_rspmm_index_t &ix, const T *relation, const T *input, T *output, int32_t *argidx,
                 long long dim, int mul_op, void *ws, size_t ws_bytes, cudaStream_t stream, const T *addend = nullptr) {
@@ -961,6 +1001,10 @@ int backward_typed(const ultra_rspmm_index_t &ix, const void *relation, const vo
         if (status) return status;
     }
     if (gr) {
+        const bool blocked = mul_op == ULTRA_RSPMM_MUL_MUL
+                                 ? run_gated_blocked<T, MSG_MUL>(ix, unit, g, o, x, r, gr, dim, ws, ws_bytes, stream, &status)
+                                 : run_gated_blocked<T, MSG_ADD>(ix, unit, g, o, x, r, gr, dim, ws, ws_bytes, stream, &status);
+        if (blocked) return status;
         status = mul_op == ULTRA_RSPMM_MUL_MUL ? run_gated<T, MSG_MUL, false>(GREL, ix.rel, unit, g, o, x, r, (long long)ix.n_out + ix.n_in, gr, dim, ws, ws_bytes, stream)
                                                : run_gated<T, MSG_ADD, false>(GREL, ix.rel, unit, g, o, x, r, (long long)ix.n_out + ix.n_in, gr, dim, ws, ws_bytes, stream);
     }

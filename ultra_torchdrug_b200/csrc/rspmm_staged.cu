@@ -370,8 +370,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) dst_blocked_kernel(const Blo
         const bool active = col < a.dim;
         const char *X = reinterpret_cast<const char *>(a.X + (active ? col : 0));
         for (int k = warp; k < a.n_rel; k += WARPS) {
-            const int begin = __ldg(a.block_ptr + (long long)k * (a.n_block + 1) + b);
-            const int end = __ldg(a.block_ptr + (long long)k * (a.n_block + 1) + b + 1);
+            const int begin = __ldg(a.block_ptr + (long long)k * (2 * a.n_block + 1) + 2 * b);   // table in half blocks
+            const int end = __ldg(a.block_ptr + (long long)k * (2 * a.n_block + 1) + 2 * b + 2);
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             auto one = [&](const Ids &e, float w) {
                 const int dst = PACKED ? (int)(id_bits_of(e) & low) : id_first(e);
@@ -439,6 +439,133 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) dst_blocked_kernel(const Blo
             }
         }
         __syncthreads();
+    }
+}
+
+// ---- destination-blocked grad_relation of the min / max aggregation (all-ties rule) ----------------------------------------
+// The gated pass needs grad_output[dst] AND output[dst] per edge (`if (output[dst] == w (x[src] (x) relation[k])) acc +=
+// grad_output[dst] w (x[src] | 1)`): the generic kernel gathers three rows per edge.  Here both are staged - 2 x 256 B per
+// destination row, so a CTA works on HALF a block at a time (the table is kept at that granularity) - and only x[src] is
+// gathered.  A (k, b) run's partial row is written after the first half and completed after the second by the same lanes.
+template <int MSG, bool PACKED, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) dst_blocked_gated_kernel(const BlockedRelArgs a) {
+    using Ids = typename std::conditional<PACKED, unsigned, int2>::type;
+    constexpr int kThreads = WARPS * 32;
+    extern __shared__ __align__(16) float4 s_rows[];   // [half_rows][16] grad_output, then [half_rows][16] output
+    __shared__ __align__(16) Ids s_edge[WARPS][32];
+    __shared__ __align__(16) float s_w[WARPS][32];
+    __shared__ int s_item;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, l16 = lane & 15;
+    const int shift = a.pack_shift;
+    const unsigned low = PACKED ? ((1u << shift) - 1u) : 0u;
+    const unsigned row_bytes = (unsigned)(a.dim * sizeof(float));
+    const int half_rows = a.block_rows / 2;
+    float4 *s_out = s_rows + half_rows * (kStagedSlab / 4);
+    const int n_item = a.n_block * a.n_slab;
+    const Ids *ids = reinterpret_cast<const Ids *>(PACKED ? (const void *)a.packed : (const void *)a.edge);
+    const unsigned long long keep_policy = policy_evict_last(), once_policy = policy_evict_first();
+    for (;;) {
+        if (threadIdx.x == 0) s_item = (int)atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_item) break;
+        const int slab = item / a.n_block, b = item - slab * a.n_block;
+        const long long col = (long long)slab * kStagedSlab + l16 * 4;
+        const bool active = col < a.dim;
+        const char *X = reinterpret_cast<const char *>(a.X + (active ? col : 0));
+        for (int part = 0; part < 2; ++part) {
+            const int first_row = b * a.block_rows + part * half_rows;
+            const int rows = max(0, min(half_rows, a.n_out - first_row));
+            for (int i = threadIdx.x; i < rows * (kStagedSlab / 4); i += kThreads) {
+                const long long c = (long long)slab * kStagedSlab + (i & 15) * 4;
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f), o = g;
+                if (c < a.dim) {
+                    Vec<float, 4> vg, vo;
+                    gather_load_keep(a.G + (long long)(first_row + (i >> 4)) * a.dim + c, vg, once_policy);
+                    gather_load_keep(a.O + (long long)(first_row + (i >> 4)) * a.dim + c, vo, once_policy);
+                    g = make_float4(vg.v[0], vg.v[1], vg.v[2], vg.v[3]);
+                    o = make_float4(vo.v[0], vo.v[1], vo.v[2], vo.v[3]);
+                }
+                s_rows[i] = g;
+                s_out[i] = o;
+            }
+            __syncthreads();
+            for (int k = warp; k < a.n_rel; k += WARPS) {
+                const int begin = __ldg(a.block_ptr + (long long)k * (2 * a.n_block + 1) + 2 * b + part);
+                const int end = __ldg(a.block_ptr + (long long)k * (2 * a.n_block + 1) + 2 * b + part + 1);
+                float *p = a.partial + ((long long)k * a.n_block + b) * a.dim + col;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (begin < end && active) own = __ldg(reinterpret_cast<const float4 *>(a.R + (long long)k * a.dim + col));
+                const float ov[4] = {own.x, own.y, own.z, own.w};
+                auto accumulate = [&](const Ids &e, float w, const Vec<float, 4> &x) {
+                    const int dst = PACKED ? (int)(id_bits_of(e) & low) : id_first(e);
+                    const float4 g = s_rows[(dst - first_row) * (kStagedSlab / 4) + l16];
+                    const float4 o = s_out[(dst - first_row) * (kStagedSlab / 4) + l16];
+                    const float gv[4] = {g.x, g.y, g.z, g.w}, out_v[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        // the same expressions as seg_gated_kernel: y = w * (x (x) own) (unit weight: no multiply)
+                        const float y = a.w ? message<float, MSG>(w, x.v[v], ov[v]) : message<float, MSG>(x.v[v], ov[v]);
+                        const float up = a.w ? gv[v] * w : gv[v];
+                        const float term = MSG == MSG_MUL ? up * x.v[v] : up;
+                        if (out_v[v] == y) acc[v] += term;
+                    }
+                };
+                Ids ahead = Ids();
+                float ahead_w = 1.f;
+                if (begin + lane < end) {
+                    ahead = edge_load_once(ids + begin + lane, once_policy);
+                    if (a.w) ahead_w = __ldg(a.w + begin + lane);
+                }
+                for (int base = begin; base < end; base += 32) {
+                    const int n = min(32, end - base);
+                    __syncwarp();
+                    s_edge[warp][lane] = ahead;
+                    s_w[warp][lane] = ahead_w;
+                    __syncwarp();
+                    if (base + 32 + lane < end) {
+                        ahead = edge_load_once(ids + base + 32 + lane, once_policy);
+                        if (a.w) ahead_w = __ldg(a.w + base + 32 + lane);
+                    }
+                    int u = 0;
+                    for (; u + 2 * kEdgesPerHalf <= n; u += 2 * kEdgesPerHalf) {
+                        const int mine = u + half * kEdgesPerHalf;
+                        Vec<float, 4> x[kEdgesPerHalf];
+#pragma unroll
+                        for (int q = 0; q < kEdgesPerHalf; ++q) {
+                            const Ids e = s_edge[warp][mine + q];
+                            const int src = PACKED ? (int)(id_bits_of(e) >> shift) : id_second(e);
+                            gather_load_keep(reinterpret_cast<const float *>(X + (unsigned long long)(unsigned)src * row_bytes), x[q], keep_policy);
+                        }
+#pragma unroll
+                        for (int q = 0; q < kEdgesPerHalf; ++q) accumulate(s_edge[warp][mine + q], s_w[warp][mine + q], x[q]);
+                    }
+                    for (; u < n; u += 2) {
+                        const int mine = u + half;
+                        if (mine < n) {
+                            const Ids e = s_edge[warp][mine];
+                            const int src = PACKED ? (int)(id_bits_of(e) >> shift) : id_second(e);
+                            Vec<float, 4> x;
+                            gather_load_keep(reinterpret_cast<const float *>(X + (unsigned long long)(unsigned)src * row_bytes), x, keep_policy);
+                            accumulate(e, s_w[warp][mine], x);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[v] += __shfl_xor_sync(kFullMask, acc[v], 16);
+                if (half == 0 && active) {
+                    float4 r = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    if (part == 1) {                     // this lane wrote the first half's sum: complete the run's partial row
+                        const float4 before = *reinterpret_cast<const float4 *>(p);
+                        r = make_float4(before.x + r.x, before.y + r.y, before.z + r.z, before.w + r.w);
+                    }
+                    *reinterpret_cast<float4 *>(p) = r;
+                }
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -532,6 +659,30 @@ int launch_dst_blocked(BlockedRelArgs args, int msg, cudaStream_t stream) {
     else { if (packed) ULTRA_BLOCKED(MSG_COPY, true); else ULTRA_BLOCKED(MSG_COPY, false); }
 #undef ULTRA_BLOCKED
 #undef ULTRA_BLOCKED_LAUNCH
+    note_launch();
+    return ULTRA_RSPMM_OK;
+}
+
+int launch_dst_blocked_gated(BlockedRelArgs args, int msg, cudaStream_t stream) {
+    if (args.n_rel == 0 || args.n_block == 0 || args.dim == 0) return ULTRA_RSPMM_OK;
+    const size_t smem = (size_t)(args.block_rows / 2) * 2 * kStagedSlab * sizeof(float);   // grad_output and output of half a block
+    if (smem > kStagedMaxSmem - 8192 || args.block_rows % 2 || !args.block_ptr || !args.counter || !args.O || !args.R ||
+        (msg != MSG_MUL && msg != MSG_ADD))
+        return ULTRA_RSPMM_ERR_ARG;
+    args.n_slab = (int)((args.dim + kStagedSlab - 1) / kStagedSlab);
+    int sms = 0;
+    if (int status = sm_count(&sms)) return status;
+    const long long items = (long long)args.n_block * args.n_slab;
+    ULTRA_CUDA_OK(cudaMemsetAsync(args.counter, 0, sizeof(unsigned), stream));
+#define ULTRA_GATED_LAUNCH(M, P)                                                                                               \
+    do {                                                                                                                       \
+        ULTRA_CUDA_OK(cudaFuncSetAttribute(dst_blocked_gated_kernel<M, P, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        dst_blocked_gated_kernel<M, P, 32><<<(items < sms ? (int)items : sms), 32 * 32, smem, stream>>>(args);                 \
+    } while (0)
+    const bool packed = args.packed != nullptr && args.pack_shift > 0;
+    if (msg == MSG_MUL) { if (packed) ULTRA_GATED_LAUNCH(MSG_MUL, true); else ULTRA_GATED_LAUNCH(MSG_MUL, false); }
+    else { if (packed) ULTRA_GATED_LAUNCH(MSG_ADD, true); else ULTRA_GATED_LAUNCH(MSG_ADD, false); }
+#undef ULTRA_GATED_LAUNCH
     note_launch();
     return ULTRA_RSPMM_OK;
 }
