@@ -160,3 +160,37 @@ def test_captured_finetune_step_equals_eager(cuda, monkeypatch):
     for a, b in zip(eager.parameters, captured.parameters):
         torch.testing.assert_close(b, a, rtol=1e-6, atol=1e-7)
     assert torch.isfinite(loss_captured)
+
+
+@pytest.mark.gpu
+def test_single_node_layers_give_the_gradients_of_the_three_node_layers(cuda, monkeypatch):
+    """Model level: the fine-tuning loss and every parameter gradient with each NBFNet layer as one autograd node
+    (`functional.nbf_layer`, the default) against the same step with the three separate nodes (ULTRA_NBF_SINGLE_NODE=0):
+    same kernels forward (equal loss), gradients equal up to the order in which the three contributions to a layer input's
+    gradient are added."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    monkeypatch.setattr(torch, "rand", lambda *shape, device=None, **unused: torch.full(shape, 0.61, device=device))
+    num_node, num_relation = 400, 6
+    triples = synthetic.triples(num_node, num_relation, 3000, seed=11)
+    graph = data.Graph(triples, num_node=num_node, num_relation=num_relation).to(cuda)
+    batch = triples[:12].to(cuda)
+
+    def gradients(single):
+        monkeypatch.setenv("ULTRA_NBF_SINGLE_NODE", "1" if single else "0")
+        torch.manual_seed(3)
+        model, rel_model = nbf.ultra_models(num_relation, hidden=64, num_layers=3)
+        step = task.FinetuneStep(model.to(cuda).train(), rel_model.to(cuda).train(), graph, num_negative=6)
+        loss = step.loss(batch)
+        loss.backward()
+        return loss.detach(), [None if p.grad is None else p.grad.clone() for p in step.parameters]
+
+    loss_single, grads_single = gradients(True)
+    loss_three, grads_three = gradients(False)
+    assert torch.equal(loss_single, loss_three)
+    assert sum(g is not None for g in grads_single) == sum(g is not None for g in grads_three) > 0
+    for a, b in zip(grads_single, grads_three):
+        if b is None:
+            assert a is None or float(a.abs().max()) == 0.0
+            continue
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()) + 1e-9)
+
