@@ -5,7 +5,7 @@
 //        forward   N = 64,  K = 128:  x = [input | update] @ W^T   (A0 = input, A1 = update: the cat is never materialised)
 //        grad rows N = 128, K = 64:   [d input | d update] = dx @ W  (A0 = dx, W passed transposed; the two 64-column
 //                                     halves go to two tensors, the first optionally + addend: the short-cut's gradient)
-//   ultra_layer_rows_gemm_weight   dW[n, k] = sum_r dx[r, n] * [A0[r, :] | A1[r, :]][k]   (mma.sync split over rows, fixed-order fold)
+//   ultra_layer_rows_gemm_weight   dW[n, k] = sum_r dx[r, n] * [A0[r, :] | A1[r, :]][k]   (tcgen05 with MN-major operands, fixed-order fold)
 //
 // rows_gemm_tc_kernel is the fused-Linear kernel of layer_linear_tc.cu with a plain epilogue: persistent CTAs, one per SM;
 // warp 0 = TMA producer (16 KB SWIZZLE_128B boxes of 32 columns x 128 rows into a ring of 3 slots, from one or two tensor
@@ -13,10 +13,14 @@
 // A from tensor memory, M 128, N 64 or 128, two accumulator stages in TMEM), warps 6-9 = epilogue (tcgen05.ld 64 columns at a time, staged through warp-private shared
 // memory, coalesced 16-byte stores).
 //
-// weight_grad_kernel reduces over millions of rows into a 64 x 128 result: persistent CTAs walk 64-row tiles (cp.async
+// weight_grad_tc_kernel: see its own header below.  weight_grad_kernel (the first version, ULTRA_WEIGHT_GRAD=mma) reduces over
+// millions of rows into a 64 x 128 result: persistent CTAs walk 64-row tiles (cp.async
 // double buffer), every warp owns a 16 x 64 block of the result in registers (mma.sync.m16n8k8 tf32, fragments gathered
 // from shared memory - the transposition dx^T costs nothing there), 3 MMAs per product; each CTA writes its partial
 // result, a second kernel folds the partials in CTA order: deterministic, no atomics.
+#include <cstdlib>
+#include <cstring>
+
 #include "tc_common.cuh"
 
 namespace ultra {
@@ -393,6 +397,176 @@ weight_grad_kernel(const float *__restrict__ dx, long long ld_dx, const float *_
     }
 }
 
+// ---- the weight gradient on tcgen05 ----------------------------------------------------------------------------------------
+// dW[n, k] = sum_r dx[r, n] J[r, k] is a GEMM whose reduction runs over the ROWS: both operands are MN-major (the row index is
+// the K index of the MMA), which tcgen05 takes directly from what TMA writes (32-column boxes in the 128B_ATOM_32B swizzle
+// mode = UMMA layout SWIZZLE_128B_BASE32B, the only one for MN-major tf32; a_major = b_major = 1).  Per 64-row tile a persistent CTA loads 6 boxes (dx: 2, J = [A0 | A1]: 4), the split warps rewrite them in
+// place as hi = tf32(x) and put lo = tf32(x - hi) behind them, and ONE thread issues per 8 rows two MMAs of M 128, N 128:
+//     [dx_hi ; dx_lo]^T (stacked along M: 4 atoms)  x  J_hi     and     [dx_hi ; dx_lo]^T  x  J_lo
+// - all four terms of (hi + lo)(hi + lo) with two full-size instructions.  The accumulator (128 lanes x 128 columns of
+// tensor memory) lives for the CTA's whole row range; at the end rows n and n + 64 (the hi and lo halves) are added and the
+// CTA writes its partial result; weight_grad_fold_kernel adds the partials in CTA order (deterministic, no atomics).
+namespace wt {
+constexpr int kTileRows = 64;
+constexpr int kStages = 2;
+constexpr int kAtomBytes = kTileRows * 128;                       // 32 columns x 64 rows
+constexpr int kAHi = 0, kALo = 2 * kAtomBytes, kBHi = 4 * kAtomBytes, kBLo = 8 * kAtomBytes;
+constexpr int kStageBytes = 12 * kAtomBytes;                      // 96 KB
+constexpr int kRawBytes = 6 * kAtomBytes;                         // what TMA delivers per tile
+constexpr int kBarrierOffset = kStages * kStageBytes;
+constexpr int kSmemBytes = kBarrierOffset + (3 * kStages + 1) * 8 + 16;
+constexpr int kThreads = 6 * 32;                                  // warp 0 TMA, warp 1 MMA, warps 2-5 split + epilogue
+constexpr int kScratchPitch = 132;
+// D = F32, A = B = TF32, both MN-major (bits 15, 16), N = 128 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
+constexpr unsigned kInstr = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+static_assert(kSmemBytes <= 227 * 1024, "does not fit shared memory");
+static_assert(64 * kScratchPitch * 4 <= kStageBytes, "epilogue scratch lives in stage 0");
+}  // namespace wt
+
+__global__ void __launch_bounds__(wt::kThreads, 1)
+weight_grad_tc_kernel(const __grid_constant__ CUtensorMap map_dx, const __grid_constant__ CUtensorMap map_a0,
+                      const __grid_constant__ CUtensorMap map_a1, long long rows, float *__restrict__ partial) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned bar_base = smem_base + wt::kBarrierOffset;
+    auto landed_bar = [&](int s) { return bar_base + 8u * s; };
+    auto full_bar = [&](int s) { return bar_base + 8u * (wt::kStages + s); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (2 * wt::kStages + s); };
+    const unsigned done_bar = bar_base + 8u * (3 * wt::kStages);
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem + wt::kBarrierOffset + (3 * wt::kStages + 1) * 8);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < wt::kStages; ++s) {
+            mbar_init(landed_bar(s), 1);
+            mbar_init(full_bar(s), 4);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+    const long long n_tiles = (rows + wt::kTileRows - 1) / wt::kTileRows;
+    const long long first = blockIdx.x;
+    const long long my_tiles = first < n_tiles ? (n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dx) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a1) : "memory");
+            for (long long t = 0; t < my_tiles; ++t) {
+                const int s = (int)(t % wt::kStages);
+                const int row0 = (int)((first + t * gridDim.x) * wt::kTileRows);
+                mbar_wait(empty_bar(s), (unsigned)((t / wt::kStages) & 1) ^ 1u);
+                mbar_expect_tx(landed_bar(s), wt::kRawBytes);
+                const unsigned at = smem_base + s * wt::kStageBytes;
+                tma_load_2d(at + wt::kAHi, &map_dx, 0, row0, landed_bar(s));          // rows past the end: zeros
+                tma_load_2d(at + wt::kAHi + wt::kAtomBytes, &map_dx, 32, row0, landed_bar(s));
+                tma_load_2d(at + wt::kBHi, &map_a0, 0, row0, landed_bar(s));
+                tma_load_2d(at + wt::kBHi + wt::kAtomBytes, &map_a0, 32, row0, landed_bar(s));
+                tma_load_2d(at + wt::kBHi + 2 * wt::kAtomBytes, &map_a1, 0, row0, landed_bar(s));
+                tma_load_2d(at + wt::kBHi + 3 * wt::kAtomBytes, &map_a1, 32, row0, landed_bar(s));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (long long t = 0; t < my_tiles; ++t) {
+                const int s = (int)(t % wt::kStages);
+                mbar_wait(full_bar(s), (unsigned)((t / wt::kStages) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned at = smem_base + s * wt::kStageBytes;
+#pragma unroll
+                for (int ks = 0; ks < wt::kTileRows / 8; ++ks) {
+                    const unsigned long long a = umma_desc_mn_sw128_32b(at + wt::kAHi + ks * 1024, wt::kAtomBytes);   // hi, hi, lo, lo atoms
+                    const unsigned long long b_hi = umma_desc_mn_sw128_32b(at + wt::kBHi + ks * 1024, wt::kAtomBytes);
+                    const unsigned long long b_lo = umma_desc_mn_sw128_32b(at + wt::kBLo + ks * 1024, wt::kAtomBytes);
+                    umma_tf32(tmem_base, a, b_lo, wt::kInstr, (t > 0 || ks > 0) ? 1u : 0u);
+                    umma_tf32(tmem_base, a, b_hi, wt::kInstr, 1u);
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(done_bar);
+        }
+    } else {
+        // ---- split: hi in place, lo behind it (elementwise: the swizzled positions carry over) -------------------------
+        const int t128 = tid - 64;
+        for (long long t = 0; t < my_tiles; ++t) {
+            const int s = (int)(t % wt::kStages);
+            mbar_wait(landed_bar(s), (unsigned)((t / wt::kStages) & 1));
+            unsigned char *at = smem + s * wt::kStageBytes;
+            constexpr int kChunks = wt::kRawBytes / 16 / 128;              // 24 chunks of 16 bytes per thread
+#pragma unroll 4
+            for (int q = 0; q < kChunks; ++q) {
+                const int chunk = t128 + q * 128;                         // [0, 1024): dx, [1024, 3072): J
+                const bool is_a = chunk < 2 * wt::kAtomBytes / 16;
+                unsigned char *hi_at = at + (is_a ? wt::kAHi + chunk * 16 : wt::kBHi + (chunk - 2 * wt::kAtomBytes / 16) * 16);
+                const int lo_offset = is_a ? wt::kALo - wt::kAHi : wt::kBLo - wt::kBHi;
+                const float4 x = *reinterpret_cast<const float4 *>(hi_at);
+                const float4 hi = make_float4(tc_tf32(x.x), tc_tf32(x.y), tc_tf32(x.z), tc_tf32(x.w));
+                const float4 lo = make_float4(tc_tf32(x.x - hi.x), tc_tf32(x.y - hi.y), tc_tf32(x.z - hi.z), tc_tf32(x.w - hi.w));
+                *reinterpret_cast<float4 *>(hi_at) = hi;
+                *reinterpret_cast<float4 *>(hi_at + lo_offset) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(s));
+        }
+        // ---- epilogue: rows n (hi half) + n + 64 (lo half) of the accumulator -> this CTA's partial result --------------
+        const int quadrant = warp & 3, row = 32 * quadrant + lane;        // TMEM lane = row of the stacked operand
+        float *scratch = reinterpret_cast<float *>(smem);
+        float *mine = partial + (long long)blockIdx.x * 64 * 128;
+        if (my_tiles > 0) {
+            mbar_wait(done_bar, 0u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float v[64];
+            if (my_tiles > 0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float part[16];
+                    tmem_load16(tmem_base + ((unsigned)(32 * quadrant) << 16) + (unsigned)(64 * h + 16 * c), part);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[16 * c + i] = part[i];
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) v[i] = 0.f;
+            }
+            if (row >= 64) {
+#pragma unroll
+                for (int c = 0; c < 64; c += 4)
+                    *reinterpret_cast<float4 *>(scratch + (row - 64) * wt::kScratchPitch + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (row < 64) {
+#pragma unroll
+                for (int c = 0; c < 64; c += 4) {
+                    const float4 lo = *reinterpret_cast<const float4 *>(scratch + row * wt::kScratchPitch + c);
+                    *reinterpret_cast<float4 *>(mine + row * 128 + 64 * h + c) = make_float4(v[c] + lo.x, v[c + 1] + lo.y, v[c + 2] + lo.z, v[c + 3] + lo.w);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    }
+}
+
 __global__ void weight_grad_fold_kernel(const float *__restrict__ partial, int n_partial, float *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 64 * 128) return;
@@ -454,8 +628,19 @@ extern "C" int ultra_layer_rows_gemm_weight(const float *dev_dx, int64_t ld_dx, 
     if (grid > 256) grid = 256;
     if (grid < 1) grid = 1;
     if (!workspace || workspace_bytes < (size_t)grid * 64 * 128 * sizeof(float)) return ULTRA_RSPMM_ERR_WORKSPACE;
-    ULTRA_CUDA_OK(cudaFuncSetAttribute(weight_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes));
-    weight_grad_kernel<<<grid, wg::kThreads, wg::kSmemBytes, s>>>(dev_dx, ld_dx, dev_a0, lda0, dev_a1, lda1, rows, (float *)workspace);
+    // ULTRA_WEIGHT_GRAD=mma keeps the mma.sync kernel (the first version: bound by the legacy tensor pipe at 3.5 TB/s)
+    static const bool legacy = getenv("ULTRA_WEIGHT_GRAD") && !strcmp(getenv("ULTRA_WEIGHT_GRAD"), "mma");
+    if (legacy || rows == 0) {
+        ULTRA_CUDA_OK(cudaFuncSetAttribute(weight_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes));
+        weight_grad_kernel<<<grid, wg::kThreads, wg::kSmemBytes, s>>>(dev_dx, ld_dx, dev_a0, lda0, dev_a1, lda1, rows, (float *)workspace);
+    } else {
+        CUtensorMap map_dx, map_a0, map_a1;
+        if (int status = encode_rows_map(&map_dx, dev_dx, rows, 64, ld_dx, wt::kTileRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return status;
+        if (int status = encode_rows_map(&map_a0, dev_a0, rows, 64, lda0, wt::kTileRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return status;
+        if (int status = encode_rows_map(&map_a1, dev_a1, rows, 64, lda1, wt::kTileRows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return status;
+        ULTRA_CUDA_OK(cudaFuncSetAttribute(weight_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wt::kSmemBytes));
+        weight_grad_tc_kernel<<<grid, wt::kThreads, wt::kSmemBytes, s>>>(map_dx, map_a0, map_a1, rows, (float *)workspace);
+    }
     note_launch();
     weight_grad_fold_kernel<<<(64 * 128 + 255) / 256, 256, 0, s>>>((const float *)workspace, grid, dev_weight_grad);
     note_launch();

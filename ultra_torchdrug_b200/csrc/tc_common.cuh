@@ -46,6 +46,16 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr, unsi
 __device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned smem_addr) {
     return (unsigned long long)((smem_addr >> 4) & 0x3fff) | ((unsigned long long)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major tf32 operand.  The only shared-memory layout tcgen05 takes for it is SWIZZLE_128B_BASE32B (layout type 1; with
+// plain SWIZZLE_128B the MMAs return zeros): atoms of 32 tf32 along M / N (128 contiguous bytes) x 4 K rows 128 bytes
+// apart, the four 32-byte chunks of a row XOR-ed with row % 4 - what TMA writes for a 32-column box in the
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B mode (the K index is the box row).  LBO = byte distance between atoms along M / N,
+// SBO = between 4-row K groups (512 bytes when the rows are contiguous).  Needs a_major / b_major = 1 in the instruction
+// descriptor.
+__device__ __forceinline__ unsigned long long umma_desc_mn_sw128_32b(unsigned smem_addr, unsigned lbo_bytes) {
+    return (unsigned long long)((smem_addr >> 4) & 0x3fff) | ((unsigned long long)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((unsigned long long)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
 __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -115,16 +125,17 @@ inline int encode_tiled(EncodeTiled *out) {
 }
 
 
-// (rows, cols) fp32 matrix with rows `ld` floats apart as a 2-D tensor, box = 32 columns x 128 rows, SWIZZLE_128B
-inline int encode_rows_map(CUtensorMap *map, const float *base, long long rows, long long cols, long long ld) {
+// (rows, cols) fp32 matrix with rows `ld` floats apart as a 2-D tensor, box = 32 columns x box_rows rows, SWIZZLE_128B
+inline int encode_rows_map(CUtensorMap *map, const float *base, long long rows, long long cols, long long ld, unsigned box_rows = 128,
+                           CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiled encode = nullptr;
     if (int status = encode_tiled(&encode)) return status;
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    const cuuint32_t box[2] = {32u, 128u};
+    const cuuint32_t box[2] = {32u, box_rows};
     const cuuint32_t element_strides[2] = {1, 1};
     if (encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, element_strides, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+               swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return fail_cuda(cudaErrorInvalidValue);
     return ULTRA_RSPMM_OK;
 }
