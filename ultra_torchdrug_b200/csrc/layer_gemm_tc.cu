@@ -406,9 +406,13 @@ weight_grad_kernel(const float *__restrict__ dx, long long ld_dx, const float *_
 // - all four terms of (hi + lo)(hi + lo) with two full-size instructions.  The accumulator (128 lanes x 128 columns of
 // tensor memory) lives for the CTA's whole row range; at the end rows n and n + 64 (the hi and lo halves) are added and the
 // CTA writes its partial result; weight_grad_fold_kernel adds the partials in CTA order (deterministic, no atomics).
+#ifndef WT_ROWS
+#define WT_ROWS 64
+#define WT_STAGES 2
+#endif
 namespace wt {
-constexpr int kTileRows = 64;
-constexpr int kStages = 2;
+constexpr int kTileRows = WT_ROWS;
+constexpr int kStages = WT_STAGES;
 constexpr int kAtomBytes = kTileRows * 128;                       // 32 columns x 64 rows
 constexpr int kAHi = 0, kALo = 2 * kAtomBytes, kBHi = 4 * kAtomBytes, kBLo = 8 * kAtomBytes;
 constexpr int kStageBytes = 12 * kAtomBytes;                      // 96 KB
