@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ULTRA_RSPMM_ABI_VERSION 6
+#define ULTRA_RSPMM_ABI_VERSION 7
 
 /* status codes (0 = ok).  For ULTRA_RSPMM_ERR_CUDA the cudaError_t is kept per thread, see
  * ultra_rspmm_last_cuda_error(). */
@@ -333,6 +333,14 @@ int ultra_layer_linear_norm_relu_residual_two(const float *dev_input, int64_t in
                                               const float *dev_gamma, const float *dev_beta, float *dev_out,
                                               int64_t out_stride, int64_t rows, int32_t out_dim, float eps, int32_t relu,
                                               int32_t shortcut, void *stream);
+/* The same with a second output: dev_pre_out[r, 0:out_dim] = the Linear's output WITHOUT its bias (the accumulators), which
+ * the backward of the layer epilogue (ultra_layer_norm_relu_residual_backward) needs - the training forward of a layer is
+ * then one kernel instead of a GEMM and an epilogue pass. */
+int ultra_layer_linear_norm_relu_residual_two_pre(const float *dev_input, int64_t input_stride, const float *dev_update,
+                                                  int64_t update_stride, const float *dev_weight, const float *dev_linear_bias,
+                                                  const float *dev_gamma, const float *dev_beta, float *dev_out,
+                                                  int64_t out_stride, float *dev_pre_out, int64_t pre_stride, int64_t rows,
+                                                  int32_t out_dim, float eps, int32_t relu, int32_t shortcut, void *stream);
 
 /* ---- the Linear of `combine` under autograd (fine-tuning; reference layer.py:386-392) on the tensor cores -------------------
  * fp32 accuracy through the 3xTF32 split, no cuBLAS SIMT SGEMM, no `cat([input, update])`.

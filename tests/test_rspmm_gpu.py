@@ -1059,9 +1059,8 @@ def test_combine_linear_forward_and_backward_have_fp32_accuracy(cuda, rows):
 def test_single_node_layer_equals_three_node_layer(cuda, nodes, batch, relations, mul, shortcut):
     """`nbf_layer` (operator + Linear + LayerNorm/ReLU/short-cut as ONE autograd node whose backward folds the three
     gradients of the layer input into the kernels) against the composition of the three separate nodes
-    (`rspmm_add_one_hot`, `combine_linear`, `layer_norm_relu_residual`): the forward runs the same kernels (bit-equal), the
-    gradients differ only in the order the three contributions to d input are added; and `backward(input_addend=...)`
-    against backward + add."""
+    (`rspmm_add_one_hot`, `combine_linear`, `layer_norm_relu_residual`): same arithmetic up to summation order, forward and
+    all seven gradients, bit-reproducible; and `backward(input_addend=...)` against backward + add."""
     from ultra_torchdrug_b200 import functional as F, synthetic
     generator = torch.Generator().manual_seed(nodes)
     edges = torch.stack([torch.randint(nodes, (nodes * 6,), generator=generator), torch.randint(nodes, (nodes * 6,), generator=generator),
@@ -1090,7 +1089,9 @@ def test_single_node_layer_equals_three_node_layer(cuda, nodes, batch, relations
     want, want_grads = grads(three_nodes)
     got, got_grads = grads(lambda: F.nbf_layer(sparse, relation, x, node_index, query, weight, linear_bias, gamma, beta, mul, 1e-5,
                                                True, shortcut))
-    assert torch.equal(got, want)
+    # the single node's forward is ONE kernel (Linear + LayerNorm + ReLU + short-cut, also returning the Linear's output); the
+    # three nodes run a GEMM and an epilogue kernel whose row statistics are summed in another order
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
     for name, a, b in zip(("x", "relation", "query", "weight", "linear_bias", "gamma", "beta"), got_grads, want_grads):
         torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5 * float(b.abs().max()), msg=lambda m, name=name: name + ": " + m)
     again, again_grads = grads(lambda: F.nbf_layer(sparse, relation, x, node_index, query, weight, linear_bias, gamma, beta, mul,

@@ -166,8 +166,8 @@ def test_captured_finetune_step_equals_eager(cuda, monkeypatch):
 def test_single_node_layers_give_the_gradients_of_the_three_node_layers(cuda, monkeypatch):
     """Model level: the fine-tuning loss and every parameter gradient with each NBFNet layer as one autograd node
     (`functional.nbf_layer`, the default) against the same step with the three separate nodes (ULTRA_NBF_SINGLE_NODE=0):
-    same kernels forward (equal loss), gradients equal up to the order in which the three contributions to a layer input's
-    gradient are added."""
+    the same arithmetic up to summation order (row statistics of the fused forward kernel, the three contributions to a
+    layer input's gradient)."""
     torch.backends.cuda.matmul.allow_tf32 = False
     monkeypatch.setattr(torch, "rand", lambda *shape, device=None, **unused: torch.full(shape, 0.61, device=device))
     num_node, num_relation = 400, 6
@@ -186,7 +186,7 @@ def test_single_node_layers_give_the_gradients_of_the_three_node_layers(cuda, mo
 
     loss_single, grads_single = gradients(True)
     loss_three, grads_three = gradients(False)
-    assert torch.equal(loss_single, loss_three)
+    torch.testing.assert_close(loss_single, loss_three, rtol=1e-5, atol=1e-7)
     assert sum(g is not None for g in grads_single) == sum(g is not None for g in grads_three) > 0
     for a, b in zip(grads_single, grads_three):
         if b is None:

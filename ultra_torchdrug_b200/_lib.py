@@ -8,7 +8,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 OK, ERR_ARG, ERR_WORKSPACE, ERR_CUDA, ERR_INDEX, ERR_DTYPE, ERR_RANGE = range(7)
 SUM_CODE = {"add": 0, "min": 1, "max": 2}
@@ -112,6 +112,9 @@ SYMBOLS = {
     "ultra_layer_linear_norm_relu_residual_two": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                                                  c_void_p, c_void_p, c_int64, c_int64, c_int32, ctypes.c_float,
                                                                  c_int32, c_int32, c_void_p]),
+    "ultra_layer_linear_norm_relu_residual_two_pre": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                                                                     c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                                                     c_int64, c_int32, ctypes.c_float, c_int32, c_int32, c_void_p]),
     "ultra_layer_linear_set_kernel": (ctypes.c_int, [c_int32]),
     "ultra_layer_linear_get_kernel": (ctypes.c_int, []),
     "ultra_layer_linear_set_debug": (ctypes.c_int, [c_void_p]),

@@ -348,7 +348,7 @@ namespace ultra {
 // layer_linear_tc.cu
 int layer_linear_tc(const float *A, long long lda, const float *A1, long long lda1, const float *W, const float *linear_bias, const float *gamma,
                     const float *beta, float *out, long long ldo, long long rows, int out_dim, float eps, int relu,
-                    int shortcut, cudaStream_t stream);
+                    int shortcut, cudaStream_t stream, float *pre_out = nullptr, long long ld_pre = 0);
 int g_linear_kernel = 0;   // 0 = default, 1 = mma.sync, 2 = tcgen05
 }  // namespace ultra
 
@@ -406,6 +406,27 @@ extern "C" int ultra_layer_linear_norm_relu_residual_two(const float *dev_input,
     if (rows == 0) return ULTRA_RSPMM_OK;
     return layer_linear_tc(dev_input, input_stride, dev_update, update_stride, dev_weight, dev_linear_bias, dev_gamma, dev_beta,
                            dev_out, out_stride, rows, out_dim, eps, relu, shortcut, (cudaStream_t)stream);
+}
+
+extern "C" int ultra_layer_linear_norm_relu_residual_two_pre(const float *dev_input, int64_t input_stride, const float *dev_update,
+                                                             int64_t update_stride, const float *dev_weight,
+                                                             const float *dev_linear_bias, const float *dev_gamma,
+                                                             const float *dev_beta, float *dev_out, int64_t out_stride,
+                                                             float *dev_pre_out, int64_t pre_stride, int64_t rows, int32_t out_dim,
+                                                             float eps, int32_t relu, int32_t shortcut, void *stream) {
+    if (!dev_pre_out || pre_stride < out_dim || pre_stride % 4 || ((uintptr_t)dev_pre_out & 15)) return ULTRA_RSPMM_ERR_ARG;
+    if (rows < 0 || (rows > 0 && (!dev_input || !dev_update || !dev_weight || !dev_out))) return ULTRA_RSPMM_ERR_ARG;
+    if ((dev_gamma == nullptr) != (dev_beta == nullptr)) return ULTRA_RSPMM_ERR_ARG;
+    if (out_dim != 32 && out_dim != 64) return ULTRA_RSPMM_ERR_RANGE;
+    if (input_stride < out_dim || input_stride % 4 || update_stride < out_dim || update_stride % 4 || out_stride < out_dim ||
+        out_stride % 4)
+        return ULTRA_RSPMM_ERR_ARG;
+    if (((uintptr_t)dev_input | (uintptr_t)dev_update | (uintptr_t)dev_out | (uintptr_t)dev_linear_bias | (uintptr_t)dev_gamma |
+         (uintptr_t)dev_beta | (uintptr_t)dev_weight) & 15)
+        return ULTRA_RSPMM_ERR_ARG;
+    if (rows == 0) return ULTRA_RSPMM_OK;
+    return layer_linear_tc(dev_input, input_stride, dev_update, update_stride, dev_weight, dev_linear_bias, dev_gamma, dev_beta,
+                           dev_out, out_stride, rows, out_dim, eps, relu, shortcut, (cudaStream_t)stream, dev_pre_out, pre_stride);
 }
 
 extern "C" int ultra_score_head_linear(const float *dev_input, int64_t input_stride, const float *dev_weight,

@@ -87,14 +87,17 @@ template <int N, int HI, int LO, bool TS> struct Shape {
 };
 }  // namespace tc
 
-template <int N, int HI, int LO, bool TS>
+template <int N, int HI, int LO, bool TS, bool PRE>   // PRE: also write the Linear's output (training forward)
+// 10 warps = 3 on two of the four SM sub-partitions: 16,384 / 3 / 32 = 170 registers per thread is the most a launch can
+// get (ptxas stops at 168; __maxnreg__(192) compiles but fails to launch)
 __global__ void __launch_bounds__(tc::kThreads, 1)
 linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap a_map2,
                                     int two_sources, const float *__restrict__ A, long long lda,
                                     const float *__restrict__ W,
                                     const float *__restrict__ linear_bias, const float *__restrict__ gamma,
                                     const float *__restrict__ beta, float *__restrict__ out, long long ldo, long long rows,
-                                    float eps, int relu, int shortcut, long long *debug) {
+                                    float eps, int relu, int shortcut, long long *debug, float *__restrict__ pre_out,
+                                    long long ld_pre) {
     using S = tc::Shape<N, HI, LO, TS>;
 #ifdef ULTRA_LINEAR_KNOCKOUT
     const int knock = g_knock;
@@ -319,10 +322,12 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
         float *staged = reinterpret_cast<float *>(smem + S::kStagingOffset) + quadrant * 32 * kStride;
         const int my_chunk = lane % kChunks, sub_row = lane / kChunks;
         float4 scale = make_float4(1.f, 1.f, 1.f, 1.f), shift = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gamma) {
             scale = __ldg(reinterpret_cast<const float4 *>(gamma + 4 * my_chunk));
             shift = __ldg(reinterpret_cast<const float4 *>(beta + 4 * my_chunk));
         }
+        if (linear_bias) bias4 = __ldg(reinterpret_cast<const float4 *>(linear_bias + 4 * my_chunk));
         constexpr float inv = 1.0f / N;
         for (long long t = 0; t < my_tiles; ++t) {
             const int stage = (int)(t & 1);
@@ -346,26 +351,54 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
                 if (v[0] + v[N - 1] == 123.456f) out[0] = v[0];
                 continue;
             }
-            float sum = 0.f;
+            float mean = 0.f, rstd = 0.f;
+            if constexpr (PRE) {
+                // the accumulators themselves (the Linear's output without its bias) are what is staged - a training caller keeps
+                // them for the backward (pre_out) - the bias and the mean are applied again in the write-back phase, with the
+                // same operations in the same order
+                float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < N; c += 4) {
-                if (linear_bias) {
-                    const float4 lb = __ldg(reinterpret_cast<const float4 *>(linear_bias + c));
-                    v[c] += lb.x; v[c + 1] += lb.y; v[c + 2] += lb.z; v[c + 3] += lb.w;
+                for (int c = 0; c < N; c += 4) {
+                    float4 lb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (linear_bias) lb = __ldg(reinterpret_cast<const float4 *>(linear_bias + c));
+                    sum += ((v[c] + lb.x) + (v[c + 1] + lb.y)) + ((v[c + 2] + lb.z) + (v[c + 3] + lb.w));
                 }
-                sum += (v[c] + v[c + 1]) + (v[c + 2] + v[c + 3]);
-            }
-            const float mean = sum * inv;
-            float sq = 0.f;
+                mean = sum * inv;
+                float sq = 0.f;
 #pragma unroll
-            for (int c = 0; c < N; ++c) {
-                v[c] -= mean;
-                sq = fmaf(v[c], v[c], sq);
-            }
-            const float rstd = rsqrtf(sq * inv + eps);
+                for (int c = 0; c < N; c += 4) {
+                    float4 lb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (linear_bias) lb = __ldg(reinterpret_cast<const float4 *>(linear_bias + c));
+                    const float c0 = (v[c] + lb.x) - mean, c1 = (v[c + 1] + lb.y) - mean, c2 = (v[c + 2] + lb.z) - mean,
+                                c3 = (v[c + 3] + lb.w) - mean;
+                    sq = fmaf(c0, c0, sq); sq = fmaf(c1, c1, sq); sq = fmaf(c2, c2, sq); sq = fmaf(c3, c3, sq);
+                }
+                rstd = rsqrtf(sq * inv + eps);
 #pragma unroll
-            for (int c = 0; c < N; c += 4)
-                *reinterpret_cast<float4 *>(staged + lane * kStride + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                for (int c = 0; c < N; c += 4)
+                    *reinterpret_cast<float4 *>(staged + lane * kStride + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            } else {
+                float sum = 0.f;
+#pragma unroll
+                for (int c = 0; c < N; c += 4) {
+                    if (linear_bias) {
+                        const float4 lb = __ldg(reinterpret_cast<const float4 *>(linear_bias + c));
+                        v[c] += lb.x; v[c + 1] += lb.y; v[c + 2] += lb.z; v[c + 3] += lb.w;
+                    }
+                    sum += (v[c] + v[c + 1]) + (v[c + 2] + v[c + 3]);
+                }
+                mean = sum * inv;
+                float sq = 0.f;
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    v[c] -= mean;
+                    sq = fmaf(v[c], v[c], sq);
+                }
+                rstd = rsqrtf(sq * inv + eps);
+#pragma unroll
+                for (int c = 0; c < N; c += 4)
+                    *reinterpret_cast<float4 *>(staged + lane * kStride + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            }
             __syncwarp();
             constexpr int kPasses = 32 / kRowsPerPass;
             float4 skip[kPasses];                                        // all short-cut loads in flight before the first use
@@ -378,8 +411,16 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
 #pragma unroll
             for (int pass = 0; pass < kPasses; ++pass) {
                 const int r = pass * kRowsPerPass + sub_row;
+                float4 x;
                 const float rs = __shfl_sync(kFullMask, rstd, r);
-                const float4 x = *reinterpret_cast<const float4 *>(staged + r * kStride + 4 * my_chunk);
+                if constexpr (PRE) {
+                    const float mu = __shfl_sync(kFullMask, mean, r);
+                    const float4 raw = *reinterpret_cast<const float4 *>(staged + r * kStride + 4 * my_chunk);
+                    if (pre_out && row0 + r < rows) __stcs(reinterpret_cast<float4 *>(pre_out + (row0 + r) * ld_pre + 4 * my_chunk), raw);
+                    x = make_float4((raw.x + bias4.x) - mu, (raw.y + bias4.y) - mu, (raw.z + bias4.z) - mu, (raw.w + bias4.w) - mu);
+                } else {
+                    x = *reinterpret_cast<const float4 *>(staged + r * kStride + 4 * my_chunk);
+                }
                 float4 y = make_float4(fmaf(x.x * rs, scale.x, shift.x), fmaf(x.y * rs, scale.y, shift.y),
                                        fmaf(x.z * rs, scale.z, shift.z), fmaf(x.w * rs, scale.w, shift.w));
                 if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
@@ -408,12 +449,12 @@ linear_norm_relu_residual_tc_kernel(const __grid_constant__ CUtensorMap a_map, c
     }
 }
 
-template <int N, int HI, int LO, bool TS>
+template <int N, int HI, int LO, bool TS, bool PRE>
 int launch_linear_tc(const float *A, long long lda, const float *A1, long long lda1, const float *W, const float *linear_bias, const float *gamma,
                      const float *beta, float *out, long long ldo, long long rows, float eps, int relu, int shortcut,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, float *pre_out, long long ld_pre) {
     using S = tc::Shape<N, HI, LO, TS>;
-    auto kernel = linear_norm_relu_residual_tc_kernel<N, HI, LO, TS>;
+    auto kernel = linear_norm_relu_residual_tc_kernel<N, HI, LO, TS, PRE>;
     int device = 0, sm_count = 0;
     ULTRA_CUDA_OK(cudaGetDevice(&device));
     ULTRA_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -430,7 +471,7 @@ int launch_linear_tc(const float *A, long long lda, const float *A1, long long l
     ULTRA_CUDA_OK(cudaMemcpyToSymbolAsync(g_knock, &knock, sizeof(int), 0, cudaMemcpyHostToDevice, stream));
 #endif
     kernel<<<grid, tc::kThreads, S::kSmemBytes, stream>>>(map, map2, two ? 1 : 0, A, lda, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu,
-                                                         shortcut, g_linear_debug);
+                                                         shortcut, g_linear_debug, pre_out, ld_pre);
     note_launch();
     ULTRA_CUDA_OK(cudaGetLastError());
     return ULTRA_RSPMM_OK;
@@ -441,11 +482,14 @@ int launch_linear_tc(const float *A, long long lda, const float *A1, long long l
 // called by ultra_layer_linear_norm_relu_residual (layer_linear.cu) after its argument checks
 int layer_linear_tc(const float *A, long long lda, const float *A1, long long lda1, const float *W, const float *linear_bias, const float *gamma,
                     const float *beta, float *out, long long ldo, long long rows, int out_dim, float eps, int relu,
-                    int shortcut, cudaStream_t stream) {
+                    int shortcut, cudaStream_t stream, float *pre_out, long long ld_pre) {
     // ULTRA_LINEAR_RING (development knob): "<ring slots><A slots>" with A in tensor memory, or 133 = the first version
     // (hi / lo tiles in shared memory, both operands read from there)
     static const int ring = getenv("ULTRA_LINEAR_RING") ? atoi(getenv("ULTRA_LINEAR_RING")) : 32;
-#define ULTRA_TC(N, HI, LO, TS) launch_linear_tc<N, HI, LO, TS>(A, lda, A1, lda1, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu, shortcut, stream)
+#define ULTRA_TC(N, HI, LO, TS) launch_linear_tc<N, HI, LO, TS, false>(A, lda, A1, lda1, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu, shortcut, stream, pre_out, ld_pre)
+    if (pre_out)    // training forward: default ring only
+        return out_dim == 64 ? launch_linear_tc<64, 3, 2, true, true>(A, lda, A1, lda1, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu, shortcut, stream, pre_out, ld_pre)
+                             : launch_linear_tc<32, 3, 2, true, true>(A, lda, A1, lda1, W, linear_bias, gamma, beta, out, ldo, rows, eps, relu, shortcut, stream, pre_out, ld_pre);
     if (out_dim == 64) {
         switch (ring) {
             case 133: return ULTRA_TC(64, 3, 3, false);

@@ -684,11 +684,22 @@ class NBFLayerFunction(torch.autograd.Function):
         w = weight.detach().contiguous()
         rows = num_node * batch
         lin = torch.empty_like(x)
-        with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().ultra_layer_rows_gemm(_ptr(x), 64, _ptr(update), 64, _ptr(w), _ptr(lin), 64, None, 0, None, 0, rows,
-                                                        64, 128, _stream_handle()), "ultra_layer_rows_gemm")
         small = [None if t is None else t.detach().contiguous() for t in (linear_bias, gamma, beta)]
-        out = _epilogue_forward(lin, small[0], small[1], small[2], x if shortcut else None, eps, relu)
+        lib = _lib.lib()
+        if (small[1] is None) == (small[2] is None) and lib.ultra_layer_linear_get_kernel() == 2 and \
+                os.environ.get("ULTRA_NBF_FUSED_FORWARD", "1") != "0":
+            # Linear + bias + LayerNorm + ReLU + short-cut in one kernel that also returns the Linear's output for the backward
+            out = torch.empty_like(x)
+            with torch.cuda.device(x.device):
+                _lib.check(lib.ultra_layer_linear_norm_relu_residual_two_pre(
+                    _ptr(x), 64, _ptr(update), 64, _ptr(w), _ptr(small[0]), _ptr(small[1]), _ptr(small[2]), _ptr(out), 64, _ptr(lin), 64,
+                    rows, 64, float(eps), int(bool(relu)), int(bool(shortcut)), _stream_handle()),
+                    "ultra_layer_linear_norm_relu_residual_two_pre")
+        else:
+            with torch.cuda.device(x.device):
+                _lib.check(lib.ultra_layer_rows_gemm(_ptr(x), 64, _ptr(update), 64, _ptr(w), _ptr(lin), 64, None, 0, None, 0, rows,
+                                                     64, 128, _stream_handle()), "ultra_layer_rows_gemm")
+            out = _epilogue_forward(lin, small[0], small[1], small[2], x if shortcut else None, eps, relu)
         ctx.index, ctx.mul, ctx.eps, ctx.relu, ctx.shortcut = index, mul, eps, relu, shortcut
         ctx.present = [t is not None for t in small]
         ctx.save_for_backward(relation, x, update, lin, w, node_index, *[t if t is not None else x.new_empty(0) for t in small])
