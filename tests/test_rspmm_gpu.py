@@ -1113,8 +1113,8 @@ def test_single_node_layer_equals_three_node_layer(cuda, nodes, batch, relations
 def test_parity_randomized_specialised_kernels(cuda, seed):
     """Seeded random shapes through the kernels that production selects only on particular graphs, all forced on here:
     rows-in-shared-memory / pair kernels (few rows; pairs need <= 4 relation types and unit weights), the
-    destination-blocked grad_relation, the sub-warp rows kernel.  Sum aggregation (the only one they serve), both
-    message functions, ragged widths, duplicates, split rows."""
+    destination-blocked grad_relation (sum, and its gated min / max form), the sub-warp rows kernel.  Both message functions,
+    ragged widths, duplicates, split rows."""
     from ultra_torchdrug_b200 import functional as F, _lib
     rng = np.random.default_rng(5000 + seed)
     family = ("pairs", "staged", "blocked", "subwarp")[seed % 4]
@@ -1158,6 +1158,18 @@ def test_parity_randomized_specialised_kernels(cuda, seed):
                                            "add", mul, dtype=np.float64)
         _assert_sum_close(g_rel.cpu().numpy(), e_rel, s_rel, "%s grad_relation" % family)
         _assert_sum_close(g_in.cpu().numpy(), e_in, s_in, "%s grad_input" % family)
+        if family == "blocked" and indices.shape[1] and dim % 4 == 0:
+            # the gated (min / max) form of the destination-blocked pass on the same graph
+            extremum = ("max", "min")[(seed // 8) % 2]
+            m_out = index.forward(d_rel, d_in, extremum, mul)
+            m_rel, m_in = index.backward(d_rel, d_in, m_out, d_grad, extremum, mul)
+            assert _lib.pass_info(_lib.PASS_GRAD_RELATION)["kernel_name"] == "dst_blocked_gated"
+            m_np = m_out.cpu().numpy()
+            e_rel, e_in = util.oracle_backward(indices, values, shape, relation, input, m_np, grad, extremum, mul, dtype=np.float64)
+            s_rel, s_in = util.oracle_backward(indices, np.abs(values), shape, np.abs(relation), np.abs(input), m_np, np.abs(grad),
+                                               "add", mul, dtype=np.float64)
+            _assert_sum_close(m_rel.cpu().numpy(), e_rel, s_rel, "blocked gated grad_relation (%s)" % extremum)
+            _assert_sum_close(m_in.cpu().numpy(), e_in, s_in, "gated grad_input (%s)" % extremum)
     finally:
         lib.ultra_rspmm_set_tuning(256, 0, 0)
         _lib.check(lib.ultra_rspmm_set_extensions(1, 1), "set_extensions")
