@@ -400,15 +400,18 @@ weight_grad_kernel(const float *__restrict__ dx, long long ld_dx, const float *_
 // ---- the weight gradient on tcgen05 ----------------------------------------------------------------------------------------
 // dW[n, k] = sum_r dx[r, n] J[r, k] is a GEMM whose reduction runs over the ROWS: both operands are MN-major (the row index is
 // the K index of the MMA), which tcgen05 takes directly from what TMA writes (32-column boxes in the 128B_ATOM_32B swizzle
-// mode = UMMA layout SWIZZLE_128B_BASE32B, the only one for MN-major tf32; a_major = b_major = 1).  Per 64-row tile a persistent CTA loads 6 boxes (dx: 2, J = [A0 | A1]: 4), the split warps rewrite them in
+// mode = UMMA layout SWIZZLE_128B_BASE32B, the only one for MN-major tf32; a_major = b_major = 1).  Per 32-row tile a persistent CTA (two per SM) loads 6 boxes (dx: 2, J = [A0 | A1]: 4), the split warps rewrite them in
 // place as hi = tf32(x) and put lo = tf32(x - hi) behind them, and ONE thread issues per 8 rows two MMAs of M 128, N 128:
 //     [dx_hi ; dx_lo]^T (stacked along M: 4 atoms)  x  J_hi     and     [dx_hi ; dx_lo]^T  x  J_lo
 // - all four terms of (hi + lo)(hi + lo) with two full-size instructions.  The accumulator (128 lanes x 128 columns of
 // tensor memory) lives for the CTA's whole row range; at the end rows n and n + 64 (the hi and lo halves) are added and the
 // CTA writes its partial result; weight_grad_fold_kernel adds the partials in CTA order (deterministic, no atomics).
+// tile rows x stages x CTAs per SM (measured per call in the C3 kernel table: 64 x 2 x 1 0.509 ms, 48 x 3 x 1 0.503, 32 x 4 x 1
+// 0.544, 32 x 2 x 2 0.381: two small CTAs per SM overlap each other's TMA wait / split / MMA phases, a deeper ring does not)
 #ifndef WT_ROWS
-#define WT_ROWS 64
+#define WT_ROWS 32
 #define WT_STAGES 2
+#define WT_CTAS 2
 #endif
 namespace wt {
 constexpr int kTileRows = WT_ROWS;
@@ -427,7 +430,7 @@ static_assert(kSmemBytes <= 227 * 1024, "does not fit shared memory");
 static_assert(64 * kScratchPitch * 4 <= kStageBytes, "epilogue scratch lives in stage 0");
 }  // namespace wt
 
-__global__ void __launch_bounds__(wt::kThreads, 1)
+__global__ void __launch_bounds__(wt::kThreads, WT_CTAS)
 weight_grad_tc_kernel(const __grid_constant__ CUtensorMap map_dx, const __grid_constant__ CUtensorMap map_a0,
                       const __grid_constant__ CUtensorMap map_a1, long long rows, float *__restrict__ partial) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -612,7 +615,7 @@ extern "C" int ultra_layer_rows_gemm(const float *dev_a0, int64_t lda0, const fl
 
 extern "C" int ultra_layer_rows_gemm_weight_bytes(size_t *workspace_bytes) {
     if (!workspace_bytes) return ULTRA_RSPMM_ERR_ARG;
-    *workspace_bytes = (size_t)256 * 64 * 128 * sizeof(float);      // one partial result per CTA (at most 256 SMs)
+    *workspace_bytes = (size_t)512 * 64 * 128 * sizeof(float);      // one partial result per CTA (at most 512)
     return ULTRA_RSPMM_OK;
 }
 
@@ -628,12 +631,14 @@ extern "C" int ultra_layer_rows_gemm_weight(const float *dev_dx, int64_t ld_dx, 
     ULTRA_CUDA_OK(cudaGetDevice(&device));
     ULTRA_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     const long long n_tiles = (rows + wg::kTileRows - 1) / wg::kTileRows;
-    int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
-    if (grid > 256) grid = 256;
+    static const bool legacy = getenv("ULTRA_WEIGHT_GRAD") && !strcmp(getenv("ULTRA_WEIGHT_GRAD"), "mma");
+    const long long n_tiles_tc = (rows + wt::kTileRows - 1) / wt::kTileRows;
+    int grid = legacy || rows == 0 ? (int)(n_tiles < sm_count ? n_tiles : sm_count)
+                                   : (int)(n_tiles_tc < (long long)WT_CTAS * sm_count ? n_tiles_tc : (long long)WT_CTAS * sm_count);
+    if (grid > 512) grid = 512;
     if (grid < 1) grid = 1;
     if (!workspace || workspace_bytes < (size_t)grid * 64 * 128 * sizeof(float)) return ULTRA_RSPMM_ERR_WORKSPACE;
     // ULTRA_WEIGHT_GRAD=mma keeps the mma.sync kernel (the first version: bound by the legacy tensor pipe at 3.5 TB/s)
-    static const bool legacy = getenv("ULTRA_WEIGHT_GRAD") && !strcmp(getenv("ULTRA_WEIGHT_GRAD"), "mma");
     if (legacy || rows == 0) {
         ULTRA_CUDA_OK(cudaFuncSetAttribute(weight_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::kSmemBytes));
         weight_grad_kernel<<<grid, wg::kThreads, wg::kSmemBytes, s>>>(dev_dx, ld_dx, dev_a0, lda0, dev_a1, lda1, rows, (float *)workspace);
