@@ -9,6 +9,18 @@ semantics mirror torchdrug's `layers/functional/spmm.py` (un-vendored; SURVEY.md
 
 Everything below the Python argument checks runs in `libultra_rspmm.so` (hand-written sm_100a kernels
 behind the C ABI of `include/ultra_rspmm.h`).  There is no CPU path: CPU tensors raise.
+
+Beyond the drop-in operator, what the layers of `nbf.py` call:
+
+    GraphIndex / graph_index / attach_index      the cached index of one edge set (forward, forward_blocked, forward_pna,
+                                                 backward(input_addend=...), derive(new weights))
+    rspmm_add_boundary / rspmm_add_one_hot       operator + boundary condition in one differentiable node
+    rspmm_pna                                    the four PNA aggregates in one pass (inference)
+    layer_norm_relu_residual                     bias + LayerNorm + ReLU + short-cut, fused forward and backward
+    combine_linear                               Linear over [input | update] without the cat, tensor cores at fp32 accuracy
+    nbf_layer                                    one whole NBFNet layer (sum aggregation) as ONE autograd node (training)
+    linear_norm_relu_residual_into / _two        the whole `combine` as one kernel (inference)
+    score_head_linear / score_head               the scoring MLP without cat([hidden, query])
 """
 import collections
 import ctypes
